@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py -- LPSR plate crops/sec on synthetic 3x64x192 crops (BASELINE.json metric), one process per GPU.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...        # the reference arithmetic on the box's host cores (torch CPU port)
+
+A step = one LPSR forward over one batch of B synthetic crops per GPU (weak scaling: per-GPU batch fixed, the path
+shards by batch with no data-path collective).  `value` = crops/s with inputs resident in HBM; `e2e` = the
+same metric through the C-ABI host-buffer call (lpsr_forward_host: pinned H2D + forward + D2H inside the timed region).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "lpsr_plate_crops_per_sec"
+UNIT = "crops/s"
+DENSE_FLOP_PER_PIXEL = 297_104          # dense-conv FLOPs per pixel (roofline numerator, whole forward)
+# MACs per pixel of the layers the tensor-core kernel executes (K x N per layer, SURVEY 8a GEMM view)
+UMMA_MAC_PER_PIXEL = {
+    "rdn.shallowF2": 288 * 32, "rdn.gff0": 128 * 32, "rdn.gff1": 288 * 32,
+    "rdb0": (288 + 432 + 576 + 720) * 16 + 96 * 32, "rdb2": (288 + 432 + 576 + 720) * 16 + 96 * 32,
+    "csar1": 2 * 288 * 32, "csar3": 2 * 288 * 32,
+}
+CSAR_TAIL_ELEMS_PER_PIXEL = 96          # read x_in + read x + write out, 32 ch each
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def load_shipped_weights():
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "weights_best_model.npz")))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference arithmetic (torch CPU ops, fp32) on the box's host cores
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(args, steps, warmup, sample_b, budget_s=None):
+    from oracle import lpsr_torch_port as port   # bench.py's cpu_baseline / reference leg may execute oracle/
+
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(cores)
+    W = port.to_torch_weights(load_shipped_weights())
+    x = torch.rand(sample_b, 3, args.height, args.width, generator=torch.Generator().manual_seed(0))
+    for _ in range(warmup):
+        port.lpsr_forward(x, W)
+    times = []
+    t_start = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        port.lpsr_forward(x, W)
+        times.append(time.perf_counter() - t0)
+        if budget_s is not None and time.perf_counter() - t_start > budget_s:
+            break
+    total = sum(times)
+    return {"value": sample_b * len(times) / total, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{len(times)} steps x {sample_b} crops of 3x{args.height}x{args.width} fp32, torch {torch.__version__} "
+                      f"CPU ops in the reference's op order (oracle/lpsr_torch_port.py), {cores} threads",
+            "ms_per_step": 1e3 * total / len(times), "steps": len(times)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_b = 16
+    r = cpu_reference_run(args, args.steps, args.warmup, sample_b)
+    line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "reference",
+            "config": workload_config(args, sample_b, "fp32", note="CPU sample of the same workload"),
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, batch, precision, note=None):
+    cfg = {"workload": f"LPSR forward {precision}, batch {batch} of 3x{args.height}x{args.width} synthetic crops per GPU "
+                       f"(BASELINE.json configs[2])", "per_gpu_batch": batch, "global_batch": batch * args.gpus,
+           "crop": [3, args.height, args.width], "precision": precision, "weights": "reference best_model.pth (fixture)",
+           "parallelism": f"batch-sharded x{args.gpus}, replicated weights, no per-layer collective",
+           "l2": "inputs (151 MB/step at B=1024) and activations (GBs) exceed the 126 MB L2; no explicit flush"}
+    if note:
+        cfg["note"] = note
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+
+    import lpsr_b200
+    from lpsr_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B, H, Wd = args.batch, args.height, args.width
+
+    model = lpsr_b200.LPSR(3, 32, 16, 4, 4, None, precision=args.precision)
+    model.load_live_weights(load_shipped_weights())
+    model = model.to(dev).eval()
+    g = torch.Generator().manual_seed(1000 + rank)
+    x_host = torch.rand(B, 3, H, Wd, generator=g).pin_memory()
+    x = x_host.to(dev)
+    launches = model.launch_count(B, H, Wd)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident throughput -------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        y = model(x)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        y = model(x)
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop()
+    ms_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---------------- per-kernel device times (CUDA events between launches, same stream) --------------------------
+    lib = capi.load_library()
+    h = model._handle(dev)
+    ws = model._workspace(h, local, B, H, Wd)
+    cap = 64
+    fam_ms, n_prof = {}, min(args.steps, 5)
+    names = []
+    for _ in range(n_prof):
+        ms = (C.c_float * cap)()
+        nm = C.create_string_buffer(cap * 64)
+        n = lib.lpsr_forward_profiled(h, x.data_ptr(), y.data_ptr(), B, H, Wd, model._aligned_ptr(ws),
+                                      ws.numel() - (model._aligned_ptr(ws) - ws.data_ptr()),
+                                      torch.cuda.current_stream(dev).cuda_stream, ms, nm, 64, cap)
+        capi.check(min(n, 0), h, "lpsr_forward_profiled")
+        names = [nm.raw[i * 64:(i + 1) * 64].split(b"\0")[0].decode() for i in range(n)]
+        for i, name in enumerate(names):
+            fam_ms[name] = fam_ms.get(name, 0.0) + ms[i] / n_prof
+    pk = peaks()
+    P = ((H + 3) // 4 * 4) * ((Wd + 3) // 4 * 4)
+    per_kernel = {}
+    for name, t in fam_ms.items():
+        kind = name.split(":")[1]
+        per_kernel.setdefault(kind, [0.0, 0])
+        per_kernel[kind][0] += t
+        per_kernel[kind][1] += names.count(name) if names.count(name) else 1
+    umma_ms = sum(t for n_, t in fam_ms.items() if n_.endswith(":umma_conv"))
+    umma_flops = 2.0 * B * P * sum(v for k, v in UMMA_MAC_PER_PIXEL.items())
+    n_umma = sum(1 for n_ in names if n_.endswith(":umma_conv"))
+    esz = 4 if args.precision == "fp32" else 2
+    tail_ms = sum(t for n_, t in fam_ms.items() if n_.endswith(":csar_tail"))
+    tail_bytes = 2.0 * B * P * CSAR_TAIL_ELEMS_PER_PIXEL * esz
+    total_prof_ms = sum(fam_ms.values())
+    if n_umma:
+        ach = umma_flops / (umma_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": f"umma_conv_kernel (tcgen05 implicit-GEMM conv, {n_umma} launches/forward)",
+                    "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
+                    "peak_kind": f"bf16 dense sustained, of {pk['src']}", "traffic": None,
+                    "algorithmic_flops_per_forward": umma_flops, "kernel_ms_per_forward": umma_ms,
+                    "share_of_step": umma_ms / total_prof_ms}
+    else:   # fp32 mode: FFMA direct convolution dominates; still reported against the bf16 tensor peak
+        d_ms = sum(t for n_, t in fam_ms.items() if n_.endswith(":conv_direct"))
+        fl = 2.0 * B * P * (DENSE_FLOP_PER_PIXEL / 2 - 12288)
+        ach = fl / (d_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "conv_direct_kernel (FFMA, fp32 parity mode)", "achieved": ach, "peak": pk["tf_sustained"],
+                    "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"], "peak_kind": f"bf16 dense sustained, of {pk['src']}",
+                    "traffic": None, "share_of_step": d_ms / total_prof_ms}
+    roofline_csar = {"bound": "hbm", "kernel": "csar_tail_kernel (2 launches/forward)", "achieved": tail_bytes / (tail_ms * 1e-3) / 1e9,
+                     "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": tail_bytes / (tail_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                     "peak_kind": f"copy bandwidth, of {pk['src']}", "traffic": None, "kernel_ms_per_forward": tail_ms}
+    conv_frac_whole = value / world * P * DENSE_FLOP_PER_PIXEL / 1e12 / pk["tf_sustained"]
+
+    # ---------------- end to end through the C-ABI host-buffer call --------------------------------------------------
+    y_host = torch.empty((B, 1, (H + 3) // 4 * 4, (Wd + 3) // 4 * 4), dtype=torch.float32).pin_memory()
+    for _ in range(2):
+        model.forward_host(x_host, out=y_host, device=local)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        model.forward_host(x_host, out=y_host, device=local)
+    torch.cuda.synchronize(dev)
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e = {"value": world * B * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
+           "d2h_bytes_per_step": y_host.numel() * 4, "ms_per_step": 1e3 * e2e_s / args.steps,
+           "api": "LPSR.forward_host -> lpsr_forward_host (C ABI, pinned host buffers)"}
+    checksum = float(y_host.double().mean())
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base = cpu_reference_run(args, steps=1000, warmup=1, sample_b=16, budget_s=args.cpu_budget)
+        cpu_base = {k: cpu_base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[args.precision], "data": "synthetic",
+                "config": workload_config(args, B, args.precision), "clocks": clocks, "e2e": e2e, "gpu_launches": launches * args.steps,
+                "launches_per_step": launches, "roofline": roofline, "roofline_csar": roofline_csar,
+                "conv_roofline_frac_whole_forward": conv_frac_whole,
+                "kernel_ms_per_forward": {k: round(v[0], 4) for k, v in per_kernel.items()},
+                "layer_ms_per_forward": {k: round(v, 4) for k, v in fam_ms.items()},
+                "cpu_baseline": cpu_base, "output_mean": checksum, "umma": os.environ.get("LPSR_UMMA", "1")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("LPSR_BENCH_PRECISION", "bf16"), choices=["bf16", "fp16", "fp32"])
+    ap.add_argument("--batch", type=int, default=1024, help="crops per GPU per step")
+    ap.add_argument("--height", type=int, default=64)
+    ap.add_argument("--width", type=int, default=192)
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        import __graft_entry__ as ge
+        if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+            ge.build()
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

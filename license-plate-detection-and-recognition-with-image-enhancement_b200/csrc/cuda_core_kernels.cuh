@@ -1,0 +1,397 @@
+// cuda_core_kernels.cuh -- the CUDA-core (FFMA) kernels of the LPSR forward.
+//
+//   conv_direct_kernel   : kxk convolution, zero 'same' padding, NHWC, fp32 accumulate. In fp32 mode it runs
+//                          every dense conv; in the 16-bit modes it runs only the layers that are not GEMM-shaped
+//                          (Cin=3 / Cout<=3 / Cout=1: AutoEncoder conv_in/conv_out, shallowF1 7x7, final conv).
+//   dconv_fused_kernel   : DConv (depthwise 5x5 + pointwise 1x1, lpsr.py:8-28) with the following
+//                          PixelUnshuffle/PixelShuffle + ReLU folded into the store address map (lpsr.py:71-96).
+//   gap_partial_kernel   : per-slice channel sums feeding AdaptiveAvgPool2d(1) (lpsr.py:124).
+//   csar_tail_kernel     : channel gate MLP + spatial gate MLP + gating + conv_out + residual (lpsr.py:180-186).
+//   layout kernels       : NCHW<->NHWC and the standalone pixel (un)shuffle used by the op-level tests.
+#pragma once
+#include "common.cuh"
+
+namespace lpsr {
+
+// ---------------------------------------------------------------------------------------------------
+// direct convolution
+// ---------------------------------------------------------------------------------------------------
+template <typename T, int KS, int CCH, int COUT, bool IN_NCHW, bool OUT_SIG>
+__global__ void __launch_bounds__(kThreads) conv_direct_kernel(const ConvParams p) {
+  constexpr int R = KS / 2;
+  constexpr int SH = kTileH + KS - 1, SW = kTileW + KS - 1;
+  constexpr int PLANE = (SH * SW) | 1;  // odd plane stride: conflict-free channel-transposed stores
+  __shared__ float s_in[CCH * PLANE];
+  __shared__ __align__(16) float s_w[KS * KS * CCH * COUT];
+
+  const int tid = threadIdx.x;
+  const int tx = tid % kTileW, ty = tid / kTileW;
+  const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH, n = blockIdx.z;
+  const int Cin = p.n_chunks * CCH;
+
+  float acc[COUT];
+#pragma unroll
+  for (int co = 0; co < COUT; ++co) acc[co] = p.bias ? __ldg(p.bias + co) : 0.f;
+
+  for (int ch = 0; ch < p.n_chunks; ++ch) {
+    __syncthreads();
+    // ---- stage the input halo tile for this channel chunk (zero outside the image = 'same' padding)
+    if constexpr (IN_NCHW) {
+      const float* src = static_cast<const float*>(p.in);
+      for (int i = tid; i < CCH * SH * SW; i += kThreads) {
+        const int c = i / (SH * SW), r = i % (SH * SW);
+        const int yy = y0 + r / SW - R, xx = x0 + r % SW - R;
+        float v = 0.f;
+        if (yy >= 0 && yy < p.inH && xx >= 0 && xx < p.inW)
+          v = __ldg(src + (((size_t)n * Cin + (p.chunk_off[ch] + c)) * p.inH + yy) * p.inW + xx);
+        s_in[c * PLANE + r] = v;
+      }
+    } else {
+      const T* src = static_cast<const T*>(p.in);
+      const int coff = p.chunk_off[ch];
+      for (int i = tid; i < CCH * SH * SW; i += kThreads) {
+        const int r = i / CCH, c = i % CCH;
+        const int yy = y0 + r / SW - R, xx = x0 + r % SW - R;
+        float v = 0.f;
+        if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W)
+          v = to_f32<T>(src[((size_t)(n * p.H + yy) * p.W + xx) * p.in_pitch + coff + c]);
+        s_in[c * PLANE + r] = v;
+      }
+    }
+    for (int i = tid; i < KS * KS * CCH * COUT; i += kThreads) {
+      const int tap = i / (CCH * COUT), rem = i % (CCH * COUT);
+      s_w[i] = __ldg(p.w + ((size_t)tap * Cin + ch * CCH) * COUT + rem);
+    }
+    __syncthreads();
+    // ---- accumulate
+#pragma unroll 1
+    for (int dy = 0; dy < KS; ++dy) {
+#pragma unroll
+      for (int dx = 0; dx < KS; ++dx) {
+        const float* a_ptr = s_in + (ty + dy) * SW + tx + dx;
+        const float* w_ptr = s_w + (dy * KS + dx) * CCH * COUT;
+#pragma unroll
+        for (int c = 0; c < CCH; ++c) {
+          const float a = a_ptr[c * PLANE];
+          if constexpr (COUT % 4 == 0) {
+#pragma unroll
+            for (int q = 0; q < COUT / 4; ++q) {
+              const float4 w4 = *reinterpret_cast<const float4*>(w_ptr + c * COUT + q * 4);
+              acc[q * 4 + 0] = fmaf(a, w4.x, acc[q * 4 + 0]);
+              acc[q * 4 + 1] = fmaf(a, w4.y, acc[q * 4 + 1]);
+              acc[q * 4 + 2] = fmaf(a, w4.z, acc[q * 4 + 2]);
+              acc[q * 4 + 3] = fmaf(a, w4.w, acc[q * 4 + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) acc[co] = fmaf(a, w_ptr[c * COUT + co], acc[co]);
+          }
+        }
+      }
+    }
+  }
+
+  const int y = y0 + ty, x = x0 + tx;
+  if (y >= p.H || x >= p.W) return;
+  const size_t pix = (size_t)(n * p.H + y) * p.W + x;
+  if (p.relu) {
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) acc[co] = fmaxf(acc[co], 0.f);
+  }
+  if constexpr (OUT_SIG) {
+    float* out = static_cast<float*>(p.out);  // NCHW fp32, sigmoid fused (lpsr.py:274)
+#pragma unroll
+    for (int co = 0; co < COUT; ++co)
+      out[(((size_t)n * COUT + co) * p.H + y) * p.W + x] = sigmoid_f32(acc[co]);
+  } else {
+    if (p.res) {
+      const T* res = static_cast<const T*>(p.res) + pix * p.res_pitch + p.res_off;
+      if constexpr ((COUT * sizeof(T)) % 16 == 0) {
+        float r[COUT];
+        load_vec<T, COUT>(res, r);
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) acc[co] += r[co];
+      } else {
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) acc[co] += to_f32<T>(res[co]);
+      }
+    }
+    T* out = static_cast<T*>(p.out) + pix * p.out_pitch + p.out_off;
+    if constexpr ((COUT * sizeof(T)) % 16 == 0) {
+      store_vec<T, COUT>(out, acc);
+    } else {
+#pragma unroll
+      for (int co = 0; co < COUT; ++co) out[co] = from_f32<T>(acc[co]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// DConv + pixel (un)shuffle + ReLU (+ skip add)
+// ---------------------------------------------------------------------------------------------------
+enum { kShuffleDown = 0, kShuffleUp = 1 };
+
+template <typename T, int CIN, int COUT, int MODE, bool ADD_RES>
+__global__ void __launch_bounds__(kThreads) dconv_fused_kernel(const DConvParams p) {
+  constexpr int KS = 5, R = 2, CCH = 12;
+  static_assert(CIN % CCH == 0, "AutoEncoder widths are multiples of 12");
+  constexpr int SH = kTileH + KS - 1, SW = kTileW + KS - 1;
+  constexpr int PLANE = (SH * SW) | 1;
+  __shared__ float s_in[CCH * PLANE];
+  __shared__ float s_dw[CIN * 26];               // 25 taps + bias per channel
+  __shared__ __align__(16) float s_pw[CIN * COUT];
+
+  const int tid = threadIdx.x;
+  const int tx = tid % kTileW, ty = tid / kTileW;
+  const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH, n = blockIdx.z;
+
+  for (int i = tid; i < CIN * 26; i += kThreads) {
+    const int c = i / 26, t = i % 26;
+    s_dw[i] = (t < 25) ? __ldg(p.dw_w + c * 25 + t) : __ldg(p.dw_b + c);
+  }
+  for (int i = tid; i < CIN * COUT; i += kThreads) s_pw[i] = __ldg(p.pw_w + i);
+
+  float acc[COUT];
+#pragma unroll
+  for (int co = 0; co < COUT; ++co) acc[co] = __ldg(p.pw_b + co);
+
+  const T* src = static_cast<const T*>(p.in);
+  for (int ch = 0; ch < CIN / CCH; ++ch) {
+    __syncthreads();
+    for (int i = tid; i < CCH * SH * SW; i += kThreads) {
+      const int r = i / CCH, c = i % CCH;
+      const int yy = y0 + r / SW - R, xx = x0 + r % SW - R;
+      float v = 0.f;
+      if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W)
+        v = to_f32<T>(src[((size_t)(n * p.H + yy) * p.W + xx) * p.in_pitch + p.in_off + ch * CCH + c]);
+      s_in[c * PLANE + r] = v;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int c = 0; c < CCH; ++c) {
+      const float* a_ptr = s_in + c * PLANE + ty * SW + tx;
+      const float* w = s_dw + (ch * CCH + c) * 26;
+      float d = w[25];
+#pragma unroll
+      for (int dy = 0; dy < KS; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < KS; ++dx) d = fmaf(a_ptr[dy * SW + dx], w[dy * KS + dx], d);
+      const float* pw = s_pw + (ch * CCH + c) * COUT;
+#pragma unroll
+      for (int q = 0; q < COUT / 4; ++q) {
+        const float4 w4 = *reinterpret_cast<const float4*>(pw + q * 4);
+        acc[q * 4 + 0] = fmaf(d, w4.x, acc[q * 4 + 0]);
+        acc[q * 4 + 1] = fmaf(d, w4.y, acc[q * 4 + 1]);
+        acc[q * 4 + 2] = fmaf(d, w4.z, acc[q * 4 + 2]);
+        acc[q * 4 + 3] = fmaf(d, w4.w, acc[q * 4 + 3]);
+      }
+    }
+  }
+
+  const int y = y0 + ty, x = x0 + tx;
+  if (y >= p.H || x >= p.W) return;
+  T* out = static_cast<T*>(p.out);
+  const T* res = static_cast<const T*>(p.res);
+#pragma unroll
+  for (int co = 0; co < COUT; ++co) {
+    float v = fmaxf(acc[co], 0.f);  // ReLU commutes with the index remap (lpsr.py:73,80,89,96)
+    size_t dst;
+    if constexpr (MODE == kShuffleDown) dst = unshuffle2_dst(n, y, x, co, p.H, p.W, p.out_pitch, p.out_off);
+    else                                dst = shuffle2_dst(n, y, x, co, p.H, p.W, p.out_pitch, p.out_off);
+    if constexpr (ADD_RES) {
+      // res has the same geometry as the (shuffled) output; only pitch/offset may differ
+      size_t rdst;
+      if constexpr (MODE == kShuffleDown) rdst = unshuffle2_dst(n, y, x, co, p.H, p.W, p.res_pitch, p.res_off);
+      else                                rdst = shuffle2_dst(n, y, x, co, p.H, p.W, p.res_pitch, p.res_off);
+      v += to_f32<T>(res[rdst]);
+    }
+    out[dst] = from_f32<T>(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// global-average-pool partial sums: partial[b][s][c] = sum over slice s of crop b
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads) gap_partial_kernel(const T* __restrict__ x, int pitch, int off,
+                                                               int P, int S, float* __restrict__ partial) {
+  __shared__ float s_red[kThreads];
+  const int s = blockIdx.x, b = blockIdx.y;
+  const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int p0 = (int)(((long long)s * P) / S), p1 = (int)(((long long)(s + 1) * P) / S);
+  const T* base = x + (size_t)b * P * pitch + off + c;
+  float sum = 0.f;
+  for (int pix = p0 + g; pix < p1; pix += kThreads / 32) sum += to_f32<T>(base[(size_t)pix * pitch]);
+  s_red[threadIdx.x] = sum;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < kThreads / 32; ++k) t += s_red[k * 32 + c];
+    partial[((size_t)b * S + s) * 32 + c] = t;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// CSAR tail (CUDA-core version; fp32 math).  One thread per pixel, grid = (ceil(P/256), B).
+//   s_c = sigmoid(W2 relu(W1 mean(x_in) + b1) + b2)                       (ChannelAttention, lpsr.py:120-135)
+//   s_s = sigmoid(W4 relu(W3 x_in + b3) + b4)  per pixel                   (SpatialAttention, lpsr.py:138-153)
+//   out = x + Wo [x_in^2 * s_c ; x_in * s_s] + bo                          (CSAR.forward, lpsr.py:182-186)
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads) csar_tail_kernel(const TailParams p) {
+  constexpr int F = 32, F2 = 64, HID = 8;
+  __shared__ __align__(16) float s_w3[F * F2];
+  __shared__ __align__(16) float s_w4[F2 * F];
+  __shared__ __align__(16) float s_wo[F2 * F];
+  __shared__ float s_b3[F2], s_b4[F], s_bo[F], s_mean[F], s_hid[HID], s_sc[F];
+  const int tid = threadIdx.x, b = blockIdx.y;
+  for (int i = tid; i < F * F2; i += kThreads) {
+    s_w3[i] = __ldg(p.sa_w1 + i);
+    s_w4[i] = __ldg(p.sa_w2 + i);
+    s_wo[i] = __ldg(p.co_w + i);
+  }
+  if (tid < F2) s_b3[tid] = __ldg(p.sa_b1 + tid);
+  if (tid < F) {
+    s_b4[tid] = __ldg(p.sa_b2 + tid);
+    s_bo[tid] = __ldg(p.co_b + tid);
+    float t = 0.f;
+    for (int s = 0; s < p.S; ++s) t += p.pool_partial[((size_t)b * p.S + s) * F + tid];
+    s_mean[tid] = t / (float)p.P;
+  }
+  __syncthreads();
+  if (tid < HID) {
+    float t = __ldg(p.ca_b1 + tid);
+    for (int c = 0; c < F; ++c) t = fmaf(s_mean[c], __ldg(p.ca_w1 + tid * F + c), t);
+    s_hid[tid] = fmaxf(t, 0.f);
+  }
+  __syncthreads();
+  if (tid < F) {
+    float t = __ldg(p.ca_b2 + tid);
+    for (int j = 0; j < HID; ++j) t = fmaf(s_hid[j], __ldg(p.ca_w2 + tid * HID + j), t);
+    s_sc[tid] = sigmoid_f32(t);
+  }
+  __syncthreads();
+
+  const int pix = blockIdx.x * kThreads + tid;
+  if (pix >= p.P) return;
+  const size_t gp = (size_t)b * p.P + pix;
+
+  float xin[F];
+  load_vec<T, F>(static_cast<const T*>(p.x_in) + gp * p.xin_pitch + p.xin_off, xin);
+
+  float acc[F];
+#pragma unroll
+  for (int c = 0; c < F; ++c) acc[c] = s_bo[c];
+  // channel branch: x_in * (x_in * s_c)  -- the reference squares x_in
+#pragma unroll
+  for (int c = 0; c < F; ++c) {
+    const float g1 = xin[c] * (xin[c] * s_sc[c]);
+    const float4* w = reinterpret_cast<const float4*>(s_wo + c * F);
+#pragma unroll
+    for (int q = 0; q < F / 4; ++q) {
+      const float4 w4 = w[q];
+      acc[q * 4 + 0] = fmaf(g1, w4.x, acc[q * 4 + 0]);
+      acc[q * 4 + 1] = fmaf(g1, w4.y, acc[q * 4 + 1]);
+      acc[q * 4 + 2] = fmaf(g1, w4.z, acc[q * 4 + 2]);
+      acc[q * 4 + 3] = fmaf(g1, w4.w, acc[q * 4 + 3]);
+    }
+  }
+  // spatial branch: 32 -> 64 (ReLU) -> 32 (sigmoid), hidden processed 16 at a time to bound registers
+  float sp[F];
+#pragma unroll
+  for (int c = 0; c < F; ++c) sp[c] = s_b4[c];
+#pragma unroll 1
+  for (int hc = 0; hc < F2 / 16; ++hc) {
+    float hid[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) hid[j] = s_b3[hc * 16 + j];
+#pragma unroll
+    for (int c = 0; c < F; ++c) {
+      const float4* w = reinterpret_cast<const float4*>(s_w3 + c * F2 + hc * 16);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 w4 = w[q];
+        hid[q * 4 + 0] = fmaf(xin[c], w4.x, hid[q * 4 + 0]);
+        hid[q * 4 + 1] = fmaf(xin[c], w4.y, hid[q * 4 + 1]);
+        hid[q * 4 + 2] = fmaf(xin[c], w4.z, hid[q * 4 + 2]);
+        hid[q * 4 + 3] = fmaf(xin[c], w4.w, hid[q * 4 + 3]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float hv = fmaxf(hid[j], 0.f);
+      const float4* w = reinterpret_cast<const float4*>(s_w4 + (hc * 16 + j) * F);
+#pragma unroll
+      for (int q = 0; q < F / 4; ++q) {
+        const float4 w4 = w[q];
+        sp[q * 4 + 0] = fmaf(hv, w4.x, sp[q * 4 + 0]);
+        sp[q * 4 + 1] = fmaf(hv, w4.y, sp[q * 4 + 1]);
+        sp[q * 4 + 2] = fmaf(hv, w4.z, sp[q * 4 + 2]);
+        sp[q * 4 + 3] = fmaf(hv, w4.w, sp[q * 4 + 3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < F; ++c) {
+    const float g2 = xin[c] * sigmoid_f32(sp[c]);
+    const float4* w = reinterpret_cast<const float4*>(s_wo + (F + c) * F);
+#pragma unroll
+    for (int q = 0; q < F / 4; ++q) {
+      const float4 w4 = w[q];
+      acc[q * 4 + 0] = fmaf(g2, w4.x, acc[q * 4 + 0]);
+      acc[q * 4 + 1] = fmaf(g2, w4.y, acc[q * 4 + 1]);
+      acc[q * 4 + 2] = fmaf(g2, w4.z, acc[q * 4 + 2]);
+      acc[q * 4 + 3] = fmaf(g2, w4.w, acc[q * 4 + 3]);
+    }
+  }
+  float r[F];
+  load_vec<T, F>(static_cast<const T*>(p.res) + gp * p.res_pitch + p.res_off, r);
+#pragma unroll
+  for (int c = 0; c < F; ++c) acc[c] += r[c];
+  store_vec<T, F>(static_cast<T*>(p.out) + gp * p.out_pitch + p.out_off, acc);
+  if (p.out2) store_vec<T, F>(static_cast<T*>(p.out2) + gp * p.out2_pitch + p.out2_off, acc);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// layout helpers (tests / op-level entry points / debug taps)
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int B, int C, int H, int W,
+                                    int pitch, int off) {
+  const size_t total = (size_t)B * C * H * W;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const size_t pix = i / C;                       // (n*H + y)*W + x
+    const int x = (int)(pix % W), y = (int)((pix / W) % H), n = (int)(pix / ((size_t)W * H));
+    dst[pix * pitch + off + c] = from_f32<T>(src[(((size_t)n * C + c) * H + y) * W + x]);
+  }
+}
+
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int B, int C, int H, int W,
+                                    int pitch, int off) {
+  const size_t total = (size_t)B * C * H * W;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W), y = (int)((i / W) % H), c = (int)((i / ((size_t)W * H)) % C);
+    const int n = (int)(i / ((size_t)W * H * C));
+    dst[i] = to_f32<T>(src[((size_t)(n * H + y) * W + x) * pitch + off + c]);
+  }
+}
+
+// standalone remap kernels: NHWC fp32 -> NHWC fp32 through the SAME address maps the fused kernels use
+template <int MODE>
+__global__ void pixel_remap_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C, int H, int W) {
+  const size_t total = (size_t)B * C * H * W;
+  const int out_pitch = (MODE == kShuffleDown) ? C * 4 : C / 4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const size_t pix = i / C;
+    const int x = (int)(pix % W), y = (int)((pix / W) % H), n = (int)(pix / ((size_t)W * H));
+    const size_t d = (MODE == kShuffleDown) ? unshuffle2_dst(n, y, x, c, H, W, out_pitch, 0)
+                                            : shuffle2_dst(n, y, x, c, H, W, out_pitch, 0);
+    dst[d] = src[i];
+  }
+}
+
+}  // namespace lpsr

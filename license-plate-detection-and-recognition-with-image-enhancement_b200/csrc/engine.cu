@@ -1,0 +1,514 @@
+// engine.cu -- host side of the C ABI declared in include/lpsr_b200.h: weight packing, workspace layout,
+// the launch plan of one LPSR forward (reference: my_models/lpsr.py:269-274) and the op-level entry points.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "cuda_core_kernels.cuh"
+#include "engine_internal.h"
+
+using namespace lpsr;
+
+namespace lpsr {
+
+std::mutex g_err_mu;
+char g_err[512] = "";
+
+int fail(lpsr_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h) snprintf(h->err, sizeof h->err, "%s", buf);
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  snprintf(g_err, sizeof g_err, "%s", buf);
+  return code;
+}
+
+}  // namespace lpsr
+
+namespace {
+
+// ---- live tensor table (names = reference state_dict keys; order = ctor order, lpsr.py) --------------
+void add_live(lpsr_handle* h, const std::string& name, int64_t numel) {
+  h->live_index[name] = (int)h->live.size();
+  LiveTensor t;
+  t.name = name;
+  t.numel = numel;
+  h->live.push_back(std::move(t));
+}
+
+void build_live_table(lpsr_handle* h) {
+  const int C = h->cfg.num_channels, F = h->cfg.num_features, G = h->cfg.growth_rate, L = h->cfg.num_layers;
+  const int E = 4 * C, O = h->cfg.out_channels;
+  add_live(h, "auto_encoder.conv_in.weight", (int64_t)E * C * 9);
+  struct { const char* blk; int cin, cout; } dcs[4] = {{"encoder.0", E, E}, {"encoder.3", 4 * E, E}, {"decoder.0", 4 * E, 4 * E}, {"decoder.3", E, 4 * E}};
+  for (auto& d : dcs) {
+    std::string p = std::string("auto_encoder.") + d.blk + ".dConv.";
+    add_live(h, p + "0.weight", (int64_t)d.cin * 25);
+    add_live(h, p + "0.bias", d.cin);
+    add_live(h, p + "1.weight", (int64_t)d.cout * d.cin);
+    add_live(h, p + "1.bias", d.cout);
+  }
+  add_live(h, "auto_encoder.conv_out.weight", (int64_t)C * E * 9);
+  add_live(h, "rdn.shallowF1.weight", (int64_t)F * C * 49);
+  add_live(h, "rdn.shallowF1.bias", F);
+  add_live(h, "rdn.shallowF2.weight", (int64_t)F * F * 9);
+  add_live(h, "rdn.shallowF2.bias", F);
+  add_live(h, "rdn.csar.conv_in.0.weight", (int64_t)F * F * 9);
+  add_live(h, "rdn.csar.conv_in.0.bias", F);
+  add_live(h, "rdn.csar.conv_in.2.weight", (int64_t)F * F * 9);
+  add_live(h, "rdn.csar.conv_in.2.bias", F);
+  add_live(h, "rdn.csar.ca.block.2.weight", (int64_t)(F / 4) * F);
+  add_live(h, "rdn.csar.ca.block.2.bias", F / 4);
+  add_live(h, "rdn.csar.ca.block.4.weight", (int64_t)F * (F / 4));
+  add_live(h, "rdn.csar.ca.block.4.bias", F);
+  add_live(h, "rdn.csar.sa.block.0.weight", (int64_t)2 * F * F);
+  add_live(h, "rdn.csar.sa.block.0.bias", 2 * F);
+  add_live(h, "rdn.csar.sa.block.2.weight", (int64_t)F * 2 * F);
+  add_live(h, "rdn.csar.sa.block.2.bias", F);
+  add_live(h, "rdn.csar.conv_out.weight", (int64_t)F * 2 * F);
+  add_live(h, "rdn.csar.conv_out.bias", F);
+  for (int r = 0; r < h->cfg.num_blocks; r += 2) {   // executed RDBs are the even module indices
+    std::string p = "rdn.rdbs." + std::to_string(r) + ".";
+    add_live(h, p + "alpha", 1);
+    for (int i = 0; i < L; ++i) {
+      add_live(h, p + "layers." + std::to_string(i) + ".conv.weight", (int64_t)G * (F + G * i) * 9);
+      add_live(h, p + "layers." + std::to_string(i) + ".conv.bias", G);
+    }
+    add_live(h, p + "lff.weight", (int64_t)F * (F + G * L));
+    add_live(h, p + "lff.bias", F);
+  }
+  add_live(h, "rdn.gff.0.weight", (int64_t)F * F * h->cfg.num_blocks);
+  add_live(h, "rdn.gff.0.bias", F);
+  add_live(h, "rdn.gff.1.weight", (int64_t)F * F * 9);
+  add_live(h, "rdn.gff.1.bias", F);
+  add_live(h, "final_conv.weight", (int64_t)O * F * 9);
+  add_live(h, "final_conv.bias", O);
+}
+
+const std::vector<float>& W(const lpsr_handle* h, const std::string& name) {
+  return h->live[h->live_index.at(name)].host;
+}
+
+// ---- device arena ------------------------------------------------------------------------------------
+template <typename U>
+U* arena_put(lpsr_handle* h, const std::vector<U>& v) {
+  DeviceArena& a = h->arena;
+  a.used = align_up(a.used, 256);
+  const size_t bytes = v.size() * sizeof(U);
+  if (a.used + bytes > a.cap) return nullptr;
+  U* p = reinterpret_cast<U*>(static_cast<char*>(a.base) + a.used);
+  if (cudaMemcpy(p, v.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+  a.used += bytes;
+  return p;
+}
+
+// conv weight OIHW -> [ks*ks][cin][cout], optional scale (alpha fold, lpsr.py:58-61)
+bool pack_conv(lpsr_handle* h, ConvW& cw, const std::string& prefix, int cin, int cout, int ks, bool bias, float scale = 1.f) {
+  const std::vector<float>& w = W(h, prefix + ".weight");
+  std::vector<float> pw((size_t)ks * ks * cin * cout);
+  for (int co = 0; co < cout; ++co)
+    for (int ci = 0; ci < cin; ++ci)
+      for (int t = 0; t < ks * ks; ++t)
+        pw[((size_t)t * cin + ci) * cout + co] = scale * w[((size_t)co * cin + ci) * ks * ks + t];
+  cw.ks = ks; cw.cin = cin; cw.cout = cout;
+  cw.w = arena_put(h, pw);
+  if (!cw.w) return false;
+  std::vector<float> pb;
+  if (bias) {
+    pb = W(h, prefix + ".bias");
+    for (auto& v : pb) v *= scale;
+    cw.b = arena_put(h, pb);
+    if (!cw.b) return false;
+  } else {
+    cw.b = nullptr;
+  }
+  if (half_mode(h) && umma_supported(ks, cin, cout)) {
+    if (!umma_pack_weights(cw.u, pw.data(), bias ? pb.data() : nullptr, ks, cin, cout,
+                           h->cfg.precision == LPSR_PREC_FP16, [&](const std::vector<uint16_t>& v) { return arena_put(h, v); },
+                           [&](const std::vector<float>& v) { return arena_put(h, v); }))
+      return false;
+  }
+  return true;
+}
+
+int pack_all(lpsr_handle* h) {
+  const int C = h->cfg.num_channels, F = h->cfg.num_features, G = h->cfg.growth_rate, L = h->cfg.num_layers, E = 4 * C;
+  if (!h->arena.base) {
+    h->arena.cap = 8u << 20;
+    CUDA_TRY(h, cudaMalloc(&h->arena.base, h->arena.cap));
+  }
+  h->arena.used = 0;
+  bool ok = true;
+  ok &= pack_conv(h, h->ae_in, "auto_encoder.conv_in", C, E, 3, false);
+  ok &= pack_conv(h, h->ae_out, "auto_encoder.conv_out", E, C, 3, false);
+  const char* blks[4] = {"encoder.0", "encoder.3", "decoder.0", "decoder.3"};
+  const int dcin[4] = {E, 4 * E, 4 * E, E}, dcout[4] = {E, E, 4 * E, 4 * E};
+  for (int i = 0; i < 4; ++i) {
+    std::string p = std::string("auto_encoder.") + blks[i] + ".dConv.";
+    DConvW& d = h->dc[i];
+    d.cin = dcin[i]; d.cout = dcout[i];
+    d.dw_w = arena_put(h, W(h, p + "0.weight"));      // [cin][1][5][5] == [cin][25]
+    d.dw_b = arena_put(h, W(h, p + "0.bias"));
+    const std::vector<float>& pw = W(h, p + "1.weight");  // [cout][cin] -> [cin][cout]
+    std::vector<float> t((size_t)d.cin * d.cout);
+    for (int co = 0; co < d.cout; ++co)
+      for (int ci = 0; ci < d.cin; ++ci) t[(size_t)ci * d.cout + co] = pw[(size_t)co * d.cin + ci];
+    d.pw_w = arena_put(h, t);
+    d.pw_b = arena_put(h, W(h, p + "1.bias"));
+    ok &= d.dw_w && d.dw_b && d.pw_w && d.pw_b;
+  }
+  ok &= pack_conv(h, h->sfe1, "rdn.shallowF1", C, F, 7, true);
+  ok &= pack_conv(h, h->sfe2, "rdn.shallowF2", F, F, 3, true);
+  for (int r = 0; r < 2; ++r) {
+    std::string p = "rdn.rdbs." + std::to_string(2 * r);
+    const float alpha = W(h, p + ".alpha")[0];
+    for (int i = 0; i < L; ++i) ok &= pack_conv(h, h->rdb[r][i], p + ".layers." + std::to_string(i) + ".conv", F + G * i, G, 3, true);
+    ok &= pack_conv(h, h->lff[r], p + ".lff", F + G * L, F, 1, true, alpha);
+  }
+  ok &= pack_conv(h, h->csar_c1, "rdn.csar.conv_in.0", F, F, 3, true);
+  ok &= pack_conv(h, h->csar_c2, "rdn.csar.conv_in.2", F, F, 3, true);
+  h->ca_w1 = arena_put(h, W(h, "rdn.csar.ca.block.2.weight"));
+  h->ca_b1 = arena_put(h, W(h, "rdn.csar.ca.block.2.bias"));
+  h->ca_w2 = arena_put(h, W(h, "rdn.csar.ca.block.4.weight"));
+  h->ca_b2 = arena_put(h, W(h, "rdn.csar.ca.block.4.bias"));
+  auto transpose_1x1 = [&](const std::string& name, int cout, int cin) {
+    const std::vector<float>& w = W(h, name);
+    std::vector<float> t((size_t)cin * cout);
+    for (int co = 0; co < cout; ++co)
+      for (int ci = 0; ci < cin; ++ci) t[(size_t)ci * cout + co] = w[(size_t)co * cin + ci];
+    return arena_put(h, t);
+  };
+  h->sa_w1 = transpose_1x1("rdn.csar.sa.block.0.weight", 2 * F, F);
+  h->sa_b1 = arena_put(h, W(h, "rdn.csar.sa.block.0.bias"));
+  h->sa_w2 = transpose_1x1("rdn.csar.sa.block.2.weight", F, 2 * F);
+  h->sa_b2 = arena_put(h, W(h, "rdn.csar.sa.block.2.bias"));
+  h->co_w = transpose_1x1("rdn.csar.conv_out.weight", F, 2 * F);
+  h->co_b = arena_put(h, W(h, "rdn.csar.conv_out.bias"));
+  ok &= h->ca_w1 && h->ca_b1 && h->ca_w2 && h->ca_b2 && h->sa_w1 && h->sa_b1 && h->sa_w2 && h->sa_b2 && h->co_w && h->co_b;
+  ok &= pack_conv(h, h->gff0, "rdn.gff.0", F * h->cfg.num_blocks, F, 1, true);
+  ok &= pack_conv(h, h->gff1, "rdn.gff.1", F, F, 3, true);
+  ok &= pack_conv(h, h->fin, "final_conv", F, h->cfg.out_channels, 3, true);
+  if (!ok) return fail(h, LPSR_ERR_CUDA, "weight packing failed (arena %zu/%zu bytes): %s", h->arena.used, h->arena.cap,
+                       cudaGetErrorString(cudaGetLastError()));
+  h->packed = true;
+  return LPSR_OK;
+}
+
+}  // namespace
+
+namespace lpsr {
+WsLayout ws_layout(const lpsr_handle* h, int B, int H, int W) {
+  WsLayout L{};
+  L.Hp = (H + 3) / 4 * 4;
+  L.Wp = (W + 3) / 4 * 4;
+  L.P = L.Hp * L.Wp;
+  int S = (592 + B - 1) / B;
+  if (S > 64) S = 64;
+  if (S > L.P / 64) S = L.P / 64;
+  if (S < 1) S = 1;
+  L.S = S;
+  const size_t es = elem_size(h), BP = (size_t)B * L.P;
+  size_t off = 0;
+  auto take = [&](size_t elems, size_t esz) { size_t o = off; off = align_up(off + elems * esz, 256); return o; };
+  L.c0 = take(BP * 12, es);
+  L.e0 = take(BP / 4 * 48, es);
+  L.e1 = take(BP / 16 * 48, es);
+  L.d0 = take(BP / 4 * 12, es);
+  L.s = take(BP * 12, es);
+  L.ae = take(BP * 3 + 8, es);
+  L.sfe1 = take(BP * 32, es);
+  L.trunk = take(BP * kTrunkPitch, es);
+  L.t = take(BP * 32, es);
+  L.xin = take(BP * 32, es);
+  L.g0 = take(BP * 32, es);
+  L.g = take(BP * 32, es);
+  L.pool = take((size_t)B * S * 32, 4);
+  L.total = off;
+  return L;
+}
+}  // namespace lpsr
+
+namespace {
+
+int forward_dispatch(lpsr_handle* h, const float* x, float* y, int B, int H, int W, char* ws, cudaStream_t st, bool dry, int* nl,
+                     LaunchProfile* prof = nullptr) {
+  switch (h->cfg.precision) {
+    case LPSR_PREC_FP32: return forward_impl<float>(h, x, y, B, H, W, ws, st, dry, nl, prof);
+    case LPSR_PREC_BF16: return forward_impl<__nv_bfloat16>(h, x, y, B, H, W, ws, st, dry, nl, prof);
+    case LPSR_PREC_FP16: return forward_impl<__half>(h, x, y, B, H, W, ws, st, dry, nl, prof);
+    default: return fail(h, LPSR_ERR_UNSUPPORTED, "precision mode %d not built", h->cfg.precision);
+  }
+}
+
+int check_shape(lpsr_handle* h, int B, int H, int W) {
+  if (B < 1 || H < 1 || W < 1) return fail(h, LPSR_ERR_INVALID_ARG, "bad shape B=%d H=%d W=%d", B, H, W);
+  if (B > 65535) return fail(h, LPSR_ERR_INVALID_ARG, "B=%d exceeds the per-call limit 65535 (split the batch)", B);
+  return LPSR_OK;
+}
+
+}  // namespace
+
+namespace {
+// ---- op-level entry points ------------------------------------------------------------------------------
+static int pixel_remap(const float* x, float* y, int B, int C, int H, int W, void* stream, int mode) {
+  if (!x || !y || B < 1 || C < 1 || H < 1 || W < 1) return fail(nullptr, LPSR_ERR_INVALID_ARG, "bad argument");
+  if (mode == kShuffleDown && ((H | W) & 1)) return fail(nullptr, LPSR_ERR_INVALID_ARG, "PixelUnshuffle(2) needs even H,W");
+  if (mode == kShuffleUp && (C % 4)) return fail(nullptr, LPSR_ERR_INVALID_ARG, "PixelShuffle(2) needs C %% 4 == 0");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t n = (size_t)B * C * H * W;
+  float *a = nullptr, *b = nullptr;
+  CUDA_TRY(nullptr, cudaMalloc(&a, n * 4));
+  if (cudaMalloc(&b, n * 4) != cudaSuccess) { cudaFree(a); return fail(nullptr, LPSR_ERR_CUDA, "cudaMalloc failed"); }
+  const int blocks = (int)((n + 255) / 256 > 8192 ? 8192 : (n + 255) / 256);
+  nchw_to_nhwc_kernel<float><<<blocks, 256, 0, st>>>(x, a, B, C, H, W, C, 0);
+  if (mode == kShuffleDown) {
+    pixel_remap_nhwc_kernel<kShuffleDown><<<blocks, 256, 0, st>>>(a, b, B, C, H, W);
+    nhwc_to_nchw_kernel<float><<<blocks, 256, 0, st>>>(b, y, B, C * 4, H / 2, W / 2, C * 4, 0);
+  } else {
+    pixel_remap_nhwc_kernel<kShuffleUp><<<blocks, 256, 0, st>>>(a, b, B, C, H, W);
+    nhwc_to_nchw_kernel<float><<<blocks, 256, 0, st>>>(b, y, B, C / 4, H * 2, W * 2, C / 4, 0);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(a);
+  cudaFree(b);
+  if (e != cudaSuccess) return fail(nullptr, LPSR_ERR_CUDA, "pixel remap: %s", cudaGetErrorString(e));
+  return LPSR_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+int lpsr_abi_version(void) { return LPSR_B200_ABI_VERSION; }
+
+const char* lpsr_last_error(const lpsr_handle* h) { return h ? h->err : g_err; }
+
+int lpsr_create(lpsr_handle** out, const lpsr_config* cfg) {
+  if (!out || !cfg) return fail(nullptr, LPSR_ERR_INVALID_ARG, "null argument");
+  *out = nullptr;
+  if (cfg->abi_version != LPSR_B200_ABI_VERSION) return fail(nullptr, LPSR_ERR_INVALID_ARG, "ABI version %d != %d", cfg->abi_version, LPSR_B200_ABI_VERSION);
+  // kernels are specialised on the canonical ctor literals every reference call site uses
+  // (inference/run.py:124, evaluation/eval.py:77, my_utils/export_onnx.py:40-47)
+  if (cfg->num_channels != 3 || cfg->num_features != 32 || cfg->growth_rate != 16 || cfg->num_blocks != 4 || cfg->num_layers != 4 ||
+      cfg->out_channels != 1)
+    return fail(nullptr, LPSR_ERR_INVALID_ARG,
+                "unsupported LPSR dims (%d,%d,%d,%d,%d,out=%d): this build is specialised on (3,32,16,4,4,out=1)", cfg->num_channels,
+                cfg->num_features, cfg->growth_rate, cfg->num_blocks, cfg->num_layers, cfg->out_channels);
+  if (cfg->precision < LPSR_PREC_FP32 || cfg->precision > LPSR_PREC_FP16)
+    return fail(nullptr, LPSR_ERR_UNSUPPORTED, "precision mode %d not built", cfg->precision);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail(nullptr, LPSR_ERR_CUDA, "no CUDA device (%s); there is no CPU fallback", cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, LPSR_ERR_INVALID_ARG, "device %d out of range [0,%d)", cfg->device, ndev);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, cfg->device)) != cudaSuccess) return fail(nullptr, LPSR_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10) return fail(nullptr, LPSR_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+  if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) return fail(nullptr, LPSR_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  lpsr_handle* h = new lpsr_handle();
+  h->cfg = *cfg;
+  h->sm = prop.major * 10 + prop.minor;
+  h->num_sms = prop.multiProcessorCount;
+  build_live_table(h);
+  *out = h;
+  return LPSR_OK;
+}
+
+int lpsr_destroy(lpsr_handle* h) {
+  if (!h) return LPSR_OK;
+  cudaSetDevice(h->cfg.device);
+  if (h->arena.base) cudaFree(h->arena.base);
+  if (h->host_x) cudaFree(h->host_x);
+  if (h->host_y) cudaFree(h->host_y);
+  if (h->host_ws) cudaFree(h->host_ws);
+  if (h->host_stream) cudaStreamDestroy(h->host_stream);
+  delete h;
+  return LPSR_OK;
+}
+
+int lpsr_device_sm(const lpsr_handle* h) { return h ? h->sm : 0; }
+int lpsr_num_live_tensors(const lpsr_handle* h) { return h ? (int)h->live.size() : 0; }
+const char* lpsr_live_tensor_name(const lpsr_handle* h, int32_t i) {
+  return (h && i >= 0 && i < (int)h->live.size()) ? h->live[i].name.c_str() : nullptr;
+}
+int64_t lpsr_live_tensor_numel(const lpsr_handle* h, int32_t i) { return (h && i >= 0 && i < (int)h->live.size()) ? h->live[i].numel : -1; }
+
+int lpsr_load_weights(lpsr_handle* h, const lpsr_tensor_desc* tensors, int32_t n) {
+  if (!h || (!tensors && n > 0)) return fail(h, LPSR_ERR_INVALID_ARG, "null argument");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  for (int i = 0; i < n; ++i) {
+    const lpsr_tensor_desc& t = tensors[i];
+    if (!t.name || !t.data) return fail(h, LPSR_ERR_INVALID_ARG, "tensor %d: null name/data", i);
+    auto it = h->live_index.find(t.name);
+    if (it == h->live_index.end()) return fail(h, LPSR_ERR_INVALID_ARG, "unexpected tensor '%s' (not on the executed path)", t.name);
+    LiveTensor& lt = h->live[it->second];
+    if (t.numel != lt.numel) return fail(h, LPSR_ERR_INVALID_ARG, "size mismatch for '%s': got %lld, expected %lld", t.name, (long long)t.numel, (long long)lt.numel);
+    lt.host.resize(lt.numel);
+    if (t.on_device) CUDA_TRY(h, cudaMemcpy(lt.host.data(), t.data, lt.numel * sizeof(float), cudaMemcpyDeviceToHost));
+    else memcpy(lt.host.data(), t.data, lt.numel * sizeof(float));
+    lt.loaded = true;
+  }
+  for (const LiveTensor& lt : h->live)
+    if (!lt.loaded) { h->packed = false; return LPSR_OK; }   // partial load: pack once everything arrived
+  CUDA_TRY(h, cudaDeviceSynchronize());   // packed buffers may still be in use by earlier forwards
+  return pack_all(h);
+}
+
+int lpsr_output_shape(const lpsr_handle* h, int32_t B, int32_t H, int32_t W, int32_t* oc, int32_t* oh, int32_t* ow) {
+  if (!h) return LPSR_ERR_INVALID_ARG;
+  (void)B;
+  if (oc) *oc = h->cfg.out_channels;
+  if (oh) *oh = (H + 3) / 4 * 4;
+  if (ow) *ow = (W + 3) / 4 * 4;
+  return LPSR_OK;
+}
+
+size_t lpsr_workspace_bytes(const lpsr_handle* h, int32_t B, int32_t H, int32_t W) {
+  if (!h || B < 1 || H < 1 || W < 1) return 0;
+  return ws_layout(h, B, H, W).total;
+}
+
+int lpsr_forward_launch_count(const lpsr_handle* h, int32_t B, int32_t H, int32_t W) {
+  if (!h || !h->packed) return -1;
+  int n = 0;
+  forward_dispatch(const_cast<lpsr_handle*>(h), nullptr, nullptr, B, H, W, nullptr, nullptr, true, &n);
+  return n;
+}
+
+int lpsr_forward(lpsr_handle* h, const float* x, float* y, int32_t B, int32_t H, int32_t W, void* ws, size_t ws_bytes, void* stream) {
+  if (!h || !x || !y || !ws) return fail(h, LPSR_ERR_INVALID_ARG, "null argument");
+  int rc = check_shape(h, B, H, W);
+  if (rc) return rc;
+  if (!h->packed) {
+    std::string missing;
+    for (const LiveTensor& lt : h->live) if (!lt.loaded) { missing = lt.name; break; }
+    return fail(h, LPSR_ERR_NO_WEIGHTS, "forward before weights were loaded (first missing: %s)", missing.c_str());
+  }
+  if (ws_bytes < ws_layout(h, B, H, W).total) return fail(h, LPSR_ERR_WORKSPACE, "workspace %zu < required %zu bytes", ws_bytes, ws_layout(h, B, H, W).total);
+  if (reinterpret_cast<uintptr_t>(ws) % 256) return fail(h, LPSR_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+  int cur = -1;
+  CUDA_TRY(h, cudaGetDevice(&cur));
+  if (cur != h->cfg.device) CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  rc = forward_dispatch(h, x, y, B, H, W, static_cast<char*>(ws), static_cast<cudaStream_t>(stream), false, nullptr);
+  if (cur != h->cfg.device && cur >= 0) cudaSetDevice(cur);
+  return rc;
+}
+
+int lpsr_forward_profiled(lpsr_handle* h, const float* x, float* y, int32_t B, int32_t H, int32_t W, void* ws, size_t ws_bytes,
+                          void* stream, float* ms_out, char* names_out, int32_t name_stride, int32_t capacity) {
+  if (!h || !x || !y || !ws || !ms_out) return fail(h, LPSR_ERR_INVALID_ARG, "null argument");
+  int rc = check_shape(h, B, H, W);
+  if (rc) return rc;
+  if (!h->packed) return fail(h, LPSR_ERR_NO_WEIGHTS, "forward before weights were loaded");
+  if (ws_bytes < ws_layout(h, B, H, W).total) return fail(h, LPSR_ERR_WORKSPACE, "workspace too small");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  LaunchProfile prof;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = forward_dispatch(h, x, y, B, H, W, static_cast<char*>(ws), st, false, nullptr, &prof);
+  cudaError_t e = cudaStreamSynchronize(st);
+  const int n = (int)prof.names.size();
+  if (rc == LPSR_OK && e == cudaSuccess && (int)prof.events.size() == n + 1 && n <= capacity) {
+    for (int i = 0; i < n; ++i) {
+      cudaEventElapsedTime(&ms_out[i], prof.events[i], prof.events[i + 1]);
+      if (names_out && name_stride > 0) snprintf(names_out + (size_t)i * name_stride, name_stride, "%s", prof.names[i].c_str());
+    }
+  } else if (rc == LPSR_OK) {
+    rc = fail(h, e != cudaSuccess ? LPSR_ERR_CUDA : LPSR_ERR_INVALID_ARG, "profiled forward: %s (launches %d, capacity %d)",
+              cudaGetErrorString(e), n, capacity);
+  }
+  for (cudaEvent_t ev : prof.events) cudaEventDestroy(ev);
+  return rc == LPSR_OK ? n : rc;
+}
+
+int lpsr_forward_host(lpsr_handle* h, const float* x_host, float* y_host, int32_t B, int32_t H, int32_t W) {
+  if (!h || !x_host || !y_host) return fail(h, LPSR_ERR_INVALID_ARG, "null argument");
+  int rc = check_shape(h, B, H, W);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  if (!h->host_stream) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking));
+  const WsLayout L = ws_layout(h, B, H, W);
+  const size_t xb = (size_t)B * 3 * H * W * 4, yb = (size_t)B * h->cfg.out_channels * L.P * 4;
+  auto grow = [&](void** p, size_t* cap, size_t need) -> cudaError_t {
+    if (*cap >= need) return cudaSuccess;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    cudaError_t e = cudaMalloc(p, need);
+    if (e == cudaSuccess) *cap = need;
+    return e;
+  };
+  CUDA_TRY(h, grow(&h->host_x, &h->host_x_cap, xb));
+  CUDA_TRY(h, grow(&h->host_y, &h->host_y_cap, yb));
+  CUDA_TRY(h, grow(&h->host_ws, &h->host_ws_cap, L.total));
+  CUDA_TRY(h, cudaMemcpyAsync(h->host_x, x_host, xb, cudaMemcpyHostToDevice, h->host_stream));
+  rc = lpsr_forward(h, static_cast<const float*>(h->host_x), static_cast<float*>(h->host_y), B, H, W, h->host_ws, h->host_ws_cap, h->host_stream);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaMemcpyAsync(y_host, h->host_y, yb, cudaMemcpyDeviceToHost, h->host_stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->host_stream));
+  return LPSR_OK;
+}
+
+int lpsr_debug_read_tap(lpsr_handle* h, const char* name, float* dst, int64_t dst_numel, int32_t B, int32_t H, int32_t W, void* wsv,
+                        void* stream) {
+  if (!h || !name || !dst || !wsv) return fail(h, LPSR_ERR_INVALID_ARG, "null argument");
+  const WsLayout L = ws_layout(h, B, H, W);
+  struct Tap { const char* name; size_t off; int pitch, choff, C, div; };
+  const Tap taps[] = {
+      {"ae.c0", L.c0, 12, 0, 12, 1},      {"ae.enc0", L.e0, 48, 0, 48, 2},   {"ae.enc1", L.e1, 48, 0, 48, 4},
+      {"ae.dec0", L.d0, 12, 0, 12, 2},    {"ae.sum", L.s, 12, 0, 12, 1},     {"ae.out", L.ae, 3, 0, 3, 1},
+      {"rdn.sfe1", L.sfe1, 32, 0, 32, 1}, {"rdn.sfe2", L.trunk, kTrunkPitch, kX0, 32, 1},
+      {"rdn.block0", L.trunk, kTrunkPitch, kF0, 32, 1}, {"rdn.block1", L.trunk, kTrunkPitch, kX2, 32, 1},
+      {"rdn.block2", L.trunk, kTrunkPitch, kF2, 32, 1}, {"rdn.block3", L.trunk, kTrunkPitch, kF3, 32, 1},
+      {"rdn.cat0", L.trunk, kTrunkPitch, kX0, 96, 1},   {"csar3.x_in", L.xin, 32, 0, 32, 1},
+      {"rdn.gff0", L.g0, 32, 0, 32, 1},   {"rdn.out", L.g, 32, 0, 32, 1}};
+  for (const Tap& t : taps) {
+    if (strcmp(t.name, name)) continue;
+    const int Ht = L.Hp / t.div, Wt = L.Wp / t.div;
+    const int64_t need = (int64_t)B * t.C * Ht * Wt;
+    if (dst_numel != need) return fail(h, LPSR_ERR_INVALID_ARG, "tap '%s' has %lld elements, buffer has %lld", name, (long long)need, (long long)dst_numel);
+    char* ws = static_cast<char*>(wsv);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (h->cfg.precision) {
+      case LPSR_PREC_FP32: return tap_copy_impl<float>(h, ws + t.off, dst, B, t.C, Ht, Wt, t.pitch, t.choff, st);
+      case LPSR_PREC_BF16: return tap_copy_impl<__nv_bfloat16>(h, ws + t.off, dst, B, t.C, Ht, Wt, t.pitch, t.choff, st);
+      default: return tap_copy_impl<__half>(h, ws + t.off, dst, B, t.C, Ht, Wt, t.pitch, t.choff, st);
+    }
+    return LPSR_OK;
+  }
+  return fail(h, LPSR_ERR_INVALID_ARG, "unknown tap '%s'", name);
+}
+
+int lpsr_op_pixel_unshuffle2(const float* x, float* y, int32_t B, int32_t C, int32_t H, int32_t W, void* stream) {
+  return pixel_remap(x, y, B, C, H, W, stream, kShuffleDown);
+}
+int lpsr_op_pixel_shuffle2(const float* x, float* y, int32_t B, int32_t C, int32_t H, int32_t W, void* stream) {
+  return pixel_remap(x, y, B, C, H, W, stream, kShuffleUp);
+}
+
+int lpsr_op_conv2d(lpsr_handle* h, const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t Cin, int32_t Cout,
+                   int32_t ks, int32_t H, int32_t W, int32_t relu, void* stream) {
+  if (!h || !x || !w || !y) return fail(h, LPSR_ERR_INVALID_ARG, "null argument");
+  if ((ks != 1 && ks != 3) || Cin % 16 || Cin < 16 || Cin > 16 * kMaxChunks || (Cout != 16 && Cout != 32 && Cout != 64))
+    return fail(h, LPSR_ERR_UNSUPPORTED, "op_conv2d supports ks in {1,3}, Cin %% 16 == 0 (<= %d), Cout in {16,32,64}", 16 * kMaxChunks);
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (h->cfg.precision) {
+    case LPSR_PREC_FP32: return op_conv_impl<float>(h, x, w, bias, y, B, Cin, Cout, ks, H, W, relu, st);
+    case LPSR_PREC_BF16: return op_conv_impl<__nv_bfloat16>(h, x, w, bias, y, B, Cin, Cout, ks, H, W, relu, st);
+    case LPSR_PREC_FP16: return op_conv_impl<__half>(h, x, w, bias, y, B, Cin, Cout, ks, H, W, relu, st);
+    default: return fail(h, LPSR_ERR_UNSUPPORTED, "precision mode %d not built", h->cfg.precision);
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,110 @@
+// engine_internal.h -- types shared by engine.cu (C ABI, packing) and the per-dtype forward instantiations.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/lpsr_b200.h"
+#include "common.cuh"
+#include "umma_weights.h"
+
+namespace lpsr {
+
+struct LiveTensor {
+  std::string name;
+  int64_t numel;
+  std::vector<float> host;   // raw fp32 as given (PyTorch layout)
+  bool loaded = false;
+};
+
+struct DeviceArena {       // one cudaMalloc for all packed weights
+  void* base = nullptr;
+  size_t cap = 0, used = 0;
+};
+
+// packed weights of one dense conv
+struct ConvW {
+  int ks = 0, cin = 0, cout = 0;
+  float* w = nullptr;      // [ks*ks][cin][cout] fp32 (CUDA-core kernels)
+  float* b = nullptr;      // [cout] fp32 (nullptr: no bias)
+  UmmaWeights u;           // tensor-core packing (16-bit modes)
+};
+
+struct DConvW { float *dw_w, *dw_b, *pw_w, *pw_b; int cin, cout; };
+
+}  // namespace lpsr
+
+struct lpsr_handle {
+  lpsr_config cfg{};
+  int sm = 0;
+  int num_sms = 0;
+  std::vector<lpsr::LiveTensor> live;
+  std::map<std::string, int> live_index;
+  bool packed = false;
+  lpsr::DeviceArena arena;
+  // packed layers
+  lpsr::ConvW ae_in, ae_out, sfe1, sfe2, rdb[2][4], lff[2], csar_c1, csar_c2, gff0, gff1, fin;
+  lpsr::DConvW dc[4];
+  float *ca_w1 = nullptr, *ca_b1 = nullptr, *ca_w2 = nullptr, *ca_b2 = nullptr;
+  float *sa_w1 = nullptr, *sa_b1 = nullptr, *sa_w2 = nullptr, *sa_b2 = nullptr, *co_w = nullptr, *co_b = nullptr;
+  // host-call path (lpsr_forward_host)
+  cudaStream_t host_stream = nullptr;
+  void* host_x = nullptr; void* host_y = nullptr; void* host_ws = nullptr;
+  size_t host_x_cap = 0, host_y_cap = 0, host_ws_cap = 0;
+  char err[512] = "";
+};
+
+namespace lpsr {
+
+int fail(lpsr_handle* h, int code, const char* fmt, ...);
+
+struct LaunchProfile {            // filled by forward_impl when profiling: events[i] precedes launch i, +1 closing event
+  std::vector<cudaEvent_t> events;
+  std::vector<std::string> names;
+};
+
+#define CUDA_TRY(h, expr)                                                                         \
+  do {                                                                                            \
+    cudaError_t e_ = (expr);                                                                      \
+    if (e_ != cudaSuccess)                                                                        \
+      return fail(h, LPSR_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+inline bool half_mode(const lpsr_handle* h) { return h->cfg.precision == LPSR_PREC_BF16 || h->cfg.precision == LPSR_PREC_FP16; }
+inline size_t elem_size(const lpsr_handle* h) { return half_mode(h) ? 2 : 4; }
+
+
+// ---- workspace layout ----------------------------------------------------------------------------------
+// Trunk buffer channel map (pitch kTrunkPitch): every 32-channel trunk tensor and both 96-channel RDB concat
+// buffers live in ONE NHWC buffer so that dense concatenation and the final torch.cat are channel windows:
+//   [  0, 32) sfe2 = RDB#0 input     [ 32, 96) RDB#0 growth (4x16)     [ 96,128) block0 out (RDB#0)
+//   [128,160) block1 out (CSAR) = RDB#2 input   [160,224) RDB#2 growth  [224,256) block2 out (RDB#2)
+//   [256,288) block3 out (CSAR)
+constexpr int kTrunkPitch = 288;
+constexpr int kX0 = 0, kF0 = 96, kX2 = 128, kF2 = 224, kF3 = 256;
+
+struct WsLayout {
+  size_t c0, e0, e1, d0, s, ae, sfe1, trunk, t, xin, g0, g, pool, total;
+  int Hp, Wp, P, S;
+};
+
+WsLayout ws_layout(const lpsr_handle* h, int B, int H, int W);
+
+// per-dtype entry points, explicitly instantiated in inst_{f32,bf16,f16}.cu
+template <typename T>
+int forward_impl(lpsr_handle* h, const float* x, float* y, int B, int H, int W, char* ws, cudaStream_t st, bool dry, int* n_launch,
+                 LaunchProfile* prof);
+template <typename T>
+int op_conv_impl(lpsr_handle* h, const float* x, const float* w_oihw, const float* bias, float* y, int B, int Cin, int Cout, int ks,
+                 int H, int W, int relu, cudaStream_t st);
+template <typename T>
+int tap_copy_impl(lpsr_handle* h, const void* src, float* dst, int B, int C, int H, int W, int pitch, int off, cudaStream_t st);
+
+}  // namespace lpsr

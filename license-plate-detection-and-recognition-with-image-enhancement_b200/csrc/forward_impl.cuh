@@ -1,0 +1,283 @@
+// forward_impl.cuh -- the launch plan of one LPSR forward (reference: my_models/lpsr.py:269-274), templated on
+// the activation storage type T.  Included only by inst_*.cu, which explicitly instantiate it per dtype so the
+// three dtypes compile in parallel.
+#pragma once
+#include <algorithm>
+
+#include "cuda_core_kernels.cuh"
+#include "engine_internal.h"
+#include "umma_conv.cuh"
+
+namespace lpsr {
+
+// ---- launch helpers ------------------------------------------------------------------------------------
+struct Ctx {
+  lpsr_handle* h;
+  cudaStream_t st;
+  bool dry;
+  int launches = 0;
+  int rc = LPSR_OK;
+  LaunchProfile* prof = nullptr;   // optional: one cudaEvent before every launch (lpsr_forward_profiled)
+  const char* tag = "";            // layer label for the profile
+  void begin(const char* kind) {
+    launches++;
+    if (prof && !dry && rc == LPSR_OK) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) == cudaSuccess) {
+        cudaEventRecord(e, st);
+        prof->events.push_back(e);
+        prof->names.push_back(std::string(tag) + ":" + kind);
+      }
+    }
+  }
+};
+
+template <typename T, int KS, int CCH, int COUT, bool IN_NCHW, bool OUT_SIG>
+void launch_direct(Ctx& c, const ConvParams& p) {
+  c.begin("conv_direct");
+  if (c.dry || c.rc != LPSR_OK) return;
+  dim3 grid((p.W + kTileW - 1) / kTileW, (p.H + kTileH - 1) / kTileH, p.B);
+  conv_direct_kernel<T, KS, CCH, COUT, IN_NCHW, OUT_SIG><<<grid, kThreads, 0, c.st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) c.rc = fail(c.h, LPSR_ERR_CUDA, "conv_direct<%d,%d,%d> launch: %s", KS, CCH, COUT, cudaGetErrorString(e));
+}
+
+inline ConvParams conv_params(const ConvW& w, const void* in, int in_pitch, int in_off, int cch, void* out, int out_pitch, int out_off,
+                       int B, int H, int Wd, bool relu, const void* res = nullptr, int res_pitch = 0, int res_off = 0) {
+  ConvParams p{};
+  p.in = in; p.in_pitch = in_pitch;
+  p.n_chunks = w.cin / cch;
+  for (int k = 0; k < p.n_chunks; ++k) p.chunk_off[k] = in_off + k * cch;
+  p.w = w.w; p.bias = w.b;
+  p.out = out; p.out_pitch = out_pitch; p.out_off = out_off;
+  p.res = res; p.res_pitch = res_pitch; p.res_off = res_off;
+  p.B = B; p.H = H; p.W = Wd; p.inH = H; p.inW = Wd;
+  p.relu = relu ? 1 : 0;
+  return p;
+}
+
+// dense 3x3 / 1x1 conv with Cin % 16 == 0: tensor cores in the 16-bit modes, FFMA in fp32 mode
+template <typename T>
+void dense_conv(Ctx& c, const ConvW& w, ConvParams p) {
+  if constexpr (sizeof(T) == 2) {
+    if (w.u.packed) {
+      c.begin("umma_conv");
+      if (c.dry || c.rc != LPSR_OK) return;
+      const char* msg = umma_conv_launch<T>(w.u, p, c.h->num_sms, c.st);
+      if (msg) c.rc = fail(c.h, LPSR_ERR_CUDA, "umma_conv launch (ks=%d cin=%d cout=%d): %s", w.ks, w.cin, w.cout, msg);
+      return;
+    }
+  }
+  if (w.ks == 3 && w.cout == 16) return launch_direct<T, 3, 16, 16, false, false>(c, p);
+  if (w.ks == 3 && w.cout == 32) return launch_direct<T, 3, 16, 32, false, false>(c, p);
+  if (w.ks == 1 && w.cout == 32) return launch_direct<T, 1, 16, 32, false, false>(c, p);
+  if (w.ks == 1 && w.cout == 16) return launch_direct<T, 1, 16, 16, false, false>(c, p);
+  if (w.ks == 1 && w.cout == 64) return launch_direct<T, 1, 16, 64, false, false>(c, p);
+  c.rc = fail(c.h, LPSR_ERR_UNSUPPORTED, "no kernel for conv ks=%d cin=%d cout=%d", w.ks, w.cin, w.cout);
+}
+
+template <typename T, int CIN, int COUT, int MODE, bool ADD>
+void launch_dconv(Ctx& c, const DConvW& w, const void* in, int in_pitch, void* out, int out_pitch, const void* res, int res_pitch,
+                  int B, int H, int Wd) {
+  c.begin("dconv_fused");
+  if (c.dry || c.rc != LPSR_OK) return;
+  DConvParams p{};
+  p.in = in; p.in_pitch = in_pitch; p.in_off = 0;
+  p.dw_w = w.dw_w; p.dw_b = w.dw_b; p.pw_w = w.pw_w; p.pw_b = w.pw_b;
+  p.out = out; p.out_pitch = out_pitch; p.out_off = 0;
+  p.res = res; p.res_pitch = res_pitch; p.res_off = 0;
+  p.B = B; p.H = H; p.W = Wd;
+  dim3 grid((Wd + kTileW - 1) / kTileW, (H + kTileH - 1) / kTileH, B);
+  dconv_fused_kernel<T, CIN, COUT, MODE, ADD><<<grid, kThreads, 0, c.st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) c.rc = fail(c.h, LPSR_ERR_CUDA, "dconv_fused<%d,%d> launch: %s", CIN, COUT, cudaGetErrorString(e));
+}
+
+template <typename T>
+void csar_block(Ctx& c, const WsLayout& L, char* ws, int B, int in_off, int out_off) {
+  lpsr_handle* h = c.h;
+  T* trunk = reinterpret_cast<T*>(ws + L.trunk);
+  T* t = reinterpret_cast<T*>(ws + L.t);
+  T* xin = reinterpret_cast<T*>(ws + L.xin);
+  float* pool = reinterpret_cast<float*>(ws + L.pool);
+  // x_in = conv_in.2(relu(conv_in.0(x)))                                               (lpsr.py:159-172,181)
+  dense_conv<T>(c, h->csar_c1, conv_params(h->csar_c1, trunk, kTrunkPitch, in_off, 16, t, 32, 0, B, L.Hp, L.Wp, true));
+  dense_conv<T>(c, h->csar_c2, conv_params(h->csar_c2, t, 32, 0, 16, xin, 32, 0, B, L.Hp, L.Wp, false));
+  // AdaptiveAvgPool2d(1) partial sums                                                    (lpsr.py:124)
+  c.begin("gap_partial");
+  if (!c.dry && c.rc == LPSR_OK) {
+    gap_partial_kernel<T><<<dim3(L.S, B), kThreads, 0, c.st>>>(xin, 32, 0, L.P, L.S, pool);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) c.rc = fail(h, LPSR_ERR_CUDA, "gap_partial launch: %s", cudaGetErrorString(e));
+  }
+  // gates + conv_out + residual                                                          (lpsr.py:182-186)
+  c.begin("csar_tail");
+  if (!c.dry && c.rc == LPSR_OK) {
+    TailParams p{};
+    p.x_in = xin; p.xin_pitch = 32; p.xin_off = 0;
+    p.res = trunk; p.res_pitch = kTrunkPitch; p.res_off = in_off;
+    p.out = trunk; p.out_pitch = kTrunkPitch; p.out_off = out_off;
+    p.out2 = nullptr;
+    p.pool_partial = pool; p.S = L.S;
+    p.ca_w1 = h->ca_w1; p.ca_b1 = h->ca_b1; p.ca_w2 = h->ca_w2; p.ca_b2 = h->ca_b2;
+    p.sa_w1 = h->sa_w1; p.sa_b1 = h->sa_b1; p.sa_w2 = h->sa_w2; p.sa_b2 = h->sa_b2;
+    p.co_w = h->co_w; p.co_b = h->co_b;
+    p.B = B; p.P = L.P;
+    csar_tail_kernel<T><<<dim3((L.P + kThreads - 1) / kThreads, B), kThreads, 0, c.st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) c.rc = fail(h, LPSR_ERR_CUDA, "csar_tail launch: %s", cudaGetErrorString(e));
+  }
+}
+
+template <typename T>
+void rdb_block(Ctx& c, const WsLayout& L, char* ws, int B, int r, int x_off, int out_off) {
+  lpsr_handle* h = c.h;
+  T* trunk = reinterpret_cast<T*>(ws + L.trunk);
+  const int F = 32, G = 16;
+  // dense layers: conv3x3(cat[0 : F+G*i]) -> ReLU -> channel slice [F+G*i, F+G*(i+1)) of the same buffer (lpsr.py:31-40)
+  for (int i = 0; i < 4; ++i)
+    dense_conv<T>(c, h->rdb[r][i], conv_params(h->rdb[r][i], trunk, kTrunkPitch, x_off, 16, trunk, kTrunkPitch, x_off + F + G * i, B, L.Hp, L.Wp, true));
+  // x + alpha*lff(cat): alpha is folded into the packed lff weights/bias (lpsr.py:52-61)
+  dense_conv<T>(c, h->lff[r], conv_params(h->lff[r], trunk, kTrunkPitch, x_off, 16, trunk, kTrunkPitch, out_off, B, L.Hp, L.Wp, false,
+                                          trunk, kTrunkPitch, x_off));
+}
+
+template <typename T>
+int forward_impl(lpsr_handle* h, const float* x, float* y, int B, int H, int W, char* ws, cudaStream_t st, bool dry, int* n_launch,
+                 LaunchProfile* prof) {
+  const WsLayout L = ws_layout(h, B, H, W);
+  Ctx c{h, st, dry};
+  c.prof = prof;
+  T* c0 = reinterpret_cast<T*>(ws + L.c0);
+  T* e0 = reinterpret_cast<T*>(ws + L.e0);
+  T* e1 = reinterpret_cast<T*>(ws + L.e1);
+  T* d0 = reinterpret_cast<T*>(ws + L.d0);
+  T* s = reinterpret_cast<T*>(ws + L.s);
+  T* ae = reinterpret_cast<T*>(ws + L.ae);
+  T* sfe1 = reinterpret_cast<T*>(ws + L.sfe1);
+  T* trunk = reinterpret_cast<T*>(ws + L.trunk);
+  T* g0 = reinterpret_cast<T*>(ws + L.g0);
+  T* g = reinterpret_cast<T*>(ws + L.g);
+  const int Hp = L.Hp, Wp = L.Wp;
+
+  // ---- AutoEncoder (lpsr.py:106-117) ------------------------------------------------------------------
+  c.tag = "ae.conv_in";
+  {  // conv_in 3->12 reads the caller's NCHW fp32 tensor; zero beyond (H,W) == pad-to-4 (lpsr.py:107-111)
+    ConvParams p = conv_params(h->ae_in, x, 0, 0, 3, c0, 12, 0, B, Hp, Wp, false);
+    p.inH = H; p.inW = W;
+    launch_direct<T, 3, 3, 12, true, false>(c, p);
+  }
+  c.tag = "ae.enc0";
+  launch_dconv<T, 12, 12, kShuffleDown, false>(c, h->dc[0], c0, 12, e0, 48, nullptr, 0, B, Hp, Wp);          // -> [48,H/2,W/2]
+  c.tag = "ae.enc1";
+  launch_dconv<T, 48, 12, kShuffleDown, false>(c, h->dc[1], e0, 48, e1, 48, nullptr, 0, B, Hp / 2, Wp / 2);  // -> [48,H/4,W/4]
+  c.tag = "ae.dec0";
+  launch_dconv<T, 48, 48, kShuffleUp, false>(c, h->dc[2], e1, 48, d0, 12, nullptr, 0, B, Hp / 4, Wp / 4);    // -> [12,H/2,W/2]
+  c.tag = "ae.dec1";
+  launch_dconv<T, 12, 48, kShuffleUp, true>(c, h->dc[3], d0, 12, s, 12, c0, 12, B, Hp / 2, Wp / 2);          // -> c0 + [12,H,W]
+  c.tag = "ae.conv_out";
+  launch_direct<T, 3, 12, 3, false, false>(c, conv_params(h->ae_out, s, 12, 0, 12, ae, 3, 0, B, Hp, Wp, false));
+
+  // ---- RDN (lpsr.py:214-225) ---------------------------------------------------------------------------
+  c.tag = "rdn.shallowF1";
+  launch_direct<T, 7, 3, 32, false, false>(c, conv_params(h->sfe1, ae, 3, 0, 3, sfe1, 32, 0, B, Hp, Wp, false));
+  c.tag = "rdn.shallowF2";
+  dense_conv<T>(c, h->sfe2, conv_params(h->sfe2, sfe1, 32, 0, 16, trunk, kTrunkPitch, kX0, B, Hp, Wp, false));
+  c.tag = "rdb0";
+  rdb_block<T>(c, L, ws, B, 0, kX0, kF0);       // rdbs[0]
+  c.tag = "csar1";
+  csar_block<T>(c, L, ws, B, kF0, kX2);         // rdbs[1] = shared CSAR
+  c.tag = "rdb2";
+  rdb_block<T>(c, L, ws, B, 1, kX2, kF2);       // rdbs[2]
+  c.tag = "csar3";
+  csar_block<T>(c, L, ws, B, kF2, kF3);         // rdbs[3] = same CSAR weights
+  c.tag = "rdn.gff0";
+  {  // gff.0 1x1 over cat(local features) = 4 channel windows of the trunk buffer (lpsr.py:207-210,224)
+    ConvParams p = conv_params(h->gff0, trunk, kTrunkPitch, 0, 16, g0, 32, 0, B, Hp, Wp, false);
+    const int offs[4] = {kF0, kX2, kF2, kF3};
+    for (int k = 0; k < 8; ++k) p.chunk_off[k] = offs[k / 2] + (k % 2) * 16;
+    dense_conv<T>(c, h->gff0, p);
+  }
+  // gff.1 3x3 + global residual sfe1 (lpsr.py:211,224)
+  c.tag = "rdn.gff1";
+  dense_conv<T>(c, h->gff1, conv_params(h->gff1, g0, 32, 0, 16, g, 32, 0, B, Hp, Wp, false, sfe1, 32, 0));
+  // ---- final conv + sigmoid, NCHW fp32 out (lpsr.py:273-274) -----------------------------------------------
+  c.tag = "final_conv";
+  launch_direct<T, 3, 16, 1, false, true>(c, conv_params(h->fin, g, 32, 0, 16, y, 1, 0, B, Hp, Wp, false));
+  if (n_launch) *n_launch = c.launches;
+  if (prof && !dry) {   // closing event
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) == cudaSuccess) { cudaEventRecord(e, st); prof->events.push_back(e); }
+  }
+  return c.rc;
+}
+
+template <typename T>
+int op_conv_impl(lpsr_handle* h, const float* x, const float* w_oihw, const float* bias, float* y, int B, int Cin, int Cout, int ks,
+                        int H, int W, int relu, cudaStream_t st) {
+  const size_t npix = (size_t)B * H * W;
+  std::vector<float> wh((size_t)Cout * Cin * ks * ks), bh(Cout, 0.f);
+  CUDA_TRY(h, cudaMemcpy(wh.data(), w_oihw, wh.size() * 4, cudaMemcpyDeviceToHost));
+  if (bias) CUDA_TRY(h, cudaMemcpy(bh.data(), bias, Cout * 4, cudaMemcpyDeviceToHost));
+  std::vector<float> pw((size_t)ks * ks * Cin * Cout);
+  for (int co = 0; co < Cout; ++co)
+    for (int ci = 0; ci < Cin; ++ci)
+      for (int t = 0; t < ks * ks; ++t) pw[((size_t)t * Cin + ci) * Cout + co] = wh[((size_t)co * Cin + ci) * ks * ks + t];
+  // private scratch: [packed weights | bias | umma weights | in NHWC | out NHWC]
+  void* scratch = nullptr;
+  const size_t wbytes = align_up(pw.size() * 4, 256) + align_up(Cout * 4, 256) + align_up(pw.size() * 2 + 4096, 256) + 256;
+  const size_t total = wbytes + align_up(npix * Cin * sizeof(T), 256) + align_up(npix * Cout * sizeof(T), 256);
+  CUDA_TRY(h, cudaMalloc(&scratch, total));
+  char* sp = static_cast<char*>(scratch);
+  size_t off = 0;
+  auto put = [&](const void* src, size_t bytes) -> void* {
+    void* d = sp + off;
+    cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice);
+    off = align_up(off + bytes, 256);
+    return d;
+  };
+  ConvW cw;
+  cw.ks = ks; cw.cin = Cin; cw.cout = Cout;
+  cw.w = static_cast<float*>(put(pw.data(), pw.size() * 4));
+  cw.b = bias ? static_cast<float*>(put(bh.data(), Cout * 4)) : nullptr;
+  if (sizeof(T) == 2 && umma_supported(ks, Cin, Cout)) {
+    bool ok = umma_pack_weights(cw.u, pw.data(), bias ? bh.data() : nullptr, ks, Cin, Cout, h->cfg.precision == LPSR_PREC_FP16,
+                                [&](const std::vector<uint16_t>& v) { return static_cast<uint16_t*>(put(v.data(), v.size() * 2)); },
+                                [&](const std::vector<float>& v) { return static_cast<float*>(put(v.data(), v.size() * 4)); });
+    if (!ok || off > wbytes) { cudaFree(scratch); return fail(h, LPSR_ERR_CUDA, "op_conv: umma weight packing failed"); }
+  }
+  T* in = reinterpret_cast<T*>(sp + wbytes);
+  T* out = reinterpret_cast<T*>(sp + wbytes + align_up(npix * Cin * sizeof(T), 256));
+  const int blocks = (int)std::min<size_t>(8192, (npix * Cin + 255) / 256);
+  nchw_to_nhwc_kernel<T><<<blocks, 256, 0, st>>>(x, in, B, Cin, H, W, Cin, 0);
+  Ctx c{h, st, false};
+  dense_conv<T>(c, cw, conv_params(cw, in, Cin, 0, 16, out, Cout, 0, B, H, W, relu != 0));
+  if (c.rc == LPSR_OK) {
+    const int blocks2 = (int)std::min<size_t>(8192, (npix * Cout + 255) / 256);
+    nhwc_to_nchw_kernel<T><<<blocks2, 256, 0, st>>>(out, y, B, Cout, H, W, Cout, 0);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(scratch);
+  if (c.rc != LPSR_OK) return c.rc;
+  if (e != cudaSuccess) return fail(h, LPSR_ERR_CUDA, "op_conv2d: %s", cudaGetErrorString(e));
+  return LPSR_OK;
+}
+
+
+template <typename T>
+int tap_copy_impl(lpsr_handle* h, const void* src, float* dst, int B, int C, int H, int W, int pitch, int off, cudaStream_t st) {
+  const long long need = (long long)B * C * H * W;
+  const int blocks = (int)std::min<long long>(4096, (need + 255) / 256);
+  nhwc_to_nchw_kernel<T><<<blocks, 256, 0, st>>>(static_cast<const T*>(src), dst, B, C, H, W, pitch, off);
+  CUDA_TRY(h, cudaGetLastError());
+  return LPSR_OK;
+}
+
+#define LPSR_INSTANTIATE(T)                                                                                             \
+  template int forward_impl<T>(lpsr_handle*, const float*, float*, int, int, int, char*, cudaStream_t, bool, int*,      \
+                               LaunchProfile*);                                                                         \
+  template int op_conv_impl<T>(lpsr_handle*, const float*, const float*, const float*, float*, int, int, int, int, int, \
+                               int, int, cudaStream_t);                                                                 \
+  template int tap_copy_impl<T>(lpsr_handle*, const void*, float*, int, int, int, int, int, int, cudaStream_t);
+
+}  // namespace lpsr

@@ -1,0 +1,71 @@
+// umma_weights.h -- host-side weight packing for the tcgen05 convolution (see umma_conv.cuh for the layout).
+#pragma once
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace lpsr {
+
+struct UmmaWeights {
+  bool packed = false;
+  int ks = 0, cin = 0, cout = 0;
+  uint16_t* w = nullptr;   // [taps][cin/8][cout][8] 16-bit (bf16 or fp16)
+  float* bias = nullptr;   // [cout] (zeros if the conv has no bias)
+};
+
+inline bool umma_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LPSR_UMMA");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+inline bool umma_supported(int ks, int cin, int cout) {
+  return umma_enabled() && (ks == 1 || ks == 3) && cin % 16 == 0 && cin >= 16 && cin <= 16 * kMaxChunks &&
+         (cout == 16 || cout == 32 || cout == 64);
+}
+
+inline uint16_t f32_to_bf16_bits(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);  // NaN
+  u += 0x7fffu + ((u >> 16) & 1);                                            // round to nearest even
+  return (uint16_t)(u >> 16);
+}
+inline uint16_t f32_to_f16_bits(float f) {
+  __half h = __float2half_rn(std::min(std::max(f, -65504.f), 65504.f));
+  uint16_t b;
+  memcpy(&b, &h, 2);
+  return b;
+}
+
+// pw: fp32 [taps][cin][cout] -> device 16-bit [taps][cin/8][cout][8]
+template <typename PutU16, typename PutF32>
+bool umma_pack_weights(UmmaWeights& u, const float* pw, const float* bias, int ks, int cin, int cout, bool fp16, PutU16 put16, PutF32 put32) {
+  const int taps = ks * ks, cg = cin / 8;
+  std::vector<uint16_t> v((size_t)taps * cin * cout);
+  for (int t = 0; t < taps; ++t)
+    for (int g = 0; g < cg; ++g)
+      for (int n = 0; n < cout; ++n)
+        for (int j = 0; j < 8; ++j) {
+          const float f = pw[((size_t)t * cin + g * 8 + j) * cout + n];
+          v[(((size_t)t * cg + g) * cout + n) * 8 + j] = fp16 ? f32_to_f16_bits(f) : f32_to_bf16_bits(f);
+        }
+  std::vector<float> b(cout, 0.f);
+  if (bias) b.assign(bias, bias + cout);
+  u.w = put16(v);
+  u.bias = put32(b);
+  u.ks = ks; u.cin = cin; u.cout = cout;
+  u.packed = (u.w != nullptr && u.bias != nullptr);
+  return u.packed;
+}
+
+}  // namespace lpsr

@@ -1,0 +1,91 @@
+"""CPU: the oracle (numpy restatement) and the torch.nn.functional port against the golden vectors generated from the
+unmodified reference (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_cases, load_case
+from oracle import lpsr_oracle as orc
+from oracle import lpsr_torch_port as port
+
+SHIPPED = [c for c in golden_cases() if not c.startswith("rand_")]
+RANDOM = [c for c in golden_cases() if c.startswith("rand_")]
+
+
+def _weights_for(case, shipped):
+    if not case.startswith("rand_"):
+        return shipped
+    d = load_case(case)
+    W = orc.random_weights(int(d["seed"]))
+    if d["alphas"].size:
+        W["rdn.rdbs.0.alpha"] = np.float32(d["alphas"][0]).reshape(())
+        W["rdn.rdbs.2.alpha"] = np.float32(d["alphas"][1]).reshape(())
+    return W
+
+
+@pytest.mark.parametrize("case", SHIPPED + RANDOM)
+def test_numpy_oracle_matches_reference_golden(case, shipped_weights):
+    if "128x384" in case:
+        pytest.skip("covered by the torch port (numpy im2col of this size is slow)")
+    d = load_case(case)
+    y = orc.lpsr_forward(d["x"], _weights_for(case, shipped_weights))
+    assert y.shape == d["y"].shape
+    assert np.abs(y - d["y"]).max() <= 2e-5     # fp32 summation-order noise only
+
+
+@pytest.mark.parametrize("case", SHIPPED + RANDOM)
+def test_torch_port_matches_reference_golden(case, shipped_weights):
+    d = load_case(case)
+    W = port.to_torch_weights(_weights_for(case, shipped_weights))
+    y = port.lpsr_forward(torch.from_numpy(d["x"]), W).numpy()
+    assert y.shape == d["y"].shape
+    assert np.abs(y - d["y"]).max() <= 2e-5     # bit-identical on the generating host; ISA-dependent elsewhere
+
+
+def test_numpy_oracle_float64_agrees(shipped_weights):
+    d = load_case("u_b2_32x192")
+    y64 = orc.lpsr_forward(d["x"], shipped_weights, dtype=np.float64)
+    assert np.abs(y64 - d["y"]).max() <= 2e-5
+
+
+def test_oracle_intermediates_match_reference_hooks(shipped_weights, golden_dir):
+    t = np.load(golden_dir + "/taps_u_b1_16x32.npz")
+    taps = {}
+    y = orc.lpsr_forward(t["x"], shipped_weights, taps=taps)
+    assert np.abs(y - t["y"]).max() <= 2e-5
+    for name in ("ae.c0", "ae.enc0", "ae.enc1", "ae.dec0", "ae.dec1", "ae.out", "rdn.sfe1", "rdn.sfe2", "rdn.block0",
+                 "rdn.block1", "rdn.block2", "rdn.block3", "csar1.x_in", "csar3.x_in", "rdn.out"):
+        ref = t[name]
+        scale = max(1.0, float(np.abs(ref).max()))
+        assert taps[name].shape == ref.shape, name
+        assert np.abs(taps[name] - ref).max() <= 2e-5 * scale, name
+
+
+def test_pixel_shuffle_index_rules():
+    """unshuffle: out[n, c*4+i*2+j, h, w] = in[n, c, 2h+i, 2w+j]; shuffle is its inverse; bit exact."""
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((2, 3, 8, 12)).astype(np.float32)
+    u = orc.pixel_unshuffle(x)
+    for c in range(3):
+        for i in range(2):
+            for j in range(2):
+                assert np.array_equal(u[:, c * 4 + i * 2 + j], x[:, c, i::2, j::2])
+    assert np.array_equal(orc.pixel_shuffle(u), x)
+    assert np.array_equal(u, torch.nn.functional.pixel_unshuffle(torch.from_numpy(x), 2).numpy())
+    assert np.array_equal(orc.pixel_shuffle(u), torch.nn.functional.pixel_shuffle(torch.from_numpy(u), 2).numpy())
+
+
+def test_pad_to_multiple_of_4_never_cropped(shipped_weights):
+    d = load_case("u_b1_33x193_pad")
+    assert d["y"].shape == (1, 1, 36, 196)
+    d = load_case("u_b1_30x190_pad")
+    assert d["y"].shape == (1, 1, 32, 192)
+
+
+def test_survey_sanity_vector(shipped_weights):
+    """SURVEY.md 8c golden sanity vector (seed 1234, 2x3x64x192), first crop only to keep the numpy run short."""
+    x = torch.rand(2, 3, 64, 192, generator=torch.Generator().manual_seed(1234))
+    y = port.lpsr_forward(x, port.to_torch_weights(shipped_weights)).numpy()
+    assert abs(float(y.sum()) - 15583.47) < 0.05
+    assert np.allclose(y[0, 0, 0, :4], [0.54689, 0.60430, 0.63589, 0.61160], atol=2e-5)
+    assert np.allclose(y[1, 0, 63, 188:], [0.64432, 0.54506, 0.48248, 0.49594], atol=2e-5)
