@@ -242,7 +242,7 @@ def run_ours(args):
         kind = name.split(":")[1]
         per_kernel.setdefault(kind, [0.0, 0])
         per_kernel[kind][0] += t
-        per_kernel[kind][1] += names.count(name) if names.count(name) else 1
+        per_kernel[kind][1] += names.count(name)
     umma_ms = sum(t for n_, t in fam_ms.items() if n_.endswith(":umma_conv"))
     umma_flops = 2.0 * B * P * sum(v for k, v in UMMA_MAC_PER_PIXEL.items())
     n_umma = sum(1 for n_ in names if n_.endswith(":umma_conv"))
