@@ -15,7 +15,7 @@ namespace lpsr {
 struct UmmaWeights {
   bool packed = false;
   int ks = 0, cin = 0, cout = 0;
-  uint16_t* w = nullptr;   // [taps][cin/8][cout][8] 16-bit (bf16 or fp16)
+  uint16_t* w = nullptr;   // 16-bit (bf16 or fp16): 1x1 [cin/8][cout][8]; 3x3 [dy][cin/8][dx*cout + co][8] (dx folded into N)
   float* bias = nullptr;   // [cout] (zeros if the conv has no bias)
 };
 
@@ -29,8 +29,14 @@ inline bool umma_enabled() {
 }
 
 inline bool umma_supported(int ks, int cin, int cout) {
-  return umma_enabled() && (ks == 1 || ks == 3) && cin % 16 == 0 && cin >= 16 && cin <= 16 * kMaxChunks &&
-         (cout == 16 || cout == 32 || cout == 64);
+  if (!umma_enabled() || cin % 16 != 0 || cin < 16 || cin > 16 * kMaxChunks) return false;
+  if (ks == 1) return cout == 16 || cout == 32 || cout == 64;
+  if (ks == 3) return cout == 16 || cout == 32 || cout == 64;
+  return false;
+}
+
+// 3x3 with Cout = 16: fold the three dx taps into GEMM-N (N = 48); wider Cout: one MMA per tap
+inline bool umma_fold(int ks, int cout) { return ks == 3 && cout == 16;
 }
 
 inline uint16_t f32_to_bf16_bits(float f) {
@@ -47,18 +53,31 @@ inline uint16_t f32_to_f16_bits(float f) {
   return b;
 }
 
-// pw: fp32 [taps][cin][cout] -> device 16-bit [taps][cin/8][cout][8]
+// pw: fp32 [taps][cin][cout] (tap = dy*3+dx) -> device 16-bit, tcgen05 no-swizzle K-major core-matrix order:
+//   1x1: [cin/8][cout][8]    3x3 per-tap: [tap][cin/8][cout][8]    3x3 folded (Cout=16): [dy][cin/8][dx*cout + co][8]
 template <typename PutU16, typename PutF32>
 bool umma_pack_weights(UmmaWeights& u, const float* pw, const float* bias, int ks, int cin, int cout, bool fp16, PutU16 put16, PutF32 put32) {
   const int taps = ks * ks, cg = cin / 8;
   std::vector<uint16_t> v((size_t)taps * cin * cout);
-  for (int t = 0; t < taps; ++t)
+  auto cvt = [&](float f) { return fp16 ? f32_to_f16_bits(f) : f32_to_bf16_bits(f); };
+  if (ks == 1) {
     for (int g = 0; g < cg; ++g)
       for (int n = 0; n < cout; ++n)
-        for (int j = 0; j < 8; ++j) {
-          const float f = pw[((size_t)t * cin + g * 8 + j) * cout + n];
-          v[(((size_t)t * cg + g) * cout + n) * 8 + j] = fp16 ? f32_to_f16_bits(f) : f32_to_bf16_bits(f);
-        }
+        for (int j = 0; j < 8; ++j) v[((size_t)g * cout + n) * 8 + j] = cvt(pw[((size_t)g * 8 + j) * cout + n]);
+  } else if (!umma_fold(ks, cout)) {
+    for (int t = 0; t < 9; ++t)
+      for (int g = 0; g < cg; ++g)
+        for (int n = 0; n < cout; ++n)
+          for (int j = 0; j < 8; ++j) v[(((size_t)t * cg + g) * cout + n) * 8 + j] = cvt(pw[((size_t)t * cin + g * 8 + j) * cout + n]);
+  } else {
+    const int nf = 3 * cout;
+    for (int dy = 0; dy < 3; ++dy)
+      for (int g = 0; g < cg; ++g)
+        for (int dx = 0; dx < 3; ++dx)
+          for (int n = 0; n < cout; ++n)
+            for (int j = 0; j < 8; ++j)
+              v[(((size_t)dy * cg + g) * nf + dx * cout + n) * 8 + j] = cvt(pw[((size_t)(dy * 3 + dx) * cin + g * 8 + j) * cout + n]);
+  }
   std::vector<float> b(cout, 0.f);
   if (bias) b.assign(bias, bias + cout);
   u.w = put16(v);

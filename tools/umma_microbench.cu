@@ -1,0 +1,85 @@
+// umma_microbench.cu -- how fast does tcgen05.mma (kind::f16, M=128, K=16, SS operands, no-swizzle K-major) retire for
+// small N, as a function of how many independent TMEM accumulators the issue stream cycles through?
+// One CTA per SM, one elected thread issues `iters` MMAs, commit, wait; clock64 around.  No global loads.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o umma_microbench tools/umma_microbench.cu
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdint>
+#include <vector>
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(128, 1) bench(int N, int n_acc, int iters, int a_shift_slots, int k_per_acc, long long* out) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 48 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;  // fp16 1.0
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;");
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem = tmem_slot;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);   // fp16 in, fp32 acc
+    const uint32_t hi = (128u >> 4) | (1u << 14);
+    const uint32_t a_lo0 = ((smem_u32(smem) >> 4) & 0x3FFF) | ((uint32_t)(2048 >> 4) << 16);           // A: 128 rows, LBO 2 KB
+    const uint32_t b_lo = (((smem_u32(smem) + 8192) >> 4) & 0x3FFF) | ((uint32_t)(N * 16 >> 4) << 16);  // B: N rows
+    long long t0 = clock64();
+    const uint32_t d0 = tmem, d1 = tmem + (uint32_t)((n_acc > 1) ? N : 0);
+    const uint32_t a_lo1 = a_lo0 + (uint32_t)a_shift_slots;
+    (void)k_per_acc;
+#define MMA(D, A, ACC)                                                                                          \
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %2};\n\t" \
+               "setp.ne.b32 p, %5, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(D), \
+               "r"(A), "r"(hi), "r"(b_lo), "r"(idesc), "r"(ACC)                                               \
+               : "memory")
+    for (int i = 0; i < iters; i += 8) {
+      MMA(d0, a_lo0, i); MMA(d1, a_lo1, 1); MMA(d0, a_lo0, 1); MMA(d1, a_lo1, 1);
+      MMA(d0, a_lo0, 1); MMA(d1, a_lo1, 1); MMA(d0, a_lo0, 1); MMA(d1, a_lo1, 1);
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    long long t_issue = clock64();
+    uint32_t ok = 0;
+    while (!ok) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(&bar)) : "memory");
+    }
+    long long t1 = clock64();
+    if (blockIdx.x == 0) { out[0] = t1 - t0; out[1] = t_issue - t0; }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+int main() {
+  long long* d_out;
+  cudaMalloc(&d_out, 16);
+  cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  const int iters = 4096;
+  printf("%5s %6s %6s %6s | %10s %10s\n", "N", "n_acc", "k/acc", "shift", "clk/MMA", "issue/MMA");
+  for (int N : {16, 32, 48, 64, 96, 128, 192, 256}) {
+    for (int n_acc : {1, 2}) {
+      if (n_acc * N > 512) continue;
+      for (int kpa : {1}) {
+        for (int shift : {0, 98, 1}) {
+          bench<<<148, 128, 56 * 1024>>>(N, n_acc, iters, shift, kpa, d_out);
+          cudaError_t e = cudaDeviceSynchronize();
+          if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
+          long long h[2];
+          cudaMemcpy(h, d_out, 16, cudaMemcpyDeviceToHost);
+          printf("%5d %6d %6d %6d | %10.1f %10.1f\n", N, n_acc, kpa, shift, (double)h[0] / iters, (double)h[1] / iters);
+        }
+      }
+    }
+  }
+  return 0;
+}
