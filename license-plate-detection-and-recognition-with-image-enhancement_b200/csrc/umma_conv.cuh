@@ -1,33 +1,34 @@
-// umma_conv.cuh -- tcgen05 / TMEM implicit-GEMM convolution (3x3 and 1x1, stride 1, zero 'same' padding)
-// for the 16-bit modes.  sm_100a only.
+// umma_conv.cuh -- TMA-fed tcgen05 / TMEM implicit-GEMM convolution (3x3 and 1x1, stride 1, zero 'same' padding) for
+// the 16-bit modes.  sm_100a only.
 //
-// GEMM view: M = output pixels, K = Cin per tap row, N = Cout (1x1) or 3*Cout (3x3: the three dx taps
-// are FOLDED into N).  A (pixels x channels) is never materialised as im2col.  Each CTA stages a HALOED, linearised
-// pixel range of the NHWC input once per 16-channel K-slice into shared memory in a "channel-group planar" layout
+// GEMM view: M = output pixels, K = Cin per tap, N = Cout (or 3*Cout when the dx taps are folded into N).
+// A (pixels x channels) is never materialised as im2col:
+//   * TMA (cp.async.bulk.tensor, 4-D tiled map over the NHWC activation buffer, hardware swizzle) copies a HALOED block
+//     of full strip rows [rows][TW+2 pixels][Cbox channels] into shared memory once per work item and K-chunk; image
+//     borders (padding='same') are the TMA's out-of-bounds zero fill, negative coordinates included.
+//   * that block IS the tcgen05 K-major swizzled operand layout (row = pixel, 32/64/128 B of channels per row), with
+//     rows linearised as slot = r*(TW+2) + x.  A 3x3 tap (dy,dx) is only a different descriptor START ADDRESS
+//     (slot + dy*pitch + dx); the hardware swizzle is a function of the absolute smem address, so any row shift is legal
+//     with base_offset = 0 (verified on B200: profiles/r1_umma_swizzle_rowshift_probe.txt).  One staged block feeds all
+//     9 taps: shared memory is written once, L2->smem traffic is ~1.3x the input instead of 9x.
+//   * Cout = 16 layers fold the three dx taps into N (N = 48, 3 MMAs per K-slice instead of 9): an M=128,N=16 MMA costs
+//     the same ~45 clk as N=48 (profiles/r1_umma_mma_rate_microbench.txt), so folding is a 3x cut of tensor time there.
+//     The epilogue then forms out[q] = D[q-1,dx=0] + D[q,dx=1] + D[q+1,dx=2] with warp shuffles (row == TMEM lane ==
+//     thread); tiles overlap by 2 rows (stride 126) so only warp boundaries need a tiny smem exchange.
 //
-//        smem_A[cg (2 per K-slice)][pixel slot][8 channels = 16 bytes]
-//
-// which is exactly the tcgen05 no-swizzle K-major canonical layout with SBO = 128 B (8 rows x 16 B): row (pixel) r
-// lives at start + r*16 B, linearly, so a row shift is just a different descriptor START ADDRESS.
-//   * the dy taps are three MMAs whose A start is shifted by dy*pitch slots (same staged data, read 3x not 9x);
-//   * the dx taps are folded into N: D[q, dx*Cout+co] = sum_{dy,ci} X[q+(dy-1)*pitch, ci] * W[dy][dx][ci][co], and the
-//     epilogue forms out[q] = D[q-1, 0] + D[q, 1] + D[q+1, 2] with warp shuffles (row == TMEM lane == thread).
-//     Consecutive M-tiles overlap by 2 rows (stride 126) so only warp boundaries need a tiny smem exchange.
-//   This cuts the tensor-core smem reads 3x and the number of MMAs 3x versus one MMA per tap (N=16 MMAs are
-//   issue- and smem-bound: measured 120 clk each in the per-tap version, profiles/r1_ncu_v1_summary.md).
-//
-// Work decomposition: the image is cut into column strips of TW pixels; inside a strip pixels are linearised with
-// pitch = TW+2 (left/right halo columns, zero filled at the image border); a work item is k tiles of 126 consecutive
-// linear positions of one strip of one crop (1x1 convs: k*128 consecutive pixels of the whole batch).  Persistent
-// CTAs (one per SM) loop over items.  An item's input (all K-slices, haloed) is staged as ONE shared-memory buffer
-// (ring of 2-4 buffers), so 50-130 KB of loads are in flight per SM, and the MMA loop runs tile-outer / K-inner:
-// only two tile accumulators (2 x N fp32 TMEM columns) ping-pong between the MMA warp and two epilogue groups.
+// Work decomposition: the image is cut into column strips of TW pixels (pitch = TW+2 with the halo columns); a work item
+// is k tiles of 128 (126 when folded) consecutive linear positions of one strip of one crop (1x1 convs: k*128 consecutive
+// pixels of the whole batch, 2-D tensor map).  Persistent CTAs (one per SM) loop over items; item buffers form a ring of
+// 2-4 so 50-130 KB of TMA loads are in flight per SM.  The MMA loop runs tile-outer / K-inner: two tile accumulators
+// (2 x N fp32 TMEM columns) ping-pong between the MMA warp and two epilogue groups.
 // Warp roles (352 threads):
 //     warps 0-3, 4-7  two epilogue groups (group g owns TMEM accumulator g; TMEM lane quadrant = warp id % 4):
 //                     tcgen05.ld, dx shifted sum, bias/ReLU/residual (or the CSAR gate), 16-byte stores
 //     warp  8         MMA issuer: tcgen05.mma (M=128, N, K=16) from one elected lane, tcgen05.commit to mbarriers
-//     warps 9-10      loaders: cp.async (zero-fill = padding) into the item ring, proxy fence, mbarrier arrive
+//     warp  9         TMA producer: one elected lane arms the item's mbarrier (expect_tx) and issues the box copies
+//     warp  10        idle (keeps the register budget of the epilogue warps at 184)
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -43,16 +44,21 @@
 namespace lpsr {
 
 constexpr int kUmmaThreads = 352;       // 11 warps: 2 x 4 epilogue, 1 MMA, 2 loaders (<= 184 registers per thread)
-constexpr int kUmmaLoaderThreads = 64;
+constexpr int kUmmaMaxKChunks = 8;      // TMA boxes (K-chunks of 16/32/64 channels) per item
 constexpr int kUmmaMmaWarp = 8;
 constexpr int kUmmaFirstLoaderWarp = 9;
 constexpr int kUmmaMaxK = 16;           // max M-tiles per item
 constexpr int kUmmaMaxBufs = 4;         // item buffers in the shared-memory ring
 
 struct UmmaParams {
-  const void* in; int in_pitch;
   int n_ks;                         // K-slices of 16 channels
-  int chunk_off[kMaxChunks];        // physical channel offset of each K-slice
+  // A operand = n_chunks TMA boxes per item: chunk c has chunk_ch[c] channels (16/32/64 -> swizzle 32/64/128 B) starting at
+  // channel coordinate chunk_coff[c] of tensor map chunk_map[c], and lives at byte offset chunk_smem[c] of the item buffer
+  int n_chunks;
+  int chunk_ch[kUmmaMaxKChunks], chunk_coff[kUmmaMaxKChunks], chunk_map[kUmmaMaxKChunks];
+  uint32_t chunk_smem[kUmmaMaxKChunks];
+  int rbox;                         // 3x3: strip rows per TMA box
+  uint32_t buf_bytes;               // bytes of one item buffer (all chunks, 1024-aligned each)
   const uint16_t* w; const float* bias;
   void* out; int out_pitch, out_off;
   const void* res; int res_pitch, res_off;
@@ -60,7 +66,7 @@ struct UmmaParams {
   int k;                            // M-tiles (128 rows) per item
   int tstride;                      // valid rows per tile: 126 (3x3, tiles overlap by the 2 shuffle-halo rows) or 128
   int TW, pitch, n_strips, items_per_strip, n_items;
-  int npx;                          // pixel slots per staged item
+  int npx;                          // pixel slots per staged item (3x3: rbox*pitch, 1x1: 128*k)
   int n_bufs;                       // item buffers in the ring
   long long total_px;               // B*H*W (1x1 mode)
   // CSAR gate epilogue (mode 1, 1x1 Cout=32 only): v = sigmoid(acc + bias); out[off2 + c] = x_in[c] * v  (spatial branch)
@@ -107,6 +113,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const void* tmap) { asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory"); }
+// TMA tiled loads: box -> shared memory, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
 
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -194,10 +214,16 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(bool bf16, int N) {
 // shared-memory matrix descriptor (no swizzle, K-major; core matrix = 8 rows x 16 B contiguous):
 //   lo = (addr >> 4) | (LBO >> 4) << 16   (LBO = byte stride between the two core matrices along K)
 //   hi = (SBO >> 4) | 1 << 14             (SBO = 128 B between 8-row groups; bit 46 = sm_100 descriptor version)
+// swizzled K-major (the TMA-written A blocks): row = rowbytes (32/64/128) of channels, SBO = 8 rows, LBO unused (=1),
+//   hi |= layout << 29 (bits 61-63: 2 = 128B, 4 = 64B, 6 = 32B swizzle), base_offset = 0 for ANY row-shifted start
 __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
   return ((smem_addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
 }
 constexpr uint32_t kUmmaDescHi = (128u >> 4) | (1u << 14);
+__device__ __forceinline__ uint32_t umma_desc_hi_swizzled(uint32_t rowbytes) {
+  const uint32_t layout = rowbytes == 128 ? 2u : rowbytes == 64 ? 4u : 6u;
+  return ((8u * rowbytes) >> 4) | (1u << 14) | (layout << 29);
+}
 
 template <typename T> struct IsBf16 { static constexpr bool value = false; };
 template <> struct IsBf16<__nv_bfloat16> { static constexpr bool value = true; };
@@ -211,23 +237,27 @@ enum { kEpiPlain = 0, kEpiGate = 1 };
 //       | kConv3x3Fold (dx folded into N = 3*Cout: used for Cout = 16 where per-tap MMAs would be issue/smem bound)
 enum { kConv1x1 = 0, kConv3x3Taps = 1, kConv3x3Fold = 2 };
 
+struct UmmaTmaps { CUtensorMap m[3]; };   // by box width: [0] 16 ch (SW32), [1] 32 ch (SW64), [2] 64 ch (SW128)
+
 template <typename T, int NOUT, int MODE>
-__global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const UmmaParams p) {
+__global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid_constant__ UmmaParams p, const __grid_constant__ UmmaTmaps tm) {
   static_assert(sizeof(T) == 2, "16-bit operands");
   constexpr bool FOLD = (MODE == kConv3x3Fold);
   constexpr bool K3 = (MODE != kConv1x1);
   constexpr int NMMA = FOLD ? 3 * NOUT : NOUT;                 // GEMM-N of one MMA = TMEM columns per tile
   constexpr int NTAP = (MODE == kConv1x1) ? 1 : (FOLD ? 3 : 9);   // MMAs per K-slice
   constexpr uint32_t kTmemCols = (2 * NMMA <= 32) ? 32 : (2 * NMMA <= 64) ? 64 : (2 * NMMA <= 128) ? 128 : (2 * NMMA <= 256) ? 256 : 512;
-  extern __shared__ __align__(128) uint8_t smem[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // TMA swizzle atoms need 1024-byte aligned destinations: align the carve-up by hand
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int CG = p.n_ks * 2;                                  // 8-channel groups of the whole K extent
   const uint32_t w_bytes = (uint32_t)NTAP * CG * NMMA * 16;
-  const uint32_t buf_bytes = (uint32_t)p.npx * CG * 16;        // [cg][slot][16 B]
-  uint8_t* w_smem = smem;
-  uint8_t* a_smem = smem + ((w_bytes + 127) & ~127u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(a_smem + (size_t)p.n_bufs * buf_bytes);
+  const uint32_t buf_bytes = p.buf_bytes;                      // multiple of 1024
+  uint8_t* a_smem = smem;                                      // item buffers first (1024-aligned)
+  uint8_t* w_smem = smem + (size_t)p.n_bufs * buf_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_smem + ((w_bytes + 127) & ~127u));
   // bars[0..R) full, [R..2R) empty, [2R..2R+2) tmem_full, [2R+2..2R+4) tmem_empty, then the TMEM base address,
   // then the warp-boundary exchange buffers of the folded epilogue: [2 groups][2 parities][4 warps][2 sides][NOUT] floats
   const int R = p.n_bufs;
@@ -247,7 +277,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const UmmaPa
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < R; ++s) {
-      ptx::mbar_init(full_bar(s), kUmmaLoaderThreads);
+      ptx::mbar_init(full_bar(s), 1);                           // the producer's arrive.expect_tx; TMA completes the bytes
       ptx::mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -270,104 +300,84 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const UmmaPa
   const int rows_per_item = p.k * p.tstride;
 
   if (warp >= kUmmaFirstLoaderWarp) {
-    // =================================== loaders ===================================================
-    const int lt = threadIdx.x - kUmmaFirstLoaderWarp * 32;     // 0..63
-    const T* in = static_cast<const T*>(p.in);
-    int pending = 0;                                            // committed cp.async groups not yet signalled
-    for (int ii = 0; ii < n_my_items; ++ii) {
-      const int item = blockIdx.x + ii * gridDim.x;
-      const int buf = ii % R;
-      const uint32_t ph = (uint32_t)(ii / R) & 1u;
-      if (!ptx::mbar_try_wait(empty_bar(buf), ph ^ 1u)) {
-        // about to block on the consumer: publish everything already requested first
-        ptx::cp_async_wait<0>();
-        ptx::fence_proxy_async();
-        for (; pending > 0; --pending) ptx::mbar_arrive(full_bar((ii - pending) % R));
+    // =================================== TMA producer ==============================================
+    if (warp == kUmmaFirstLoaderWarp && ptx::elect_one()) {
+      for (int c = 0; c < 3; ++c) ptx::prefetch_tmap(&tm.m[c]);
+      uint32_t item_bytes = 0;
+      for (int c = 0; c < p.n_chunks; ++c) item_bytes += (uint32_t)p.npx * (uint32_t)p.chunk_ch[c] * 2u;
+      for (int ii = 0; ii < n_my_items; ++ii) {
+        const int item = blockIdx.x + ii * gridDim.x;
+        const int buf = ii % R;
+        const uint32_t ph = (uint32_t)(ii / R) & 1u;
         ptx::mbar_wait(empty_bar(buf), ph ^ 1u);
-      }
-      long long base_px = 0;   // 1x1: first pixel of the item
-      int n = 0, x0 = 0, qlo = 0;
-      if constexpr (K3) {
-        const int per_crop = p.n_strips * p.items_per_strip;
-        n = item / per_crop;
-        const int rem = item % per_crop;
-        const int strip = rem / p.items_per_strip, j = rem % p.items_per_strip;
-        x0 = strip * p.TW;
-        qlo = j * rows_per_item - 1 - p.pitch;                  // linear strip position held by slot 0
-      } else {
-        base_px = (long long)item * rows_per_item;
-      }
-      const uint32_t dst0 = ptx::smem_u32(a_smem + (size_t)buf * buf_bytes);
-      for (int i = lt; i < p.npx; i += kUmmaLoaderThreads) {
-        const T* src = in;
-        uint32_t nbytes = 0;
+        const uint32_t dst0 = ptx::smem_u32(a_smem + (size_t)buf * buf_bytes);
+        const uint32_t bar = full_bar(buf);
+        ptx::mbar_arrive_expect_tx(bar, item_bytes);
         if constexpr (K3) {
-          const int qq = qlo + i + 2 * p.pitch;                // >= 0
-          const int y = qq / p.pitch - 2, xs = qq % p.pitch;
-          const int x = x0 + xs - 1;
-          if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
-            src = in + ((size_t)(n * p.H + y) * p.W + x) * p.in_pitch;
-            nbytes = 16;
-          }
+          const int per_crop = p.n_strips * p.items_per_strip;
+          const int n = item / per_crop;
+          const int rem = item % per_crop;
+          const int strip = rem / p.items_per_strip, j = rem % p.items_per_strip;
+          const int qlo = j * rows_per_item - 1 - p.pitch;      // first linear strip position any tap of this item reads
+          const int y_lo = (qlo + 2 * p.pitch) / p.pitch - 2;   // floor(qlo / pitch), qlo >= -pitch-1
+          for (int c = 0; c < p.n_chunks; ++c)                   // box [rbox rows][pitch px][ch]; out-of-image = zero fill
+            ptx::tma_load_4d(dst0 + p.chunk_smem[c], &tm.m[p.chunk_map[c]], bar, p.chunk_coff[c], strip * p.TW - 1, y_lo, n);
         } else {
-          const long long px = base_px + i;
-          if (px < p.total_px) {
-            src = in + (size_t)px * p.in_pitch;
-            nbytes = 16;
-          }
+          const long long base_px = (long long)item * rows_per_item;
+          for (int c = 0; c < p.n_chunks; ++c)
+            for (int m = 0; m < p.k; ++m)                        // one 128-pixel box per tile; rows past the end are zero filled
+              ptx::tma_load_2d(dst0 + p.chunk_smem[c] + (uint32_t)m * 128u * (uint32_t)p.chunk_ch[c] * 2u, &tm.m[p.chunk_map[c]], bar,
+                               p.chunk_coff[c], (int)(base_px + (long long)m * 128));
         }
-        uint32_t dst = dst0 + (uint32_t)i * 16;
-        for (int ks = 0; ks < p.n_ks; ++ks) {
-          const T* s2 = nbytes ? src + p.chunk_off[ks] : src;
-          ptx::cp_async_16(dst, s2, nbytes);
-          ptx::cp_async_16(dst + (uint32_t)p.npx * 16, nbytes ? s2 + 8 : s2, nbytes);
-          dst += (uint32_t)p.npx * 32;
-        }
-      }
-      ptx::cp_async_commit();
-      ++pending;
-      if (pending > 1) {                                        // keep one item in flight, publish the older one
-        ptx::cp_async_wait<1>();
-        ptx::fence_proxy_async();
-        ptx::mbar_arrive(full_bar((ii + 1 - pending) % R));
-        --pending;
       }
     }
-    ptx::cp_async_wait<0>();
-    ptx::fence_proxy_async();
-    for (; pending > 0; --pending) ptx::mbar_arrive(full_bar((n_my_items - pending) % R));
   } else if (warp == kUmmaMmaWarp) {
     // =================================== MMA issuer ================================================
     // The whole warp runs the (uniform) control flow and waits; one elected lane issues MMAs and commits.
     const bool leader = ptx::elect_one();
     constexpr uint32_t idesc = umma_idesc_f16(IsBf16<T>::value, NMMA);
     const uint32_t w_lo = umma_desc_lo(ptx::smem_u32(w_smem), (uint32_t)NMMA * 16);
-    const uint32_t a_lbo = (uint32_t)p.npx * 16;
     uint32_t tile_ctr = 0;
     for (int ii = 0; ii < n_my_items; ++ii) {
       const int buf = ii % R;
       const uint32_t ph = (uint32_t)(ii / R) & 1u;
+      int slot_base = 0;                                        // slot of accumulator row 0 of tile 0, tap (0,0)
+      if constexpr (K3) {
+        const int item = blockIdx.x + ii * gridDim.x;
+        const int j = (item % (p.n_strips * p.items_per_strip)) % p.items_per_strip;
+        const int qlo = j * rows_per_item - 1 - p.pitch;
+        const int y_lo = (qlo + 2 * p.pitch) / p.pitch - 2;
+        slot_base = qlo - y_lo * p.pitch;                       // in [0, pitch)
+      }
       ptx::mbar_wait(full_bar(buf), ph);
       ptx::tc_fence_after();
-      const uint32_t a_lo_item = umma_desc_lo(ptx::smem_u32(a_smem + (size_t)buf * buf_bytes), a_lbo);
+      const uint32_t buf16 = ptx::smem_u32(a_smem + (size_t)buf * buf_bytes) >> 4;
       for (int m = 0; m < p.k; ++m, ++tile_ctr) {
         const uint32_t acc = tile_ctr & 1u;
         ptx::mbar_wait(tempty_bar(acc), ((tile_ctr >> 1) & 1u) ^ 1u);   // the epilogue group drained this accumulator
         ptx::tc_fence_after();
         if (leader) {
           const uint32_t d = tmem_base + acc * NMMA;
-          uint32_t a_lo = a_lo_item + (uint32_t)(m * p.tstride);          // slot units == 16-byte units
+          const uint32_t slot = (uint32_t)(slot_base + m * p.tstride);
           uint32_t b_lo = w_lo;
+          uint32_t first = 0;                                             // 0 only for the tile's very first MMA
 #pragma unroll 1
-          for (int ks = 0; ks < p.n_ks; ++ks) {
+          for (int c = 0; c < p.n_chunks; ++c) {
+            const uint32_t rb16 = (uint32_t)p.chunk_ch[c] >> 3;          // row bytes / 16
+            const uint32_t a_hi = umma_desc_hi_swizzled(rb16 << 4);
+            const uint32_t a0 = ((buf16 + (p.chunk_smem[c] >> 4) + slot * rb16) & 0x3FFFu) | (1u << 16);
+            const uint32_t dyshift = (uint32_t)p.pitch * rb16;
+#pragma unroll 1
+            for (int kk = 0; kk < (p.chunk_ch[c] >> 4); ++kk) {
 #pragma unroll
-            for (int t = 0; t < NTAP; ++t) {
-              // tap -> slot shift: folded: dy*pitch (dx lives in N); per-tap: dy*pitch + dx
-              const uint32_t shift = FOLD ? (uint32_t)(t * p.pitch) : (uint32_t)((t / 3) * p.pitch + (t % 3));
-              ptx::tc_mma_f16_lohi(d, a_lo + shift, kUmmaDescHi, b_lo + (uint32_t)(t * CG * NMMA), kUmmaDescHi, idesc, (uint32_t)(ks | t));
+              for (int t = 0; t < NTAP; ++t) {
+                // tap -> start shift in 16-byte units: folded: dy rows (dx lives in N); per-tap: dy rows + dx pixels
+                const uint32_t shift = FOLD ? (uint32_t)t * dyshift : (uint32_t)(t / 3) * dyshift + (uint32_t)(t % 3) * rb16;
+                ptx::tc_mma_f16_lohi(d, a0 + shift + 2u * (uint32_t)kk, a_hi, b_lo + (uint32_t)(t * CG * NMMA), kUmmaDescHi, idesc, first | (uint32_t)t);
+              }
+              first = 1;
+              b_lo += 2 * NMMA;                                           // next K-slice of the weights
             }
-            a_lo += (uint32_t)p.npx * 2;                                  // next K-slice: 2 channel-group planes
-            b_lo += 2 * NMMA;
           }
           ptx::tc_commit(tfull_bar(acc));                                 // this tile's accumulator is complete
           if (m == p.k - 1) ptx::tc_commit(empty_bar(buf));               // item buffer reusable once all MMAs retire
@@ -536,22 +546,81 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const UmmaPa
 // ---------------------------------------------------------------------------------------------------
 struct UmmaPlan {
   UmmaParams p;
+  UmmaTmaps tm;
   size_t smem_bytes;
   int grid;
 };
 
-inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvParams& cp, int num_sms) {
+typedef CUresult (*PFN_lpsr_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline PFN_lpsr_tmapEncodeTiled umma_encode_fn() {
+  static PFN_lpsr_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_lpsr_tmapEncodeTiled>(p);
+  }
+  return fn;
+}
+
+// tensor map over an NHWC activation buffer (pitch channels per pixel), box = [rows][px][ch] (4-D) or [px][ch] (2-D)
+inline const char* umma_make_tmap(CUtensorMap* out, const void* base, bool fp16, int pitch_ch, int ch_box, bool k3, int B, int H, int W,
+                                  int box_px, int box_rows, long long total_px) {
+  PFN_lpsr_tmapEncodeTiled enc = umma_encode_fn();
+  if (!enc) return "cuTensorMapEncodeTiled entry point not found";
+  const CUtensorMapSwizzle sw = ch_box == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : ch_box == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  const CUtensorMapDataType dt = fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r;
+  if (k3) {
+    const cuuint64_t gdim[4] = {(cuuint64_t)pitch_ch, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t gstr[3] = {(cuuint64_t)pitch_ch * 2, (cuuint64_t)W * pitch_ch * 2, (cuuint64_t)H * W * pitch_ch * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)ch_box, (cuuint32_t)box_px, (cuuint32_t)box_rows, 1};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    r = enc(out, dt, 4, const_cast<void*>(base), gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    const cuuint64_t gdim[2] = {(cuuint64_t)pitch_ch, (cuuint64_t)total_px};
+    const cuuint64_t gstr[1] = {(cuuint64_t)pitch_ch * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)ch_box, (cuuint32_t)box_px};
+    const cuuint32_t es[2] = {1, 1};
+    r = enc(out, dt, 2, const_cast<void*>(base), gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  return r == CUDA_SUCCESS ? nullptr : "cuTensorMapEncodeTiled failed";
+}
+
+inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvParams& cp, int num_sms, bool fp16) {
   UmmaParams& p = plan.p;
   p = UmmaParams{};
+  memset(&plan.tm, 0, sizeof plan.tm);
   const bool k3 = (w.ks == 3), fold = umma_fold(w.ks, w.cout);
-  const int N = w.cout, NMMA = fold ? 3 * N : N, ndy = fold ? 3 : (k3 ? 9 : 1);
-  p.in = cp.in; p.in_pitch = cp.in_pitch;
+  const int N = w.cout, NMMA = fold ? 3 * N : N, ntap = fold ? 3 : (k3 ? 9 : 1);
   p.n_ks = w.cin / 16;
   if (cp.n_chunks != p.n_ks) return "chunk table does not match Cin/16";
-  for (int k = 0; k < p.n_ks; ++k) p.chunk_off[k] = cp.chunk_off[k];
   if (cp.in_pitch % 8 || cp.out_pitch % 8 || cp.out_off % 8 || (cp.res && (cp.res_pitch % 8 || cp.res_off % 8))) return "pitch/offset not 16-byte aligned";
-  for (int k = 0; k < p.n_ks; ++k) if (p.chunk_off[k] % 8) return "chunk offset not 16-byte aligned";
+  if (reinterpret_cast<uintptr_t>(cp.in) % 16) return "input base not 16-byte aligned";
   if (2 * NMMA > 512) return "N too large for two TMEM accumulators";
+  // ---- K-chunks: merge runs of contiguous 16-channel slices into TMA boxes of 64 / 32 / 16 channels
+  p.n_chunks = 0;
+  for (int k = 0; k < p.n_ks;) {
+    int run = 1;
+    while (k + run < p.n_ks && cp.chunk_off[k + run] == cp.chunk_off[k] + 16 * run) ++run;
+    int off = cp.chunk_off[k];
+    if (off % 8) return "chunk offset not 16-byte aligned";
+    for (int left = run; left > 0;) {
+      const int take = left >= 4 ? 4 : left >= 2 ? 2 : 1;      // 64, 32 or 16 channels
+      if (p.n_chunks == kUmmaMaxKChunks) return "too many K-chunks";
+      p.chunk_ch[p.n_chunks] = 16 * take;
+      p.chunk_coff[p.n_chunks] = off;
+      p.chunk_map[p.n_chunks] = take == 4 ? 2 : take == 2 ? 1 : 0;
+      ++p.n_chunks;
+      off += 16 * take;
+      left -= take;
+    }
+    k += run;
+  }
   p.w = w.w; p.bias = w.bias;
   p.out = cp.out; p.out_pitch = cp.out_pitch; p.out_off = cp.out_off;
   p.res = cp.res; p.res_pitch = cp.res_pitch; p.res_off = cp.res_off;
@@ -559,34 +628,38 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
   p.total_px = (long long)cp.B * cp.H * cp.W;
   p.mode = kEpiPlain;
   p.px_per_crop = cp.H * cp.W;
-  const size_t w_bytes = ((size_t)ndy * w.cin * NMMA * 2 + 127) & ~(size_t)127;
-  const size_t fixed = w_bytes + (2 * kUmmaMaxBufs + 6) * 8 + 2 * 2 * 4 * 2 * N * 4 + 256;
+  const size_t w_bytes = ((size_t)ntap * w.cin * NMMA * 2 + 127) & ~(size_t)127;
+  const size_t fixed = w_bytes + (2 * kUmmaMaxBufs + 6) * 8 + 2 * 2 * 4 * 2 * N * 4 + 1024 /*alignment slack*/ + 256;
   const size_t smem_cap = 227 * 1024 - fixed;
-  const size_t slot_bytes = (size_t)w.cin * 2;                 // all K-slices of one pixel slot
+  auto item_buf_bytes = [&](size_t npx) {                      // every chunk is 1024-aligned inside the buffer
+    size_t b = 0;
+    for (int c = 0; c < p.n_chunks; ++c) b += (npx * p.chunk_ch[c] * 2 + 1023) & ~(size_t)1023;
+    return b;
+  };
   if (k3) {
     const int ts = fold ? 126 : 128;
     p.tstride = ts;
     // choose strip width TW (equalised over W) and tiles per item k by a cost model:
-    //   MMA/epilogue work ~ computed rows per output pixel; staging traffic ~ staged slots per output pixel;
-    //   at least 2 item buffers must fit; prefer >= 48 KB per buffer in flight
+    //   MMA/epilogue work ~ computed rows per output pixel; staging traffic ~ staged slots per output pixel
     double best_cost = 1e30;
     int best_k = 0, best_ns = 0;
     for (int ns = 1; ns <= std::max(1, (cp.W + 15) / 16); ++ns) {
       const int TW = (cp.W + ns - 1) / ns, pitch = TW + 2;
-      if (TW > 254) continue;
+      if (pitch > 256) continue;                               // TMA box dimension limit
       if (ns > 1 && TW < 24) break;
       const long long lin = (long long)cp.H * pitch;
       for (int k = 1; k <= kUmmaMaxK; ++k) {
-        const size_t npx = (size_t)((ts * k + 2 * pitch + 2 + 7) & ~7);
-        if (npx * slot_bytes * 2 > smem_cap) break;
-        if (npx * 16 >= (1u << 18)) break;                     // LBO field: 14 bits of 16-byte units
+        const int rbox = (k * ts + 3 * pitch + 1 + pitch - 1) / pitch;   // rows covering any item's tap footprint
+        if (rbox > 256) break;
+        const size_t npx = (size_t)rbox * pitch;
+        if (item_buf_bytes(npx) * 2 > smem_cap) break;
         const long long items_strip = (lin + (long long)ts * k - 1) / ((long long)ts * k);
         const long long items = items_strip * ns * cp.B;
         const double work = (double)items_strip * k * 128 / (double)(cp.H * TW);
         const double stage = (double)items_strip * (double)npx / (double)(cp.H * TW);
         const long long waves = (items + num_sms - 1) / num_sms;
         const double fill = (double)(waves * num_sms) / (double)items;
-        const double cost = fill * (0.6 * work + 0.4 * stage);
+        const double cost = fill * (0.75 * work + 0.25 * stage);
         if (cost < best_cost - 1e-9) { best_cost = cost; best_k = k; best_ns = ns; }
       }
     }
@@ -598,30 +671,44 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
     const long long lin = (long long)cp.H * p.pitch;
     p.items_per_strip = (int)((lin + (long long)ts * p.k - 1) / ((long long)ts * p.k));
     p.n_items = p.items_per_strip * p.n_strips * cp.B;
-    p.npx = (ts * p.k + 2 * p.pitch + 2 + 7) & ~7;
+    p.rbox = (p.k * ts + 3 * p.pitch + 1 + p.pitch - 1) / p.pitch;
+    p.npx = p.rbox * p.pitch;
   } else {
     p.tstride = 128;
     int best_k = 1;
     double best_cost = 1e30;
     for (int k = 1; k <= kUmmaMaxK; ++k) {
-      if ((size_t)128 * k * slot_bytes * 2 > smem_cap) break;
+      if (item_buf_bytes((size_t)128 * k) * 2 > smem_cap) break;
       const long long items = (p.total_px + 128LL * k - 1) / (128LL * k);
       const long long waves = (items + num_sms - 1) / num_sms;
       const double cost = (double)(waves * num_sms) * k * 128 / (double)p.total_px + 0.04 / k;
       if (cost < best_cost - 1e-9) { best_cost = cost; best_k = k; }
     }
     p.k = best_k;
-    p.TW = p.pitch = p.n_strips = p.items_per_strip = 0;
+    p.TW = p.pitch = p.n_strips = p.items_per_strip = p.rbox = 0;
     p.n_items = (int)((p.total_px + 128LL * p.k - 1) / (128LL * p.k));
     p.npx = 128 * p.k;
   }
-  const size_t bb = (size_t)p.npx * slot_bytes;
-  int bufs = (int)(smem_cap / bb);
+  size_t off = 0;
+  for (int c = 0; c < p.n_chunks; ++c) {
+    p.chunk_smem[c] = (uint32_t)off;
+    off += ((size_t)p.npx * p.chunk_ch[c] * 2 + 1023) & ~(size_t)1023;
+  }
+  p.buf_bytes = (uint32_t)off;
+  int bufs = (int)(smem_cap / off);
   if (bufs < 2) return "tile does not fit in shared memory";
   if (bufs > kUmmaMaxBufs) bufs = kUmmaMaxBufs;
   p.n_bufs = bufs;
-  plan.smem_bytes = w_bytes + (size_t)bufs * bb + (2 * bufs + 6) * 8 + 2 * 2 * 4 * 2 * N * 4 + 16;
+  plan.smem_bytes = (size_t)bufs * off + w_bytes + (2 * bufs + 6) * 8 + 2 * 2 * 4 * 2 * N * 4 + 1024 + 64;
   plan.grid = std::min(p.n_items, num_sms);
+  // ---- tensor maps, one per box width in use
+  bool need[3] = {false, false, false};
+  for (int c = 0; c < p.n_chunks; ++c) need[p.chunk_map[c]] = true;
+  for (int i = 0; i < 3; ++i) {
+    if (!need[i]) continue;
+    if (const char* msg = umma_make_tmap(&plan.tm.m[i], cp.in, fp16, cp.in_pitch, 16 << i, k3, cp.B, cp.H, cp.W, k3 ? p.pitch : 128, p.rbox, p.total_px))
+      return msg;
+  }
   return nullptr;
 }
 
@@ -633,7 +720,7 @@ inline const char* umma_launch_inst(const UmmaPlan& plan, cudaStream_t st) {
     if (e != cudaSuccess) return cudaGetErrorString(e);
     configured = true;
   }
-  umma_conv_kernel<T, N, MODE><<<plan.grid, kUmmaThreads, plan.smem_bytes, st>>>(plan.p);
+  umma_conv_kernel<T, N, MODE><<<plan.grid, kUmmaThreads, plan.smem_bytes, st>>>(plan.p, plan.tm);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
@@ -655,7 +742,7 @@ inline const char* umma_plan_launch(const UmmaPlan& plan, const UmmaWeights& w, 
 template <typename T>
 inline const char* umma_conv_launch(const UmmaWeights& w, const ConvParams& cp, int num_sms, cudaStream_t st) {
   UmmaPlan plan;
-  if (const char* msg = umma_plan(plan, w, cp, num_sms)) return msg;
+  if (const char* msg = umma_plan(plan, w, cp, num_sms, !IsBf16<T>::value)) return msg;
   return umma_plan_launch<T>(plan, w, st);
 }
 
