@@ -36,7 +36,8 @@ DENSE_FLOP_PER_PIXEL = 297_104          # dense-conv FLOPs per p
 UMMA_MAC_PER_PIXEL = {
     "rdn.shallowF2": 288 * 32, "rdn.gff0": 128 * 32, "rdn.gff1": 288 * 32,
     "rdb0": (288 + 432 + 576 + 720) * 16 + 96 * 32, "rdb2": (288 + 432 + 576 + 720) * 16 + 96 * 32,
-    "csar1": 2 * 288 * 32, "csar3": 2 * 288 * 32,
+    "csar1.conv_in": 2 * 288 * 32, "csar3.conv_in": 2 * 288 * 32,
+    "csar1.tail": 32 * 64 + 64 * 32 + 64 * 32, "csar3.tail": 32 * 64 + 64 * 32 + 64 * 32,   # only when the tail runs on tensor cores
 }
 CSAR_TAIL_ELEMS_PER_PIXEL = 96          # read x_in + read x + write out, 32 ch each
 
@@ -243,11 +244,15 @@ def run_ours(args):
         per_kernel.setdefault(kind, [0.0, 0])
         per_kernel[kind][0] += t
         per_kernel[kind][1] += names.count(name)
-    umma_ms = sum(t for n_, t in fam_ms.items() if n_.endswith(":umma_conv"))
-    umma_flops = 2.0 * B * P * sum(v for k, v in UMMA_MAC_PER_PIXEL.items())
-    n_umma = sum(1 for n_ in names if n_.endswith(":umma_conv"))
+    is_umma = lambda n_: n_.endswith(":umma_conv") or n_.endswith(":umma_conv_gate")
+    umma_ms = sum(t for n_, t in fam_ms.items() if is_umma(n_))
+    umma_tags = {n_.split(":")[0] for n_ in names if is_umma(n_)}
+    umma_flops = 2.0 * B * P * sum(v for k, v in UMMA_MAC_PER_PIXEL.items() if k in umma_tags)
+    n_umma = sum(1 for n_ in names if is_umma(n_))
     esz = 4 if args.precision == "fp32" else 2
-    tail_ms = sum(t for n_, t in fam_ms.items() if n_.endswith(":csar_tail"))
+    # CSAR tail = everything after conv_in: pooling, channel gate, spatial MLP, gating, conv_out, residual
+    tail_ms = sum(t for n_, t in fam_ms.items() if ".tail:" in n_)
+    n_tail = sum(1 for n_ in names if ".tail:" in n_)
     tail_bytes = 2.0 * B * P * CSAR_TAIL_ELEMS_PER_PIXEL * esz
     total_prof_ms = sum(fam_ms.values())
     if n_umma:
@@ -264,7 +269,7 @@ def run_ours(args):
         roofline = {"bound": "tensor", "kernel": "conv_direct_kernel (FFMA, fp32 parity mode)", "achieved": ach, "peak": pk["tf_sustained"],
                     "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"], "peak_kind": f"bf16 dense sustained, of {pk['src']}",
                     "traffic": None, "share_of_step": d_ms / total_prof_ms}
-    roofline_csar = {"bound": "hbm", "kernel": "csar_tail_kernel (2 launches/forward)", "achieved": tail_bytes / (tail_ms * 1e-3) / 1e9,
+    roofline_csar = {"bound": "hbm", "kernel": f"CSAR tail (pool + channel gate + spatial MLP + gating + conv_out + residual; {n_tail} launches/forward)", "achieved": tail_bytes / (tail_ms * 1e-3) / 1e9,
                      "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": tail_bytes / (tail_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
                      "peak_kind": f"copy bandwidth, of {pk['src']}", "traffic": None, "kernel_ms_per_forward": tail_ms}
     conv_frac_whole = value / world * P * DENSE_FLOP_PER_PIXEL / 1e12 / pk["tf_sustained"]

@@ -95,8 +95,10 @@ __device__ __forceinline__ size_t shuffle2_dst(int n, int y, int x, int c, int H
 struct ConvParams {
   const void* in;        // NHWC T (or NCHW fp32 when the kernel is instantiated with IN_NCHW)
   int in_pitch;          // channels per pixel of the input buffer
-  int n_chunks;          // input channels = n_chunks * CCH, gathered chunk by chunk:
-  int chunk_off[kMaxChunks];  //   physical channel offset of logical chunk k
+  int n_chunks;          // input channels = n_chunks * CCH, gathered chunk by chunk (dense concat costs no copy):
+  int chunk_off[kMaxChunks];          //   channel offset of logical chunk k inside its tensor
+  const void* chunk_ptr[kMaxChunks];  //   base of the NHWC tensor holding chunk k (nullptr: `in`)
+  int chunk_pitch[kMaxChunks];        //   channels per pixel of that tensor
   const float* w;        // packed fp32 [KS*KS][Cin][COUT] (logical channel order)
   const float* bias;     // [COUT] or nullptr
   void* out;             // NHWC T (or NCHW fp32 when OUT_SIG)

@@ -47,14 +47,14 @@ __global__ void __launch_bounds__(kThreads) conv_direct_kernel(const ConvParams 
         s_in[c * PLANE + r] = v;
       }
     } else {
-      const T* src = static_cast<const T*>(p.in);
-      const int coff = p.chunk_off[ch];
+      const T* src = static_cast<const T*>(p.chunk_ptr[ch] ? p.chunk_ptr[ch] : p.in);
+      const int coff = p.chunk_off[ch], cpitch = p.chunk_ptr[ch] ? p.chunk_pitch[ch] : p.in_pitch;
       for (int i = tid; i < CCH * SH * SW; i += kThreads) {
         const int r = i / CCH, c = i % CCH;
         const int yy = y0 + r / SW - R, xx = x0 + r % SW - R;
         float v = 0.f;
         if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W)
-          v = to_f32<T>(src[((size_t)(n * p.H + yy) * p.W + xx) * p.in_pitch + coff + c]);
+          v = to_f32<T>(src[((size_t)(n * p.H + yy) * p.W + xx) * cpitch + coff + c]);
         s_in[c * PLANE + r] = v;
       }
     }
@@ -230,6 +230,30 @@ __global__ void __launch_bounds__(kThreads) gap_partial_kernel(const T* __restri
     for (int k = 0; k < kThreads / 32; ++k) t += s_red[k * 32 + c];
     partial[((size_t)b * S + s) * 32 + c] = t;
   }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// channel gate: s_c[b][c] = sigmoid(W2 relu(W1 mean_hw(x_in[b]) + b1) + b2)   (ChannelAttention, lpsr.py:120-135)
+// one CTA of 32 threads per crop; the mean comes from gap_partial_kernel's slice sums
+// ---------------------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(32) channel_gate_kernel(const float* __restrict__ partial, int S, int P, const float* __restrict__ w1,
+                                                          const float* __restrict__ b1, const float* __restrict__ w2,
+                                                          const float* __restrict__ b2, float* __restrict__ s_c) {
+  __shared__ float s_mean[32], s_hid[8];
+  const int b = blockIdx.x, c = threadIdx.x;
+  float t = 0.f;
+  for (int s = 0; s < S; ++s) t += partial[((size_t)b * S + s) * 32 + c];
+  s_mean[c] = t / (float)P;
+  __syncwarp();
+  if (c < 8) {
+    float h = __ldg(b1 + c);
+    for (int k = 0; k < 32; ++k) h = fmaf(s_mean[k], __ldg(w1 + c * 32 + k), h);
+    s_hid[c] = fmaxf(h, 0.f);
+  }
+  __syncwarp();
+  float g = __ldg(b2 + c);
+  for (int j = 0; j < 8; ++j) g = fmaf(s_hid[j], __ldg(w2 + c * 8 + j), g);
+  s_c[(size_t)b * 32 + c] = sigmoid_f32(g);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -177,6 +177,9 @@ int pack_all(lpsr_handle* h) {
   }
   ok &= pack_conv(h, h->csar_c1, "rdn.csar.conv_in.0", F, F, 3, true);
   ok &= pack_conv(h, h->csar_c2, "rdn.csar.conv_in.2", F, F, 3, true);
+  ok &= pack_conv(h, h->csar_sa1, "rdn.csar.sa.block.0", F, 2 * F, 1, true);    // tensor-core CSAR tail (16-bit modes)
+  ok &= pack_conv(h, h->csar_sa2, "rdn.csar.sa.block.2", 2 * F, F, 1, true);
+  ok &= pack_conv(h, h->csar_co, "rdn.csar.conv_out", 2 * F, F, 1, true);
   h->ca_w1 = arena_put(h, W(h, "rdn.csar.ca.block.2.weight"));
   h->ca_b1 = arena_put(h, W(h, "rdn.csar.ca.block.2.bias"));
   h->ca_w2 = arena_put(h, W(h, "rdn.csar.ca.block.4.weight"));
@@ -198,6 +201,15 @@ int pack_all(lpsr_handle* h) {
   ok &= pack_conv(h, h->gff0, "rdn.gff.0", F * h->cfg.num_blocks, F, 1, true);
   ok &= pack_conv(h, h->gff1, "rdn.gff.1", F, F, 3, true);
   ok &= pack_conv(h, h->fin, "final_conv", F, h->cfg.out_channels, 3, true);
+  if (half_mode(h) && umma_supported(3, F, 16)) {   // tensor-core final conv: pad Cout 1 -> 16 with zero filters
+    const std::vector<float>& w = W(h, "final_conv.weight");
+    std::vector<float> pw((size_t)9 * F * 16, 0.f), pb(16, 0.f);
+    for (int ci = 0; ci < F; ++ci)
+      for (int t = 0; t < 9; ++t) pw[((size_t)t * F + ci) * 16] = w[(size_t)ci * 9 + t];
+    pb[0] = W(h, "final_conv.bias")[0];
+    ok &= umma_pack_weights(h->fin_u, pw.data(), pb.data(), 3, F, 16, h->cfg.precision == LPSR_PREC_FP16,
+                            [&](const std::vector<uint16_t>& v) { return arena_put(h, v); }, [&](const std::vector<float>& v) { return arena_put(h, v); });
+  }
   if (!ok) return fail(h, LPSR_ERR_CUDA, "weight packing failed (arena %zu/%zu bytes): %s", h->arena.used, h->arena.cap,
                        cudaGetErrorString(cudaGetLastError()));
   h->packed = true;
@@ -212,9 +224,8 @@ WsLayout ws_layout(const lpsr_handle* h, int B, int H, int W) {
   L.Hp = (H + 3) / 4 * 4;
   L.Wp = (W + 3) / 4 * 4;
   L.P = L.Hp * L.Wp;
-  int S = (592 + B - 1) / B;
+  int S = L.P / 256;   // pooling slices per crop: a function of the crop size only, so a crop's result does not depend on B
   if (S > 64) S = 64;
-  if (S > L.P / 64) S = L.P / 64;
   if (S < 1) S = 1;
   L.S = S;
   const size_t es = elem_size(h), BP = (size_t)B * L.P;
@@ -227,12 +238,20 @@ WsLayout ws_layout(const lpsr_handle* h, int B, int H, int W) {
   L.s = take(BP * 12, es);
   L.ae = take(BP * 3 + 8, es);
   L.sfe1 = take(BP * 32, es);
-  L.trunk = take(BP * kTrunkPitch, es);
+  L.x0 = take(BP * 32, es);
+  for (int r = 0; r < 2; ++r)
+    for (int i = 0; i < 4; ++i) L.grow[r][i] = take(BP * 16, es);
+  for (int i = 0; i < 4; ++i) L.f[i] = take(BP * 32, es);
   L.t = take(BP * 32, es);
   L.xin = take(BP * 32, es);
   L.g0 = take(BP * 32, es);
   L.g = take(BP * 32, es);
   L.pool = take((size_t)B * S * 32, 4);
+  L.sc = take((size_t)B * 32, 4);
+  if (half_mode(h)) {   // tensor-core CSAR tail: 64-channel hidden map and the gated concat [x_in^2*s_c | x_in*s_s]
+    L.hid = take(BP * 64, es);
+    L.gate = take(BP * 64, es);
+  }
   L.total = off;
   return L;
 }
@@ -467,10 +486,10 @@ int lpsr_debug_read_tap(lpsr_handle* h, const char* name, float* dst, int64_t ds
   const Tap taps[] = {
       {"ae.c0", L.c0, 12, 0, 12, 1},      {"ae.enc0", L.e0, 48, 0, 48, 2},   {"ae.enc1", L.e1, 48, 0, 48, 4},
       {"ae.dec0", L.d0, 12, 0, 12, 2},    {"ae.sum", L.s, 12, 0, 12, 1},     {"ae.out", L.ae, 3, 0, 3, 1},
-      {"rdn.sfe1", L.sfe1, 32, 0, 32, 1}, {"rdn.sfe2", L.trunk, kTrunkPitch, kX0, 32, 1},
-      {"rdn.block0", L.trunk, kTrunkPitch, kF0, 32, 1}, {"rdn.block1", L.trunk, kTrunkPitch, kX2, 32, 1},
-      {"rdn.block2", L.trunk, kTrunkPitch, kF2, 32, 1}, {"rdn.block3", L.trunk, kTrunkPitch, kF3, 32, 1},
-      {"rdn.cat0", L.trunk, kTrunkPitch, kX0, 96, 1},   {"csar3.x_in", L.xin, 32, 0, 32, 1},
+      {"rdn.sfe1", L.sfe1, 32, 0, 32, 1}, {"rdn.sfe2", L.x0, 32, 0, 32, 1},
+      {"rdn.block0", L.f[0], 32, 0, 32, 1}, {"rdn.block1", L.f[1], 32, 0, 32, 1},
+      {"rdn.block2", L.f[2], 32, 0, 32, 1}, {"rdn.block3", L.f[3], 32, 0, 32, 1},
+      {"rdb0.growth3", L.grow[0][3], 16, 0, 16, 1},   {"csar3.x_in", L.xin, 32, 0, 32, 1},
       {"rdn.gff0", L.g0, 32, 0, 32, 1},   {"rdn.out", L.g, 32, 0, 32, 1}};
   for (const Tap& t : taps) {
     if (strcmp(t.name, name)) continue;

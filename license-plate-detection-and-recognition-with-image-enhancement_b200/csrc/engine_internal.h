@@ -48,7 +48,8 @@ struct lpsr_handle {
   bool packed = false;
   lpsr::DeviceArena arena;
   // packed layers
-  lpsr::ConvW ae_in, ae_out, sfe1, sfe2, rdb[2][4], lff[2], csar_c1, csar_c2, gff0, gff1, fin;
+  lpsr::ConvW ae_in, ae_out, sfe1, sfe2, rdb[2][4], lff[2], csar_c1, csar_c2, csar_sa1, csar_sa2, csar_co, gff0, gff1, fin;
+  lpsr::UmmaWeights fin_u;   // final conv with Cout padded 1 -> 16 for the tensor-core path
   lpsr::DConvW dc[4];
   float *ca_w1 = nullptr, *ca_b1 = nullptr, *ca_w2 = nullptr, *ca_b2 = nullptr;
   float *sa_w1 = nullptr, *sa_b1 = nullptr, *sa_w2 = nullptr, *sa_b2 = nullptr, *co_w = nullptr, *co_b = nullptr;
@@ -82,16 +83,12 @@ inline size_t elem_size(const lpsr_handle* h) { return half_mode(h) ? 2 : 4; }
 
 
 // ---- workspace layout ----------------------------------------------------------------------------------
-// Trunk buffer channel map (pitch kTrunkPitch): every 32-channel trunk tensor and both 96-channel RDB concat
-// buffers live in ONE NHWC buffer so that dense concatenation and the final torch.cat are channel windows:
-//   [  0, 32) sfe2 = RDB#0 input     [ 32, 96) RDB#0 growth (4x16)     [ 96,128) block0 out (RDB#0)
-//   [128,160) block1 out (CSAR) = RDB#2 input   [160,224) RDB#2 growth  [224,256) block2 out (RDB#2)
-//   [256,288) block3 out (CSAR)
-constexpr int kTrunkPitch = 288;
-constexpr int kX0 = 0, kF0 = 96, kX2 = 128, kF2 = 224, kF3 = 256;
-
+// Trunk tensors: every activation is its OWN dense NHWC tensor (pitch == channels), so each layer streams contiguous
+// rows in and out:  x0 = sfe2 out (32 ch) = RDB#0 input;  grow[r][i] = growth i of RDB r (16 ch each);
+// f[0..3] = block0..3 outputs (32 ch each; f[1] is also RDB#2's input).  Dense concatenation (lpsr.py:39-40) and the final
+// torch.cat (lpsr.py:224) are channel-chunk gather lists over these tensors (ConvParams::chunk_ptr), never copies.
 struct WsLayout {
-  size_t c0, e0, e1, d0, s, ae, sfe1, trunk, t, xin, g0, g, pool, total;
+  size_t c0, e0, e1, d0, s, ae, sfe1, x0, f[4], grow[2][4], t, xin, g0, g, pool, hid, gate, sc, total;
   int Hp, Wp, P, S;
 };
 

@@ -42,18 +42,33 @@ void launch_direct(Ctx& c, const ConvParams& p) {
   if (e != cudaSuccess) c.rc = fail(c.h, LPSR_ERR_CUDA, "conv_direct<%d,%d,%d> launch: %s", KS, CCH, COUT, cudaGetErrorString(e));
 }
 
-inline ConvParams conv_params(const ConvW& w, const void* in, int in_pitch, int in_off, int cch, void* out, int out_pitch, int out_off,
-                       int B, int H, int Wd, bool relu, const void* res = nullptr, int res_pitch = 0, int res_off = 0) {
+struct Seg { const void* ptr; int pitch, off, nch; };   // nch channels [off, off+nch) of a dense NHWC tensor
+
+// input = concatenation of channel segments (possibly of different tensors), consumed in chunks of cch channels
+inline ConvParams conv_params(const ConvW& w, std::initializer_list<Seg> segs, int cch, void* out, int out_pitch, int out_off,
+                              int B, int H, int Wd, bool relu, const void* res = nullptr, int res_pitch = 0, int res_off = 0) {
   ConvParams p{};
-  p.in = in; p.in_pitch = in_pitch;
-  p.n_chunks = w.cin / cch;
-  for (int k = 0; k < p.n_chunks; ++k) p.chunk_off[k] = in_off + k * cch;
+  p.in = segs.begin()->ptr; p.in_pitch = segs.begin()->pitch;
+  p.n_chunks = 0;
+  for (const Seg& s : segs)
+    for (int c = 0; c < s.nch; c += cch) {
+      if (p.n_chunks < kMaxChunks) {
+        p.chunk_ptr[p.n_chunks] = s.ptr;
+        p.chunk_pitch[p.n_chunks] = s.pitch;
+        p.chunk_off[p.n_chunks] = s.off + c;
+      }
+      ++p.n_chunks;
+    }
   p.w = w.w; p.bias = w.b;
   p.out = out; p.out_pitch = out_pitch; p.out_off = out_off;
   p.res = res; p.res_pitch = res_pitch; p.res_off = res_off;
   p.B = B; p.H = H; p.W = Wd; p.inH = H; p.inW = Wd;
   p.relu = relu ? 1 : 0;
   return p;
+}
+inline ConvParams conv_params(const ConvW& w, const void* in, int in_pitch, int in_off, int cch, void* out, int out_pitch, int out_off,
+                              int B, int H, int Wd, bool relu, const void* res = nullptr, int res_pitch = 0, int res_off = 0) {
+  return conv_params(w, {Seg{in, in_pitch, in_off, w.cin}}, cch, out, out_pitch, out_off, B, H, Wd, relu, res, res_pitch, res_off);
 }
 
 // dense 3x3 / 1x1 conv with Cin % 16 == 0: tensor cores in the 16-bit modes, FFMA in fp32 mode
@@ -94,15 +109,18 @@ void launch_dconv(Ctx& c, const DConvW& w, const void* in, int in_pitch, void* o
 }
 
 template <typename T>
-void csar_block(Ctx& c, const WsLayout& L, char* ws, int B, int in_off, int out_off) {
+void csar_block(Ctx& c, const WsLayout& L, char* ws, int B, size_t in_t, size_t out_t, const char* tag_conv, const char* tag_tail) {
   lpsr_handle* h = c.h;
-  T* trunk = reinterpret_cast<T*>(ws + L.trunk);
+  T* xres = reinterpret_cast<T*>(ws + in_t);      // CSAR input x (dense 32-channel tensor)
+  T* yout = reinterpret_cast<T*>(ws + out_t);
   T* t = reinterpret_cast<T*>(ws + L.t);
   T* xin = reinterpret_cast<T*>(ws + L.xin);
   float* pool = reinterpret_cast<float*>(ws + L.pool);
+  c.tag = tag_conv;
   // x_in = conv_in.2(relu(conv_in.0(x)))                                               (lpsr.py:159-172,181)
-  dense_conv<T>(c, h->csar_c1, conv_params(h->csar_c1, trunk, kTrunkPitch, in_off, 16, t, 32, 0, B, L.Hp, L.Wp, true));
+  dense_conv<T>(c, h->csar_c1, conv_params(h->csar_c1, xres, 32, 0, 16, t, 32, 0, B, L.Hp, L.Wp, true));
   dense_conv<T>(c, h->csar_c2, conv_params(h->csar_c2, t, 32, 0, 16, xin, 32, 0, B, L.Hp, L.Wp, false));
+  c.tag = tag_tail;
   // AdaptiveAvgPool2d(1) partial sums                                                    (lpsr.py:124)
   c.begin("gap_partial");
   if (!c.dry && c.rc == LPSR_OK) {
@@ -111,12 +129,36 @@ void csar_block(Ctx& c, const WsLayout& L, char* ws, int B, int in_off, int out_
     if (e != cudaSuccess) c.rc = fail(h, LPSR_ERR_CUDA, "gap_partial launch: %s", cudaGetErrorString(e));
   }
   // gates + conv_out + residual                                                          (lpsr.py:182-186)
+  if constexpr (sizeof(T) == 2) {
+    if (h->csar_sa1.u.packed && h->csar_sa2.u.packed && h->csar_co.u.packed) {
+      // tensor-core tail: s_c (tiny kernel) -> 1x1 32->64 ReLU -> 1x1 64->32 with the gate epilogue -> 1x1 64->32 + x
+      T* hid = reinterpret_cast<T*>(ws + L.hid);
+      T* gate = reinterpret_cast<T*>(ws + L.gate);
+      float* sc = reinterpret_cast<float*>(ws + L.sc);
+      c.begin("channel_gate");
+      if (!c.dry && c.rc == LPSR_OK) {
+        channel_gate_kernel<<<B, 32, 0, c.st>>>(pool, L.S, L.P, h->ca_w1, h->ca_b1, h->ca_w2, h->ca_b2, sc);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) c.rc = fail(h, LPSR_ERR_CUDA, "channel_gate launch: %s", cudaGetErrorString(e));
+      }
+      dense_conv<T>(c, h->csar_sa1, conv_params(h->csar_sa1, xin, 32, 0, 16, hid, 64, 0, B, L.Hp, L.Wp, true));
+      c.begin("umma_conv_gate");
+      if (!c.dry && c.rc == LPSR_OK) {
+        UmmaGate g{xin, 32, 0, sc, 32};
+        const char* msg = umma_conv_launch<T>(h->csar_sa2.u, conv_params(h->csar_sa2, hid, 64, 0, 16, gate, 64, 0, B, L.Hp, L.Wp, false),
+                                              h->num_sms, c.st, &g);
+        if (msg) c.rc = fail(h, LPSR_ERR_CUDA, "umma_conv gate launch: %s", msg);
+      }
+      dense_conv<T>(c, h->csar_co, conv_params(h->csar_co, gate, 64, 0, 16, yout, 32, 0, B, L.Hp, L.Wp, false, xres, 32, 0));
+      return;
+    }
+  }
   c.begin("csar_tail");
   if (!c.dry && c.rc == LPSR_OK) {
     TailParams p{};
     p.x_in = xin; p.xin_pitch = 32; p.xin_off = 0;
-    p.res = trunk; p.res_pitch = kTrunkPitch; p.res_off = in_off;
-    p.out = trunk; p.out_pitch = kTrunkPitch; p.out_off = out_off;
+    p.res = xres; p.res_pitch = 32; p.res_off = 0;
+    p.out = yout; p.out_pitch = 32; p.out_off = 0;
     p.out2 = nullptr;
     p.pool_partial = pool; p.S = L.S;
     p.ca_w1 = h->ca_w1; p.ca_b1 = h->ca_b1; p.ca_w2 = h->ca_w2; p.ca_b2 = h->ca_b2;
@@ -130,16 +172,22 @@ void csar_block(Ctx& c, const WsLayout& L, char* ws, int B, int in_off, int out_
 }
 
 template <typename T>
-void rdb_block(Ctx& c, const WsLayout& L, char* ws, int B, int r, int x_off, int out_off) {
+void rdb_block(Ctx& c, const WsLayout& L, char* ws, int B, int r, size_t x_t, size_t out_t) {
   lpsr_handle* h = c.h;
-  T* trunk = reinterpret_cast<T*>(ws + L.trunk);
-  const int F = 32, G = 16;
-  // dense layers: conv3x3(cat[0 : F+G*i]) -> ReLU -> channel slice [F+G*i, F+G*(i+1)) of the same buffer (lpsr.py:31-40)
-  for (int i = 0; i < 4; ++i)
-    dense_conv<T>(c, h->rdb[r][i], conv_params(h->rdb[r][i], trunk, kTrunkPitch, x_off, 16, trunk, kTrunkPitch, x_off + F + G * i, B, L.Hp, L.Wp, true));
-  // x + alpha*lff(cat): alpha is folded into the packed lff weights/bias (lpsr.py:52-61)
-  dense_conv<T>(c, h->lff[r], conv_params(h->lff[r], trunk, kTrunkPitch, x_off, 16, trunk, kTrunkPitch, out_off, B, L.Hp, L.Wp, false,
-                                          trunk, kTrunkPitch, x_off));
+  T* x = reinterpret_cast<T*>(ws + x_t);
+  T* out = reinterpret_cast<T*>(ws + out_t);
+  T* g[4];
+  for (int i = 0; i < 4; ++i) g[i] = reinterpret_cast<T*>(ws + L.grow[r][i]);
+  // dense layers: conv3x3(cat[x, g0..g(i-1)]) -> ReLU -> its own 16-channel tensor g[i]              (lpsr.py:31-40)
+  dense_conv<T>(c, h->rdb[r][0], conv_params(h->rdb[r][0], {Seg{x, 32, 0, 32}}, 16, g[0], 16, 0, B, L.Hp, L.Wp, true));
+  dense_conv<T>(c, h->rdb[r][1], conv_params(h->rdb[r][1], {Seg{x, 32, 0, 32}, Seg{g[0], 16, 0, 16}}, 16, g[1], 16, 0, B, L.Hp, L.Wp, true));
+  dense_conv<T>(c, h->rdb[r][2], conv_params(h->rdb[r][2], {Seg{x, 32, 0, 32}, Seg{g[0], 16, 0, 16}, Seg{g[1], 16, 0, 16}}, 16, g[2], 16, 0, B,
+                                             L.Hp, L.Wp, true));
+  dense_conv<T>(c, h->rdb[r][3], conv_params(h->rdb[r][3], {Seg{x, 32, 0, 32}, Seg{g[0], 16, 0, 16}, Seg{g[1], 16, 0, 16}, Seg{g[2], 16, 0, 16}},
+                                             16, g[3], 16, 0, B, L.Hp, L.Wp, true));
+  // x + alpha*lff(cat): alpha is folded into the packed lff weights/bias                               (lpsr.py:52-61)
+  dense_conv<T>(c, h->lff[r], conv_params(h->lff[r], {Seg{x, 32, 0, 32}, Seg{g[0], 16, 0, 16}, Seg{g[1], 16, 0, 16}, Seg{g[2], 16, 0, 16},
+                                                     Seg{g[3], 16, 0, 16}}, 16, out, 32, 0, B, L.Hp, L.Wp, false, x, 32, 0));
 }
 
 template <typename T>
@@ -155,7 +203,7 @@ int forward_impl(lpsr_handle* h, const float* x, float* y, int B, int H, int W, 
   T* s = reinterpret_cast<T*>(ws + L.s);
   T* ae = reinterpret_cast<T*>(ws + L.ae);
   T* sfe1 = reinterpret_cast<T*>(ws + L.sfe1);
-  T* trunk = reinterpret_cast<T*>(ws + L.trunk);
+  T* x0 = reinterpret_cast<T*>(ws + L.x0);
   T* g0 = reinterpret_cast<T*>(ws + L.g0);
   T* g = reinterpret_cast<T*>(ws + L.g);
   const int Hp = L.Hp, Wp = L.Wp;
@@ -182,28 +230,41 @@ int forward_impl(lpsr_handle* h, const float* x, float* y, int B, int H, int W, 
   c.tag = "rdn.shallowF1";
   launch_direct<T, 7, 3, 32, false, false>(c, conv_params(h->sfe1, ae, 3, 0, 3, sfe1, 32, 0, B, Hp, Wp, false));
   c.tag = "rdn.shallowF2";
-  dense_conv<T>(c, h->sfe2, conv_params(h->sfe2, sfe1, 32, 0, 16, trunk, kTrunkPitch, kX0, B, Hp, Wp, false));
+  dense_conv<T>(c, h->sfe2, conv_params(h->sfe2, sfe1, 32, 0, 16, x0, 32, 0, B, Hp, Wp, false));
   c.tag = "rdb0";
-  rdb_block<T>(c, L, ws, B, 0, kX0, kF0);       // rdbs[0]
-  c.tag = "csar1";
-  csar_block<T>(c, L, ws, B, kF0, kX2);         // rdbs[1] = shared CSAR
+  rdb_block<T>(c, L, ws, B, 0, L.x0, L.f[0]);   // rdbs[0]
+  csar_block<T>(c, L, ws, B, L.f[0], L.f[1], "csar1.conv_in", "csar1.tail");         // rdbs[1] = shared CSAR
   c.tag = "rdb2";
-  rdb_block<T>(c, L, ws, B, 1, kX2, kF2);       // rdbs[2]
-  c.tag = "csar3";
-  csar_block<T>(c, L, ws, B, kF2, kF3);         // rdbs[3] = same CSAR weights
+  rdb_block<T>(c, L, ws, B, 1, L.f[1], L.f[2]); // rdbs[2]
+  csar_block<T>(c, L, ws, B, L.f[2], L.f[3], "csar3.conv_in", "csar3.tail");         // rdbs[3] = same CSAR weights
   c.tag = "rdn.gff0";
-  {  // gff.0 1x1 over cat(local features) = 4 channel windows of the trunk buffer (lpsr.py:207-210,224)
-    ConvParams p = conv_params(h->gff0, trunk, kTrunkPitch, 0, 16, g0, 32, 0, B, Hp, Wp, false);
-    const int offs[4] = {kF0, kX2, kF2, kF3};
-    for (int k = 0; k < 8; ++k) p.chunk_off[k] = offs[k / 2] + (k % 2) * 16;
-    dense_conv<T>(c, h->gff0, p);
+  {  // gff.0 1x1 over cat(local features): a gather list over the four block outputs, no 128-channel copy (lpsr.py:207-210,224)
+    T* f[4];
+    for (int i = 0; i < 4; ++i) f[i] = reinterpret_cast<T*>(ws + L.f[i]);
+    dense_conv<T>(c, h->gff0, conv_params(h->gff0, {Seg{f[0], 32, 0, 32}, Seg{f[1], 32, 0, 32}, Seg{f[2], 32, 0, 32}, Seg{f[3], 32, 0, 32}}, 16,
+                                          g0, 32, 0, B, Hp, Wp, false));
   }
   // gff.1 3x3 + global residual sfe1 (lpsr.py:211,224)
   c.tag = "rdn.gff1";
   dense_conv<T>(c, h->gff1, conv_params(h->gff1, g0, 32, 0, 16, g, 32, 0, B, Hp, Wp, false, sfe1, 32, 0));
   // ---- final conv + sigmoid, NCHW fp32 out (lpsr.py:273-274) -----------------------------------------------
   c.tag = "final_conv";
-  launch_direct<T, 3, 16, 1, false, true>(c, conv_params(h->fin, g, 32, 0, 16, y, 1, 0, B, Hp, Wp, false));
+  bool fin_done = false;
+  if constexpr (sizeof(T) == 2) {
+    if (h->fin_u.packed) {   // tensor cores: Cout padded to 16, folded taps, epilogue keeps channel 0 -> sigmoid -> fp32
+      c.begin("umma_conv_final");
+      fin_done = true;
+      if (!c.dry && c.rc == LPSR_OK) {
+        ConvW fw;
+        fw.ks = 3; fw.cin = 32; fw.cout = 16;
+        UmmaGate fg{};
+        fg.final_sigmoid = 1;
+        const char* msg = umma_conv_launch<T>(h->fin_u, conv_params(fw, g, 32, 0, 16, y, 1, 0, B, Hp, Wp, false), h->num_sms, c.st, &fg);
+        if (msg) c.rc = fail(h, LPSR_ERR_CUDA, "umma_conv final launch: %s", msg);
+      }
+    }
+  }
+  if (!fin_done) launch_direct<T, 3, 16, 1, false, true>(c, conv_params(h->fin, g, 32, 0, 16, y, 1, 0, B, Hp, Wp, false));
   if (n_launch) *n_launch = c.launches;
   if (prof && !dry) {   // closing event
     cudaEvent_t e;

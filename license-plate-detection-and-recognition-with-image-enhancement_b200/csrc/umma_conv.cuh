@@ -19,14 +19,13 @@
 // Work decomposition: the image is cut into column strips of TW pixels (pitch = TW+2 with the halo columns); a work item
 // is k tiles of 128 (126 when folded) consecutive linear positions of one strip of one crop (1x1 convs: k*128 consecutive
 // pixels of the whole batch, 2-D tensor map).  Persistent CTAs (one per SM) loop over items; item buffers form a ring of
-// 2-4 so 50-130 KB of TMA loads are in flight per SM.  The MMA loop runs tile-outer / K-inner: two tile accumulators
-// (2 x N fp32 TMEM columns) ping-pong between the MMA warp and two epilogue groups.
-// Warp roles (352 threads):
-//     warps 0-3, 4-7  two epilogue groups (group g owns TMEM accumulator g; TMEM lane quadrant = warp id % 4):
+// 2-4 so 50-130 KB of TMA loads are in flight per SM.  The MMA loop runs tile-outer / K-inner: G tile accumulators
+// (G x N fp32 TMEM columns) rotate between the MMA warp and G epilogue groups.
+// Warp roles ((4G+2) warps, G = kEpiGroups = 3 epilogue groups / TMEM tile accumulators):
+//     warps 0..4G-1   G epilogue groups (group g owns TMEM accumulator g; TMEM lane quadrant = warp id % 4):
 //                     tcgen05.ld, dx shifted sum, bias/ReLU/residual (or the CSAR gate), 16-byte stores
-//     warp  8         MMA issuer: tcgen05.mma (M=128, N, K=16) from one elected lane, tcgen05.commit to mbarriers
-//     warp  9         TMA producer: one elected lane arms the item's mbarrier (expect_tx) and issues the box copies
-//     warp  10        idle (keeps the register budget of the epilogue warps at 184)
+//     warp  4G        MMA issuer: tcgen05.mma (M=128, N, K=16) from one elected lane, tcgen05.commit to mbarriers
+//     warp  4G+1      TMA producer: one elected lane arms the item's mbarrier (expect_tx) and issues the box copies
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -43,10 +42,14 @@
 
 namespace lpsr {
 
-constexpr int kUmmaThreads = 352;       // 11 warps: 2 x 4 epilogue, 1 MMA, 2 loaders (<= 184 registers per thread)
+#ifndef LPSR_UMMA_EPI_GROUPS
+#define LPSR_UMMA_EPI_GROUPS 3
+#endif
+constexpr int kEpiGroups = LPSR_UMMA_EPI_GROUPS;   // epilogue groups == TMEM tile accumulators in flight
+constexpr int kUmmaThreads = (4 * kEpiGroups + 2) * 32;   // G x 4 epilogue warps, 1 MMA warp, 1 TMA producer warp
 constexpr int kUmmaMaxKChunks = 8;      // TMA boxes (K-chunks of 16/32/64 channels) per item
-constexpr int kUmmaMmaWarp = 8;
-constexpr int kUmmaFirstLoaderWarp = 9;
+constexpr int kUmmaMmaWarp = 4 * kEpiGroups;
+constexpr int kUmmaFirstLoaderWarp = 4 * kEpiGroups + 1;
 constexpr int kUmmaMaxK = 16;           // max M-tiles per item
 constexpr int kUmmaMaxBufs = 4;         // item buffers in the shared-memory ring
 
@@ -76,6 +79,7 @@ struct UmmaParams {
   const float* gate;                         // s_c [B][32]
   int out_off2;
   int px_per_crop;
+  int debug;                        // LPSR_UMMA_DEBUG bitmask (profiling experiments only): 1 skip MMAs, 2 skip stores, 4 skip TMA loads
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -104,12 +108,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must become a trap (reported as a CUDA error), never a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
-    if (spins > (1u << 26)) {
-      printf("umma_conv: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
+  if (mbar_try_wait(bar, parity)) return;
+  for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
+    if (spins > (1u << 26)) __trap();
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -228,16 +229,43 @@ __device__ __forceinline__ uint32_t umma_desc_hi_swizzled(uint32_t rowbytes) {
 template <typename T> struct IsBf16 { static constexpr bool value = false; };
 template <> struct IsBf16<__nv_bfloat16> { static constexpr bool value = true; };
 
-enum { kEpiPlain = 0, kEpiGate = 1 };
+enum { kEpiPlain = 0, kEpiGate = 1, kEpiFinalSigmoid = 2 };   // 2: out channel 0 -> sigmoid -> fp32 [pixel] (final conv, lpsr.py:273-274)
 
 // ---------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------
+// Coalesced store of one 16-channel chunk (32 bytes) per accumulator row.  Thread = row, and consecutive rows are
+// consecutive pixels of the output tensor, but a per-thread 32-byte store makes every STG.128 touch 32 different sectors
+// half-way.  Instead the warp stages its 32 rows x 32 B in shared memory and re-reads them so that each of the two store
+// instructions writes one contiguous 512-byte run (lane -> row 16j + lane/2, 16-byte half lane%2).
+template <typename T>
+__device__ __forceinline__ void store_chunk16_coalesced(T* __restrict__ out, int pitch, int off, int pix, const float (&v)[16],
+                                                        uint8_t* __restrict__ stage /*1 KB per warp*/, int lane) {
+  uint4 lo, hi;
+  {
+    T* e0 = reinterpret_cast<T*>(&lo);
+    T* e1 = reinterpret_cast<T*>(&hi);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { e0[c] = from_f32<T>(v[c]); e1[c] = from_f32<T>(v[8 + c]); }
+  }
+  __syncwarp();                                                  // previous use of the staging rows is finished
+  *reinterpret_cast<uint4*>(stage + lane * 32) = lo;
+  *reinterpret_cast<uint4*>(stage + lane * 32 + 16) = hi;
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int r = 16 * j + (lane >> 1);
+    const int rp = __shfl_sync(0xffffffffu, pix, r);
+    const uint4 d = *reinterpret_cast<const uint4*>(stage + j * 512 + lane * 16);
+    if (rp >= 0) *reinterpret_cast<uint4*>(out + (size_t)rp * pitch + off + (lane & 1) * 8) = d;
+  }
+}
+
 // MODE: kConv1x1 | kConv3x3Taps (one MMA per tap, N = Cout: used for Cout >= 32 where the MMA is already efficient)
 //       | kConv3x3Fold (dx folded into N = 3*Cout: used for Cout = 16 where per-tap MMAs would be issue/smem bound)
 enum { kConv1x1 = 0, kConv3x3Taps = 1, kConv3x3Fold = 2 };
 
-struct UmmaTmaps { CUtensorMap m[3]; };   // by box width: [0] 16 ch (SW32), [1] 32 ch (SW64), [2] 64 ch (SW128)
+struct UmmaTmaps { CUtensorMap m[kUmmaMaxKChunks]; };   // one tiled map per K-chunk (its tensor, its box width)
 
 template <typename T, int NOUT, int MODE>
 __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid_constant__ UmmaParams p, const __grid_constant__ UmmaTmaps tm) {
@@ -246,7 +274,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
   constexpr bool K3 = (MODE != kConv1x1);
   constexpr int NMMA = FOLD ? 3 * NOUT : NOUT;                 // GEMM-N of one MMA = TMEM columns per tile
   constexpr int NTAP = (MODE == kConv1x1) ? 1 : (FOLD ? 3 : 9);   // MMAs per K-slice
-  constexpr uint32_t kTmemCols = (2 * NMMA <= 32) ? 32 : (2 * NMMA <= 64) ? 64 : (2 * NMMA <= 128) ? 128 : (2 * NMMA <= 256) ? 256 : 512;
+  constexpr int G = kEpiGroups;
+  static_assert(G * NMMA <= 512, "accumulators exceed TMEM");
+  constexpr uint32_t kTmemCols = (G * NMMA <= 32) ? 32 : (G * NMMA <= 64) ? 64 : (G * NMMA <= 128) ? 128 : (G * NMMA <= 256) ? 256 : 512;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // TMA swizzle atoms need 1024-byte aligned destinations: align the carve-up by hand
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -265,9 +295,13 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (R + s); };
   auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * R + a); };
-  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * R + 2 + a); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * R + 4);
-  float* xchg = reinterpret_cast<float*>(bars + 2 * R + 6);
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * R + G + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * R + 2 * G);
+  float* xchg = reinterpret_cast<float*>(bars + 2 * R + 2 * G + 2);
+  // per-K-slice MMA operand table {A offset in 16-B units inside the item buffer, row bytes/16, descriptor hi word, dy shift/16}
+  uint4* steps = reinterpret_cast<uint4*>(xchg + (size_t)G * 2 * 4 * 2 * NOUT);
+  int* slot_base_s = reinterpret_cast<int*>(steps + kMaxChunks);   // [R] written by the producer, read by the MMA warp
+  uint8_t* stage_all = reinterpret_cast<uint8_t*>(slot_base_s + 8);  // 1 KB of store staging per epilogue warp
 
   // ---- one-time setup ------------------------------------------------------------------------------
   {
@@ -280,7 +314,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
       ptx::mbar_init(full_bar(s), 1);                           // the producer's arrive.expect_tx; TMA completes the bytes
       ptx::mbar_init(empty_bar(s), 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < G; ++a) {
       ptx::mbar_init(tfull_bar(a), 1);
       ptx::mbar_init(tempty_bar(a), 128);
     }
@@ -289,6 +323,14 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
   if (warp == kUmmaMmaWarp) {
     ptx::tmem_alloc(ptx::smem_u32(tmem_slot), kTmemCols);
     ptx::tmem_relinquish();
+    if (lane == 0) {
+      int ks = 0;
+      for (int c = 0; c < p.n_chunks; ++c) {
+        const uint32_t rb16 = (uint32_t)p.chunk_ch[c] >> 3;
+        for (int kk = 0; kk < (p.chunk_ch[c] >> 4); ++kk, ++ks)
+          steps[ks] = make_uint4((p.chunk_smem[c] >> 4) + 2u * (uint32_t)kk, rb16, umma_desc_hi_swizzled(rb16 << 4), (uint32_t)p.pitch * rb16);
+      }
+    }
   }
   ptx::fence_proxy_async();      // weights were written with st.shared: make them visible to the tensor core proxy
   ptx::tc_fence_before();
@@ -302,17 +344,17 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
   if (warp >= kUmmaFirstLoaderWarp) {
     // =================================== TMA producer ==============================================
     if (warp == kUmmaFirstLoaderWarp && ptx::elect_one()) {
-      for (int c = 0; c < 3; ++c) ptx::prefetch_tmap(&tm.m[c]);
+      for (int c = 0; c < p.n_chunks; ++c) ptx::prefetch_tmap(&tm.m[c]);
       uint32_t item_bytes = 0;
       for (int c = 0; c < p.n_chunks; ++c) item_bytes += (uint32_t)p.npx * (uint32_t)p.chunk_ch[c] * 2u;
-      for (int ii = 0; ii < n_my_items; ++ii) {
+      int buf = 0;
+      uint32_t ph = 0;
+      for (int ii = 0; ii < n_my_items; ++ii, (++buf == R ? (buf = 0, ph ^= 1u) : 0u)) {
         const int item = blockIdx.x + ii * gridDim.x;
-        const int buf = ii % R;
-        const uint32_t ph = (uint32_t)(ii / R) & 1u;
         ptx::mbar_wait(empty_bar(buf), ph ^ 1u);
         const uint32_t dst0 = ptx::smem_u32(a_smem + (size_t)buf * buf_bytes);
         const uint32_t bar = full_bar(buf);
-        ptx::mbar_arrive_expect_tx(bar, item_bytes);
+        if (p.debug & 4) { slot_base_s[buf] = 0; ptx::mbar_arrive(bar); continue; }
         if constexpr (K3) {
           const int per_crop = p.n_strips * p.items_per_strip;
           const int n = item / per_crop;
@@ -320,9 +362,12 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
           const int strip = rem / p.items_per_strip, j = rem % p.items_per_strip;
           const int qlo = j * rows_per_item - 1 - p.pitch;      // first linear strip position any tap of this item reads
           const int y_lo = (qlo + 2 * p.pitch) / p.pitch - 2;   // floor(qlo / pitch), qlo >= -pitch-1
+          slot_base_s[buf] = qlo - y_lo * p.pitch;               // slot of accumulator row 0 of tile 0 at tap (0,0); in [0, pitch)
           for (int c = 0; c < p.n_chunks; ++c)                   // box [rbox rows][pitch px][ch]; out-of-image = zero fill
             ptx::tma_load_4d(dst0 + p.chunk_smem[c], &tm.m[p.chunk_map[c]], bar, p.chunk_coff[c], strip * p.TW - 1, y_lo, n);
+          ptx::mbar_arrive_expect_tx(bar, item_bytes);            // after the slot_base store: release-orders it for the MMA warp
         } else {
+          ptx::mbar_arrive_expect_tx(bar, item_bytes);
           const long long base_px = (long long)item * rows_per_item;
           for (int c = 0; c < p.n_chunks; ++c)
             for (int m = 0; m < p.k; ++m)                        // one 128-pixel box per tile; rows past the end are zero filled
@@ -333,136 +378,141 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
     }
   } else if (warp == kUmmaMmaWarp) {
     // =================================== MMA issuer ================================================
-    // The whole warp runs the (uniform) control flow and waits; one elected lane issues MMAs and commits.
+    // The whole warp runs the (uniform) control flow and waits; one elected lane issues MMAs and commits.  The per-tile
+    // path is kept to a handful of instructions: everything shape dependent sits in the `steps` table.
     const bool leader = ptx::elect_one();
     constexpr uint32_t idesc = umma_idesc_f16(IsBf16<T>::value, NMMA);
     const uint32_t w_lo = umma_desc_lo(ptx::smem_u32(w_smem), (uint32_t)NMMA * 16);
-    uint32_t tile_ctr = 0;
+    const uint32_t cgn = (uint32_t)(CG * NMMA);               // weights: 16-byte units between taps
+    const uint32_t a_smem16 = ptx::smem_u32(a_smem) >> 4, buf16_sz = buf_bytes >> 4;
+    const int n_ks = p.n_ks, k_tiles = p.k;
+    const uint32_t tstride = (uint32_t)p.tstride;
+    const bool no_mma = (p.debug & 1) != 0;
+    __syncwarp();
+    uint32_t acc = 0, acc_par = 1;                            // accumulator ring position and the parity to wait for
+    int buf = 0;
+    uint32_t buf_par = 0;
     for (int ii = 0; ii < n_my_items; ++ii) {
-      const int buf = ii % R;
-      const uint32_t ph = (uint32_t)(ii / R) & 1u;
-      int slot_base = 0;                                        // slot of accumulator row 0 of tile 0, tap (0,0)
-      if constexpr (K3) {
-        const int item = blockIdx.x + ii * gridDim.x;
-        const int j = (item % (p.n_strips * p.items_per_strip)) % p.items_per_strip;
-        const int qlo = j * rows_per_item - 1 - p.pitch;
-        const int y_lo = (qlo + 2 * p.pitch) / p.pitch - 2;
-        slot_base = qlo - y_lo * p.pitch;                       // in [0, pitch)
-      }
-      ptx::mbar_wait(full_bar(buf), ph);
+      ptx::mbar_wait(full_bar(buf), buf_par);
       ptx::tc_fence_after();
-      const uint32_t buf16 = ptx::smem_u32(a_smem + (size_t)buf * buf_bytes) >> 4;
-      for (int m = 0; m < p.k; ++m, ++tile_ctr) {
-        const uint32_t acc = tile_ctr & 1u;
-        ptx::mbar_wait(tempty_bar(acc), ((tile_ctr >> 1) & 1u) ^ 1u);   // the epilogue group drained this accumulator
+      uint32_t slot = K3 ? (uint32_t)slot_base_s[buf] : 0u;
+      const uint32_t buf16 = a_smem16 + (uint32_t)buf * buf16_sz;
+      for (int m = 0; m < k_tiles; ++m) {
+        ptx::mbar_wait(tempty_bar(acc), acc_par);             // the epilogue group drained this accumulator
         ptx::tc_fence_after();
         if (leader) {
           const uint32_t d = tmem_base + acc * NMMA;
-          const uint32_t slot = (uint32_t)(slot_base + m * p.tstride);
           uint32_t b_lo = w_lo;
-          uint32_t first = 0;                                             // 0 only for the tile's very first MMA
+          if (!no_mma) {
 #pragma unroll 1
-          for (int c = 0; c < p.n_chunks; ++c) {
-            const uint32_t rb16 = (uint32_t)p.chunk_ch[c] >> 3;          // row bytes / 16
-            const uint32_t a_hi = umma_desc_hi_swizzled(rb16 << 4);
-            const uint32_t a0 = ((buf16 + (p.chunk_smem[c] >> 4) + slot * rb16) & 0x3FFFu) | (1u << 16);
-            const uint32_t dyshift = (uint32_t)p.pitch * rb16;
-#pragma unroll 1
-            for (int kk = 0; kk < (p.chunk_ch[c] >> 4); ++kk) {
+            for (int ks = 0; ks < n_ks; ++ks) {
+              const uint4 e = steps[ks];
+              const uint32_t a0 = (buf16 + e.x + slot * e.y) | (1u << 16);
 #pragma unroll
               for (int t = 0; t < NTAP; ++t) {
                 // tap -> start shift in 16-byte units: folded: dy rows (dx lives in N); per-tap: dy rows + dx pixels
-                const uint32_t shift = FOLD ? (uint32_t)t * dyshift : (uint32_t)(t / 3) * dyshift + (uint32_t)(t % 3) * rb16;
-                ptx::tc_mma_f16_lohi(d, a0 + shift + 2u * (uint32_t)kk, a_hi, b_lo + (uint32_t)(t * CG * NMMA), kUmmaDescHi, idesc, first | (uint32_t)t);
+                const uint32_t shift = FOLD ? (uint32_t)t * e.w : (uint32_t)(t / 3) * e.w + (uint32_t)(t % 3) * e.y;
+                ptx::tc_mma_f16_lohi(d, a0 + shift, e.z, b_lo + (uint32_t)t * cgn, kUmmaDescHi, idesc, (uint32_t)(ks | t));
               }
-              first = 1;
-              b_lo += 2 * NMMA;                                           // next K-slice of the weights
+              b_lo += 2 * NMMA;                               // next K-slice of the weights
             }
           }
-          ptx::tc_commit(tfull_bar(acc));                                 // this tile's accumulator is complete
-          if (m == p.k - 1) ptx::tc_commit(empty_bar(buf));               // item buffer reusable once all MMAs retire
+          ptx::tc_commit(tfull_bar(acc));                     // this tile's accumulator is complete
+          if (m == k_tiles - 1) ptx::tc_commit(empty_bar(buf));   // item buffer reusable once all MMAs retire
         }
         __syncwarp();
+        slot += tstride;
+        if (++acc == (uint32_t)G) { acc = 0; acc_par ^= 1u; }
       }
+      if (++buf == R) { buf = 0; buf_par ^= 1u; }
     }
   } else {
     // =================================== epilogue (two groups) ======================================
-    const int grp = warp >> 2, wq = warp & 3;                   // group == TMEM accumulator, wq == TMEM lane quadrant
+    const int grp = warp >> 2, wq = warp & 3;                   // group == TMEM accumulator (0..G-1), wq == TMEM lane quadrant
     const int row = wq * 32 + lane;                             // accumulator row
-    constexpr int CH = NOUT < 32 ? NOUT : 32;                   // output channels handled per pass (bounds registers)
-    float bias[CH];
-    if constexpr (NOUT <= 32) {
-#pragma unroll
-      for (int c = 0; c < CH; ++c) bias[c] = __ldg(p.bias + c);
-    }
+    constexpr int CH = 16;                                      // output channels handled per pass (bounds registers)
+    constexpr int NRES = NOUT <= 32 ? NOUT * 2 / 16 : 1;        // raw residual registers (uint4) prefetched per tile
     T* out = static_cast<T*>(p.out);
     const T* res = static_cast<const T*>(p.res);
     float* xg = xchg + (size_t)grp * (2 * 4 * 2 * NOUT);
+    uint8_t* stage = stage_all + (size_t)warp * 1024;
     const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(grp * NMMA);
-    uint32_t tile_ctr = 0, my_ctr = 0;
+    uint32_t my_par = 0;                                        // parity of this group's tmem_full barrier
+    int turn = 0;                                               // which group owns the next tile (round robin, same order as the MMA warp)
+    const int pitch = p.pitch, tstride = p.tstride, k_tiles = p.k;
     for (int ii = 0; ii < n_my_items; ++ii) {
       const int item = blockIdx.x + ii * gridDim.x;
-      int n = 0, x0 = 0, q0 = 0, tw = 0;
-      long long base_px = 0;
+      // per item: one division per thread; per tile the row position advances incrementally
+      int y = 0, xs = 0, tw = 0, xbase = 0;                     // K3: strip row / strip column (halo included) of this thread's row
+      long long px = 0;                                         // 1x1: pixel index of this thread's row; K3: first pixel of the crop
       if constexpr (K3) {
         const int per_crop = p.n_strips * p.items_per_strip;
-        n = item / per_crop;
-        const int rem = item % per_crop;
-        const int strip = rem / p.items_per_strip, j = rem % p.items_per_strip;
-        x0 = strip * p.TW;
-        tw = min(p.TW, p.W - x0);
-        q0 = j * rows_per_item - (FOLD ? 1 : 0);                // linear position of accumulator row 0 of tile 0
+        const int n = item / per_crop;
+        const int rem = item - n * per_crop;
+        const int strip = rem / p.items_per_strip, j = rem - strip * p.items_per_strip;
+        xbase = strip * p.TW - 1;                               // image x of strip column xs is xbase + xs
+        tw = min(p.TW, p.W - strip * p.TW);
+        const int q = j * rows_per_item - (FOLD ? 1 : 0) + row; // linear strip position of this thread's row in tile 0 (>= -1)
+        y = (q + pitch) / pitch - 1;
+        xs = q - y * pitch;
+        px = (long long)n * p.H * p.W;
       } else {
-        base_px = (long long)item * rows_per_item;
+        px = (long long)item * rows_per_item + row;
       }
-      for (int m = 0; m < p.k; ++m, ++tile_ctr) {
-        if ((int)(tile_ctr & 1u) != grp) continue;
-        // pixel of this row
+      for (int m = 0; m < k_tiles; ++m) {
+        const bool mine = (turn == grp);
+        if (++turn == G) turn = 0;
         long long pix = -1;
-        if constexpr (K3) {
-          const int q = q0 + m * p.tstride + row;               // folded: rows 0 and 127 are the shuffle halo of the tile
-          if (!FOLD || (row >= 1 && row <= 126)) {
-            const int y = q / p.pitch, xs = q - y * p.pitch;
-            if (y < p.H && xs >= 1 && xs <= tw) pix = (long long)(n * p.H + y) * p.W + (x0 + xs - 1);
+        if (mine) {
+          if constexpr (K3) {
+            // folded: rows 0 and 127 are the shuffle halo of the tile
+            if ((!FOLD || (row >= 1 && row <= 126)) && y >= 0 && y < p.H && xs >= 1 && xs <= tw) pix = px + (long long)y * p.W + (xbase + xs);
+          } else {
+            if (px < p.total_px) pix = px;
           }
-        } else {
-          const long long px = base_px + m * 128 + row;
-          if (px < p.total_px) pix = px;
         }
+        if constexpr (K3) {                                     // advance to the next tile (1-2 strip rows for the usual pitch ~ 100)
+          xs += tstride;
+          while (xs >= pitch) { xs -= pitch; ++y; }
+        } else {
+          px += 128;
+        }
+        if (!mine) continue;
         // operands that do not depend on the accumulator are requested before waiting for it
-        float rsd[CH];
+        uint4 rsd_raw[NRES];                                    // raw 16-bit residual: converted only after the accumulator arrived
         const bool has_res = (p.mode == kEpiPlain && res != nullptr && pix >= 0);
         if constexpr (NOUT <= 32) {
-          if (has_res) load_vec<T, CH>(res + (size_t)pix * p.res_pitch + p.res_off, rsd);
+          if (has_res) {
+#pragma unroll
+            for (int i = 0; i < NRES; ++i) rsd_raw[i] = *reinterpret_cast<const uint4*>(res + (size_t)pix * p.res_pitch + p.res_off + i * 8);
+          }
         }
-        ptx::mbar_wait(tfull_bar(grp), my_ctr & 1u);
+        ptx::mbar_wait(tfull_bar(grp), my_par);
         ptx::tc_fence_after();
-        float* xb = xg + (size_t)(my_ctr & 1u) * (4 * 2 * NOUT);
-        ++my_ctr;
+        float* xb = xg + (size_t)my_par * (4 * 2 * NOUT);
+        my_par ^= 1u;
 #pragma unroll
         for (int cc = 0; cc < NOUT; cc += CH) {
           float v[CH];
           if constexpr (FOLD) {
-            static_assert(!FOLD || NOUT <= 32, "folded epilogue keeps the whole tile row in registers");
             float lf[CH], rg[CH];
-#pragma unroll
-            for (int c0 = 0; c0 < CH; c0 += 16) {
-              ptx::tc_ld16_nowait(taddr + c0, &lf[c0]);
-              ptx::tc_ld16_nowait(taddr + NOUT + c0, &v[c0]);
-              ptx::tc_ld16_nowait(taddr + 2 * NOUT + c0, &rg[c0]);
-            }
+            ptx::tc_ld16_nowait(taddr + cc, lf);
+            ptx::tc_ld16_nowait(taddr + NOUT + cc, v);
+            ptx::tc_ld16_nowait(taddr + 2 * NOUT + cc, rg);
             ptx::tc_wait_ld();
-            ptx::tc_fence_before();
-            ptx::mbar_arrive(tempty_bar(grp));                  // accumulator is in registers: hand TMEM back to the MMA warp
+            if (cc + CH >= NOUT) {
+              ptx::tc_fence_before();
+              ptx::mbar_arrive(tempty_bar(grp));                // accumulator is in registers: hand TMEM back to the MMA warp
+            }
             // out[q] = D[q-1, dx=0] + D[q, dx=1] + D[q+1, dx=2]: neighbours by warp shuffle; across warp boundaries lane 31's
             // dx=0 partial / lane 0's dx=2 partial travel through a small smem exchange
             if (lane == 31) {
 #pragma unroll
-              for (int c = 0; c < CH; c += 4) *reinterpret_cast<float4*>(&xb[(wq * 2 + 0) * NOUT + c]) = make_float4(lf[c], lf[c + 1], lf[c + 2], lf[c + 3]);
+              for (int c = 0; c < CH; c += 4) *reinterpret_cast<float4*>(&xb[(wq * 2 + 0) * NOUT + cc + c]) = make_float4(lf[c], lf[c + 1], lf[c + 2], lf[c + 3]);
             }
             if (lane == 0) {
 #pragma unroll
-              for (int c = 0; c < CH; c += 4) *reinterpret_cast<float4*>(&xb[(wq * 2 + 1) * NOUT + c]) = make_float4(rg[c], rg[c + 1], rg[c + 2], rg[c + 3]);
+              for (int c = 0; c < CH; c += 4) *reinterpret_cast<float4*>(&xb[(wq * 2 + 1) * NOUT + cc + c]) = make_float4(rg[c], rg[c + 1], rg[c + 2], rg[c + 3]);
             }
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
@@ -473,14 +523,14 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
             if (lane == 0 && wq > 0) {
 #pragma unroll
               for (int c = 0; c < CH; c += 4) {
-                const float4 t = *reinterpret_cast<const float4*>(&xb[((wq - 1) * 2 + 0) * NOUT + c]);
+                const float4 t = *reinterpret_cast<const float4*>(&xb[((wq - 1) * 2 + 0) * NOUT + cc + c]);
                 lf[c] = t.x; lf[c + 1] = t.y; lf[c + 2] = t.z; lf[c + 3] = t.w;
               }
             }
             if (lane == 31 && wq < 3) {
 #pragma unroll
               for (int c = 0; c < CH; c += 4) {
-                const float4 t = *reinterpret_cast<const float4*>(&xb[((wq + 1) * 2 + 1) * NOUT + c]);
+                const float4 t = *reinterpret_cast<const float4*>(&xb[((wq + 1) * 2 + 1) * NOUT + cc + c]);
                 rg[c] = t.x; rg[c + 1] = t.y; rg[c + 2] = t.z; rg[c + 3] = t.w;
               }
             }
@@ -495,27 +545,31 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
               ptx::mbar_arrive(tempty_bar(grp));
             }
           }
-          if (pix >= 0) {
-            if constexpr (NOUT <= 32) {
+          const bool valid = pix >= 0 && !(p.debug & 2);
+          float g1[CH];                                         // gate mode: channel-branch output
+          if (valid) {
 #pragma unroll
-              for (int c = 0; c < CH; ++c) v[c] += bias[c];
-            } else {
-#pragma unroll
-              for (int c = 0; c < CH; ++c) v[c] += __ldg(p.bias + cc + c);
+            for (int c = 0; c < CH; c += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cc + c));
+              v[c] += b4.x; v[c + 1] += b4.y; v[c + 2] += b4.z; v[c + 3] += b4.w;
             }
             if (p.mode == kEpiGate) {
               // CSAR gates (1x1, NOUT = 32): spatial branch x_in * sigmoid(.), channel branch x_in^2 * s_c
               if constexpr (NOUT == 32 && MODE == kConv1x1) {
-                float xi[NOUT], g1[NOUT];
-                load_vec<T, NOUT>(static_cast<const T*>(p.aux) + (size_t)pix * p.aux_pitch + p.aux_off, xi);
-                const float* sc = p.gate + (size_t)(pix / p.px_per_crop) * NOUT;
+                float xi[CH];
+                load_vec<T, CH>(static_cast<const T*>(p.aux) + (size_t)pix * p.aux_pitch + p.aux_off + cc, xi);
+                const float4* sc4 = reinterpret_cast<const float4*>(p.gate + (size_t)(pix / p.px_per_crop) * NOUT + cc);
 #pragma unroll
-                for (int c = 0; c < NOUT; ++c) {
-                  v[c] = xi[c] * sigmoid_f32(v[c]);
-                  g1[c] = xi[c] * (xi[c] * __ldg(sc + c));
+                for (int c = 0; c < CH; c += 4) {
+                  const float4 s4 = __ldg(sc4 + c / 4);
+                  const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    // 16-bit modes: ex2.approx-based logistic (the result is rounded to bf16/fp16 anyway)
+                    v[c + j] = xi[c + j] * __fdividef(1.f, 1.f + __expf(-v[c + j]));
+                    g1[c + j] = xi[c + j] * (xi[c + j] * sv[j]);
+                  }
                 }
-                store_vec<T, NOUT>(out + (size_t)pix * p.out_pitch + p.out_off, g1);
-                store_vec<T, NOUT>(out + (size_t)pix * p.out_pitch + p.out_off2, v);
               }
             } else {
               if (p.relu) {
@@ -523,12 +577,31 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
                 for (int c = 0; c < CH; ++c) v[c] = fmaxf(v[c], 0.f);
               }
               if (has_res) {
-                if constexpr (NOUT > 32) load_vec<T, CH>(res + (size_t)pix * p.res_pitch + p.res_off + cc, rsd);
+                float r[CH];
+                if constexpr (NOUT > 32) {
+                  load_vec<T, CH>(res + (size_t)pix * p.res_pitch + p.res_off + cc, r);
+                } else {
+                  const T* re = reinterpret_cast<const T*>(rsd_raw) + cc;
 #pragma unroll
-                for (int c = 0; c < CH; ++c) v[c] += rsd[c];
+                  for (int c = 0; c < CH; ++c) r[c] = to_f32<T>(re[c]);
+                }
+#pragma unroll
+                for (int c = 0; c < CH; ++c) v[c] += r[c];
               }
-              store_vec<T, CH>(out + (size_t)pix * p.out_pitch + p.out_off + cc, v);
             }
+          }
+          // all 32 lanes take part in the staged, coalesced store (rows without a pixel are skipped inside)
+          const int pix32 = valid ? (int)pix : -1;
+          if (p.mode == kEpiFinalSigmoid) {
+            // final conv (Cout = 1, padded to 16): channel 0 only, fp32; lanes are consecutive pixels -> coalesced 4-byte stores
+            if (valid) static_cast<float*>(p.out)[pix] = __fdividef(1.f, 1.f + __expf(-v[0]));
+          } else if (p.mode == kEpiGate) {
+            if constexpr (NOUT == 32 && MODE == kConv1x1) {
+              store_chunk16_coalesced<T>(out, p.out_pitch, p.out_off + cc, pix32, g1, stage, lane);
+              store_chunk16_coalesced<T>(out, p.out_pitch, p.out_off2 + cc, pix32, v, stage, lane);
+            }
+          } else {
+            store_chunk16_coalesced<T>(out, p.out_pitch, p.out_off + cc, pix32, v, stage, lane);
           }
         }
       }
@@ -591,7 +664,7 @@ inline const char* umma_make_tmap(CUtensorMap* out, const void* base, bool fp16,
   return r == CUDA_SUCCESS ? nullptr : "cuTensorMapEncodeTiled failed";
 }
 
-inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvParams& cp, int num_sms, bool fp16) {
+inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvParams& cp, int num_sms, bool fp16, bool fp32_out = false) {
   UmmaParams& p = plan.p;
   p = UmmaParams{};
   memset(&plan.tm, 0, sizeof plan.tm);
@@ -599,22 +672,28 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
   const int N = w.cout, NMMA = fold ? 3 * N : N, ntap = fold ? 3 : (k3 ? 9 : 1);
   p.n_ks = w.cin / 16;
   if (cp.n_chunks != p.n_ks) return "chunk table does not match Cin/16";
-  if (cp.in_pitch % 8 || cp.out_pitch % 8 || cp.out_off % 8 || (cp.res && (cp.res_pitch % 8 || cp.res_off % 8))) return "pitch/offset not 16-byte aligned";
-  if (reinterpret_cast<uintptr_t>(cp.in) % 16) return "input base not 16-byte aligned";
-  if (2 * NMMA > 512) return "N too large for two TMEM accumulators";
-  // ---- K-chunks: merge runs of contiguous 16-channel slices into TMA boxes of 64 / 32 / 16 channels
+  if (!fp32_out && (cp.out_pitch % 8 || cp.out_off % 8 || (cp.res && (cp.res_pitch % 8 || cp.res_off % 8)))) return "pitch/offset not 16-byte aligned";
+  if (kEpiGroups * NMMA > 512) return "N too large for the TMEM accumulators";
+  // ---- K-chunks: merge runs of 16-channel slices that are contiguous in the SAME tensor into TMA boxes of 64 / 32 / 16 ch
+  const void* chunk_base[kUmmaMaxKChunks];
+  int chunk_pitch[kUmmaMaxKChunks];
   p.n_chunks = 0;
+  auto base_of = [&](int k) { return cp.chunk_ptr[k] ? cp.chunk_ptr[k] : cp.in; };
+  auto pitch_of = [&](int k) { return cp.chunk_ptr[k] ? cp.chunk_pitch[k] : cp.in_pitch; };
   for (int k = 0; k < p.n_ks;) {
     int run = 1;
-    while (k + run < p.n_ks && cp.chunk_off[k + run] == cp.chunk_off[k] + 16 * run) ++run;
+    while (k + run < p.n_ks && base_of(k + run) == base_of(k) && cp.chunk_off[k + run] == cp.chunk_off[k] + 16 * run) ++run;
     int off = cp.chunk_off[k];
-    if (off % 8) return "chunk offset not 16-byte aligned";
+    if (off % 8 || pitch_of(k) % 8) return "chunk offset/pitch not 16-byte aligned";
+    if (reinterpret_cast<uintptr_t>(base_of(k)) % 16) return "input base not 16-byte aligned";
     for (int left = run; left > 0;) {
       const int take = left >= 4 ? 4 : left >= 2 ? 2 : 1;      // 64, 32 or 16 channels
       if (p.n_chunks == kUmmaMaxKChunks) return "too many K-chunks";
       p.chunk_ch[p.n_chunks] = 16 * take;
       p.chunk_coff[p.n_chunks] = off;
-      p.chunk_map[p.n_chunks] = take == 4 ? 2 : take == 2 ? 1 : 0;
+      p.chunk_map[p.n_chunks] = p.n_chunks;
+      chunk_base[p.n_chunks] = base_of(k);
+      chunk_pitch[p.n_chunks] = pitch_of(k);
       ++p.n_chunks;
       off += 16 * take;
       left -= take;
@@ -626,10 +705,16 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
   p.res = cp.res; p.res_pitch = cp.res_pitch; p.res_off = cp.res_off;
   p.B = cp.B; p.H = cp.H; p.W = cp.W; p.relu = cp.relu;
   p.total_px = (long long)cp.B * cp.H * cp.W;
+  if (p.total_px >= (1LL << 31)) return "batch too large for 32-bit pixel indices (split the batch)";
   p.mode = kEpiPlain;
   p.px_per_crop = cp.H * cp.W;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("LPSR_UMMA_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.debug = dbg;
+  }
   const size_t w_bytes = ((size_t)ntap * w.cin * NMMA * 2 + 127) & ~(size_t)127;
-  const size_t fixed = w_bytes + (2 * kUmmaMaxBufs + 6) * 8 + 2 * 2 * 4 * 2 * N * 4 + 1024 /*alignment slack*/ + 256;
+  const size_t fixed = w_bytes + (2 * kUmmaMaxBufs + 2 * kEpiGroups + 2) * 8 + kEpiGroups * 2 * 4 * 2 * N * 4 + 256 /*steps, slot_base*/ + 4 * kEpiGroups * 1024 /*store staging*/ + 1024 /*alignment slack*/ + 256;
   const size_t smem_cap = 227 * 1024 - fixed;
   auto item_buf_bytes = [&](size_t npx) {                      // every chunk is 1024-aligned inside the buffer
     size_t b = 0;
@@ -699,16 +784,13 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
   if (bufs < 2) return "tile does not fit in shared memory";
   if (bufs > kUmmaMaxBufs) bufs = kUmmaMaxBufs;
   p.n_bufs = bufs;
-  plan.smem_bytes = (size_t)bufs * off + w_bytes + (2 * bufs + 6) * 8 + 2 * 2 * 4 * 2 * N * 4 + 1024 + 64;
+  plan.smem_bytes = (size_t)bufs * off + w_bytes + (2 * bufs + 2 * kEpiGroups + 2) * 8 + kEpiGroups * 2 * 4 * 2 * N * 4 + 256 + 4 * kEpiGroups * 1024 + 1024 + 64;
   plan.grid = std::min(p.n_items, num_sms);
-  // ---- tensor maps, one per box width in use
-  bool need[3] = {false, false, false};
-  for (int c = 0; c < p.n_chunks; ++c) need[p.chunk_map[c]] = true;
-  for (int i = 0; i < 3; ++i) {
-    if (!need[i]) continue;
-    if (const char* msg = umma_make_tmap(&plan.tm.m[i], cp.in, fp16, cp.in_pitch, 16 << i, k3, cp.B, cp.H, cp.W, k3 ? p.pitch : 128, p.rbox, p.total_px))
+  // ---- tensor maps, one per K-chunk
+  for (int c = 0; c < p.n_chunks; ++c)
+    if (const char* msg = umma_make_tmap(&plan.tm.m[c], chunk_base[c], fp16, chunk_pitch[c], p.chunk_ch[c], k3, cp.B, cp.H, cp.W,
+                                         k3 ? p.pitch : 128, p.rbox, p.total_px))
       return msg;
-  }
   return nullptr;
 }
 
@@ -729,7 +811,7 @@ template <typename T>
 inline const char* umma_plan_launch(const UmmaPlan& plan, const UmmaWeights& w, cudaStream_t st) {
   if (w.ks == 3) {
     if (w.cout == 16) return umma_launch_inst<T, 16, kConv3x3Fold>(plan, st);
-    if (w.cout == 32) return umma_launch_inst<T, 32, kConv3x3Taps>(plan, st);
+    if (w.cout == 32) return umma_fold(3, 32) ? umma_launch_inst<T, 32, kConv3x3Fold>(plan, st) : umma_launch_inst<T, 32, kConv3x3Taps>(plan, st);
     if (w.cout == 64) return umma_launch_inst<T, 64, kConv3x3Taps>(plan, st);
   } else {
     if (w.cout == 16) return umma_launch_inst<T, 16, kConv1x1>(plan, st);
@@ -739,14 +821,33 @@ inline const char* umma_plan_launch(const UmmaPlan& plan, const UmmaWeights& w, 
   return "unsupported Cout";
 }
 
+// special epilogue request: CSAR gate (1x1, Cout = 32) or final sigmoid (see UmmaParams::mode)
+struct UmmaGate {
+  const void* x_in; int xin_pitch, xin_off;
+  const float* s_c;        // [B][32] channel gates
+  int out_off_spatial;     // channel offset of x_in * sigmoid(.) in the output buffer (x_in^2 * s_c goes to ConvParams::out_off)
+  int final_sigmoid;       // 1: kEpiFinalSigmoid instead (ConvParams::out is a float [B*H*W] tensor)
+};
+
 template <typename T>
-inline const char* umma_conv_launch(const UmmaWeights& w, const ConvParams& cp, int num_sms, cudaStream_t st) {
+inline const char* umma_conv_launch(const UmmaWeights& w, const ConvParams& cp, int num_sms, cudaStream_t st, const UmmaGate* gate = nullptr) {
   UmmaPlan plan;
-  if (const char* msg = umma_plan(plan, w, cp, num_sms, !IsBf16<T>::value)) return msg;
+  if (const char* msg = umma_plan(plan, w, cp, num_sms, !IsBf16<T>::value, gate && gate->final_sigmoid)) return msg;
+  if (gate && gate->final_sigmoid) {
+    if (w.ks != 3 || w.cout != 16) return "final epilogue needs the folded 3x3 conv with Cout padded to 16";
+    plan.p.mode = kEpiFinalSigmoid;
+  } else if (gate) {
+    if (w.ks != 1 || w.cout != 32) return "gate epilogue needs a 1x1 conv with Cout = 32";
+    if (gate->xin_pitch % 8 || gate->xin_off % 8 || gate->out_off_spatial % 8) return "gate operands not 16-byte aligned";
+    plan.p.mode = kEpiGate;
+    plan.p.aux = gate->x_in; plan.p.aux_pitch = gate->xin_pitch; plan.p.aux_off = gate->xin_off;
+    plan.p.gate = gate->s_c;
+    plan.p.out_off2 = gate->out_off_spatial;
+  }
   return umma_plan_launch<T>(plan, w, st);
 }
 
-template <> inline const char* umma_conv_launch<float>(const UmmaWeights&, const ConvParams&, int, cudaStream_t) {
+template <> inline const char* umma_conv_launch<float>(const UmmaWeights&, const ConvParams&, int, cudaStream_t, const UmmaGate*) {
   return "tensor-core path is 16-bit only";
 }
 

@@ -36,7 +36,10 @@ inline bool umma_supported(int ks, int cin, int cout) {
 }
 
 // 3x3 with Cout = 16: fold the three dx taps into GEMM-N (N = 48); wider Cout: one MMA per tap
-inline bool umma_fold(int ks, int cout) { return ks == 3 && cout == 16;
+inline bool umma_fold(int ks, int cout) {
+  static int fold32 = -1;
+  if (fold32 < 0) { const char* e = getenv("LPSR_FOLD32"); fold32 = (e && e[0] == '1') ? 1 : 0; }
+  return ks == 3 && (cout == 16 || (cout == 32 && fold32));
 }
 
 inline uint16_t f32_to_bf16_bits(float f) {

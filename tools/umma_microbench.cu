@@ -9,14 +9,15 @@
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(128, 1) bench(int N, int n_acc, int iters, int a_shift_slots, int k_per_acc, long long* out) {
+__global__ void __launch_bounds__(128, 1) bench(int N, int n_acc, int iters, int a_shift_slots, int k_per_acc, long long* out, int rowbytes) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, bar2;
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < 48 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;  // fp16 1.0
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2)));
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   if (warp == 0) {
@@ -30,8 +31,13 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int n_acc, int iters, int
   const uint32_t tmem = tmem_slot;
   if (threadIdx.x == 0) {
     const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);   // fp16 in, fp32 acc
-    const uint32_t hi = (128u >> 4) | (1u << 14);
-    const uint32_t a_lo0 = ((smem_u32(smem) >> 4) & 0x3FFF) | ((uint32_t)(2048 >> 4) << 16);           // A: 128 rows, LBO 2 KB
+    // rowbytes == 16: no-swizzle planar (LBO 2 KB, SBO 128 B); 32/64/128: swizzled K-major rows of that width
+    const uint32_t layout = rowbytes == 128 ? 2u : rowbytes == 64 ? 4u : rowbytes == 32 ? 6u : 0u;
+    const uint32_t hi_b = (128u >> 4) | (1u << 14);
+    const uint32_t hi = rowbytes == 16 ? hi_b : (((8u * rowbytes) >> 4) | (1u << 14) | (layout << 29));
+    const uint32_t a_lo0 = rowbytes == 16 ? (((smem_u32(smem) >> 4) & 0x3FFF) | ((uint32_t)(2048 >> 4) << 16))
+                                          : ((((smem_u32(smem) + 1023) & ~1023u) >> 4) & 0x3FFF) | (1u << 16);
+    a_shift_slots *= (rowbytes == 16 ? 1 : rowbytes / 16);
     const uint32_t b_lo = (((smem_u32(smem) + 8192) >> 4) & 0x3FFF) | ((uint32_t)(N * 16 >> 4) << 16);  // B: N rows
     long long t0 = clock64();
     const uint32_t d0 = tmem, d1 = tmem + (uint32_t)((n_acc > 1) ? N : 0);
@@ -40,11 +46,30 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int n_acc, int iters, int
 #define MMA(D, A, ACC)                                                                                          \
   asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %2};\n\t" \
                "setp.ne.b32 p, %5, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(D), \
-               "r"(A), "r"(hi), "r"(b_lo), "r"(idesc), "r"(ACC)                                               \
+               "r"(A), "r"(hi), "r"(b_lo), "r"(idesc), "r"(ACC), "r"(hi_b)                                  \
                : "memory")
-    for (int i = 0; i < iters; i += 8) {
-      MMA(d0, a_lo0, i); MMA(d1, a_lo1, 1); MMA(d0, a_lo0, 1); MMA(d1, a_lo1, 1);
-      MMA(d0, a_lo0, 1); MMA(d1, a_lo1, 1); MMA(d0, a_lo0, 1); MMA(d1, a_lo1, 1);
+    // k_per_acc == 1: two fixed A tiles; k_per_acc == 2: A start walks over a 32 KB window (fresh rows for every MMA)
+    if (k_per_acc == 3) {   // 9 MMAs on one accumulator then a commit to a scratch mbarrier, alternate accumulators (the conv kernel's pattern)
+      for (int i = 0; i < iters; i += 18) {
+        for (int t = 0; t < 9; ++t) MMA(d0, a_lo0 + t, t);
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2)) : "memory");
+        for (int t = 0; t < 9; ++t) MMA(d1, a_lo1 + t, t);
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2)) : "memory");
+      }
+    } else if (k_per_acc == 1) {
+      for (int i = 0; i < iters; i += 8) {
+        MMA(d0, a_lo0, i); MMA(d1, a_lo1, 1); MMA(d0, a_lo0, 1); MMA(d1, a_lo1, 1);
+        MMA(d0, a_lo0, 1); MMA(d1, a_lo1, 1); MMA(d0, a_lo0, 1); MMA(d1, a_lo1, 1);
+      }
+    } else {
+      const uint32_t step = (uint32_t)(rowbytes == 16 ? 128 : 128 * (rowbytes / 16)) / 4;   // quarter-tile steps
+      uint32_t off = 0;
+      const uint32_t wrap = 2048 - 512 * (rowbytes == 16 ? 1 : rowbytes / 16 > 4 ? 4 : rowbytes / 16);
+      for (int i = 0; i < iters; i += 4) {
+        MMA(d0, a_lo0 + off, i); off += step; MMA(d1, a_lo0 + off, 1); off += step;
+        MMA(d0, a_lo0 + off, 1); off += step; MMA(d1, a_lo0 + off, 1); off += step;
+        if (off >= wrap) off = 0;
+      }
     }
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
     long long t_issue = clock64();
@@ -64,19 +89,21 @@ int main() {
   long long* d_out;
   cudaMalloc(&d_out, 16);
   cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-  const int iters = 4096;
-  printf("%5s %6s %6s %6s | %10s %10s\n", "N", "n_acc", "k/acc", "shift", "clk/MMA", "issue/MMA");
-  for (int N : {16, 32, 48, 64, 96, 128, 192, 256}) {
-    for (int n_acc : {1, 2}) {
+  const int iters = 4608;
+  printf("%5s %6s %6s %6s %6s | %10s %10s\n", "N", "n_acc", "rowB", "k/acc", "shift", "clk/MMA", "issue/MMA");
+  for (int N : {16, 32, 48, 96, 256}) {
+    for (int n_acc : {2}) {
       if (n_acc * N > 512) continue;
-      for (int kpa : {1}) {
-        for (int shift : {0, 98, 1}) {
-          bench<<<148, 128, 56 * 1024>>>(N, n_acc, iters, shift, kpa, d_out);
+      for (int kpa : {1, 3}) {
+        for (int shift : {99}) {
+         for (int rowbytes : {16, 64}) {
+          bench<<<148, 128, 56 * 1024>>>(N, n_acc, iters, shift, kpa, d_out, rowbytes);
           cudaError_t e = cudaDeviceSynchronize();
           if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
           long long h[2];
           cudaMemcpy(h, d_out, 16, cudaMemcpyDeviceToHost);
-          printf("%5d %6d %6d %6d | %10.1f %10.1f\n", N, n_acc, kpa, shift, (double)h[0] / iters, (double)h[1] / iters);
+          printf("%5d %6d %6d %6d %6d | %10.1f %10.1f\n", N, n_acc, rowbytes, kpa, shift, (double)h[0] / iters, (double)h[1] / iters);
+         }
         }
       }
     }
