@@ -168,6 +168,34 @@ int pack_all(lpsr_handle* h) {
     ok &= d.dw_w && d.dw_b && d.pw_w && d.pw_b;
   }
   ok &= pack_conv(h, h->sfe1, "rdn.shallowF1", C, F, 7, true);
+  h->sfe1_u.packed = false;
+  if (half_mode(h) && umma_enabled()) {
+    // 7x7 on tensor cores: K-step (dy, dx-pair) = 16 values = {pixel dx: 8 ch (3 real), pixel dx+1: 8 ch}; dx = 7 and ch >= 3 are zero
+    const std::vector<float>& w = W(h, "rdn.shallowF1.weight");   // [F][C][7][7]
+    std::vector<float> pw((size_t)448 * F, 0.f);
+    for (int dy = 0; dy < 7; ++dy)
+      for (int pr = 0; pr < 4; ++pr)
+        for (int half = 0; half < 2; ++half) {
+          const int dx = 2 * pr + half;
+          if (dx >= 7) continue;
+          for (int ci = 0; ci < C; ++ci)
+            for (int co = 0; co < F; ++co)
+              pw[((size_t)((dy * 4 + pr) * 16 + half * 8 + ci)) * F + co] = w[(((size_t)co * C + ci) * 7 + dy) * 7 + dx];
+        }
+    ok &= umma_pack_weights(h->sfe1_u, pw.data(), W(h, "rdn.shallowF1.bias").data(), 1, 448, F, h->cfg.precision == LPSR_PREC_FP16,
+                            [&](const std::vector<uint16_t>& v) { return arena_put(h, v); }, [&](const std::vector<float>& v) { return arena_put(h, v); });
+    h->sfe1_u.ks = 7;
+    // AutoEncoder conv_out 12 -> 3 padded to 8 output channels (zeros) so the 7x7 reads 16-byte pixels
+    const std::vector<float>& wo = W(h, "auto_encoder.conv_out.weight");   // [C][E][3][3]
+    std::vector<float> p8((size_t)9 * E * 8, 0.f);
+    for (int co = 0; co < C; ++co)
+      for (int ci = 0; ci < E; ++ci)
+        for (int t = 0; t < 9; ++t) p8[((size_t)t * E + ci) * 8 + co] = wo[((size_t)co * E + ci) * 9 + t];
+    h->ae_out8.ks = 3; h->ae_out8.cin = E; h->ae_out8.cout = 8;
+    h->ae_out8.w = arena_put(h, p8);
+    h->ae_out8.b = nullptr;
+    ok &= h->ae_out8.w != nullptr;
+  }
   ok &= pack_conv(h, h->sfe2, "rdn.shallowF2", F, F, 3, true);
   for (int r = 0; r < 2; ++r) {
     std::string p = "rdn.rdbs." + std::to_string(2 * r);
@@ -236,7 +264,7 @@ WsLayout ws_layout(const lpsr_handle* h, int B, int H, int W) {
   L.e1 = take(BP / 16 * 48, es);
   L.d0 = take(BP / 4 * 12, es);
   L.s = take(BP * 12, es);
-  L.ae = take(BP * 3 + 8, es);
+  L.ae = take(BP * 8, es);   // AutoEncoder output: 3 channels (pitch 3), or padded to 8 channels for the tensor-core 7x7
   L.sfe1 = take(BP * 32, es);
   L.x0 = take(BP * 32, es);
   for (int r = 0; r < 2; ++r)
@@ -485,7 +513,7 @@ int lpsr_debug_read_tap(lpsr_handle* h, const char* name, float* dst, int64_t ds
   struct Tap { const char* name; size_t off; int pitch, choff, C, div; };
   const Tap taps[] = {
       {"ae.c0", L.c0, 12, 0, 12, 1},      {"ae.enc0", L.e0, 48, 0, 48, 2},   {"ae.enc1", L.e1, 48, 0, 48, 4},
-      {"ae.dec0", L.d0, 12, 0, 12, 2},    {"ae.sum", L.s, 12, 0, 12, 1},     {"ae.out", L.ae, 3, 0, 3, 1},
+      {"ae.dec0", L.d0, 12, 0, 12, 2},    {"ae.sum", L.s, 12, 0, 12, 1},     {"ae.out", L.ae, h->sfe1_u.packed ? 8 : 3, 0, 3, 1},
       {"rdn.sfe1", L.sfe1, 32, 0, 32, 1}, {"rdn.sfe2", L.x0, 32, 0, 32, 1},
       {"rdn.block0", L.f[0], 32, 0, 32, 1}, {"rdn.block1", L.f[1], 32, 0, 32, 1},
       {"rdn.block2", L.f[2], 32, 0, 32, 1}, {"rdn.block3", L.f[3], 32, 0, 32, 1},

@@ -224,11 +224,24 @@ int forward_impl(lpsr_handle* h, const float* x, float* y, int B, int H, int W, 
   c.tag = "ae.dec1";
   launch_dconv<T, 12, 48, kShuffleUp, true>(c, h->dc[3], d0, 12, s, 12, c0, 12, B, Hp / 2, Wp / 2);          // -> c0 + [12,H,W]
   c.tag = "ae.conv_out";
-  launch_direct<T, 3, 12, 3, false, false>(c, conv_params(h->ae_out, s, 12, 0, 12, ae, 3, 0, B, Hp, Wp, false));
+  const bool sfe1_tc = (sizeof(T) == 2) && h->sfe1_u.packed;
+  if (sfe1_tc) launch_direct<T, 3, 12, 8, false, false>(c, conv_params(h->ae_out8, s, 12, 0, 12, ae, 8, 0, B, Hp, Wp, false));
+  else         launch_direct<T, 3, 12, 3, false, false>(c, conv_params(h->ae_out, s, 12, 0, 12, ae, 3, 0, B, Hp, Wp, false));
 
   // ---- RDN (lpsr.py:214-225) ---------------------------------------------------------------------------
   c.tag = "rdn.shallowF1";
-  launch_direct<T, 7, 3, 32, false, false>(c, conv_params(h->sfe1, ae, 3, 0, 3, sfe1, 32, 0, B, Hp, Wp, false));
+  if constexpr (sizeof(T) == 2) {
+    if (sfe1_tc) {
+      c.begin("umma_conv7x7");
+      if (!c.dry && c.rc == LPSR_OK) {
+        ConvW w7;
+        w7.ks = 7; w7.cin = 448; w7.cout = 32;
+        const char* msg = umma_conv_launch<T>(h->sfe1_u, conv_params(w7, {Seg{ae, 8, 0, 8}}, 8, sfe1, 32, 0, B, Hp, Wp, false), h->num_sms, c.st);
+        if (msg) c.rc = fail(h, LPSR_ERR_CUDA, "umma_conv 7x7 launch: %s", msg);
+      }
+    }
+  }
+  if (!sfe1_tc) launch_direct<T, 7, 3, 32, false, false>(c, conv_params(h->sfe1, ae, 3, 0, 3, sfe1, 32, 0, B, Hp, Wp, false));
   c.tag = "rdn.shallowF2";
   dense_conv<T>(c, h->sfe2, conv_params(h->sfe2, sfe1, 32, 0, 16, x0, 32, 0, B, Hp, Wp, false));
   c.tag = "rdb0";

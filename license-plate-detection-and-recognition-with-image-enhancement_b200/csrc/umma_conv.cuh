@@ -48,6 +48,7 @@ namespace lpsr {
 constexpr int kEpiGroups = LPSR_UMMA_EPI_GROUPS;   // epilogue groups == TMEM tile accumulators in flight
 constexpr int kUmmaThreads = (4 * kEpiGroups + 2) * 32;   // G x 4 epilogue warps, 1 MMA warp, 1 TMA producer warp
 constexpr int kUmmaMaxKChunks = 8;      // TMA boxes (K-chunks of 16/32/64 channels) per item
+constexpr int kUmmaMaxSteps = 32;       // K-steps (MMAs per tap) per tile: Cin/16, or 28 pixel-pair steps of the 7x7 conv
 constexpr int kUmmaMmaWarp = 4 * kEpiGroups;
 constexpr int kUmmaFirstLoaderWarp = 4 * kEpiGroups + 1;
 constexpr int kUmmaMaxK = 16;           // max M-tiles per item
@@ -60,7 +61,8 @@ struct UmmaParams {
   int n_chunks;
   int chunk_ch[kUmmaMaxKChunks], chunk_coff[kUmmaMaxKChunks], chunk_map[kUmmaMaxKChunks];
   uint32_t chunk_smem[kUmmaMaxKChunks];
-  int rbox;                         // 3x3: strip rows per TMA box
+  int halo;                         // strip geometry: halo columns/rows on each side (1 for 3x3, 3 for 7x7)
+  int rbox;                         // 3x3 / 7x7: strip rows per TMA box
   uint32_t buf_bytes;               // bytes of one item buffer (all chunks, 1024-aligned each)
   const uint16_t* w; const float* bias;
   void* out; int out_pitch, out_off;
@@ -263,7 +265,9 @@ __device__ __forceinline__ void store_chunk16_coalesced(T* __restrict__ out, int
 
 // MODE: kConv1x1 | kConv3x3Taps (one MMA per tap, N = Cout: used for Cout >= 32 where the MMA is already efficient)
 //       | kConv3x3Fold (dx folded into N = 3*Cout: used for Cout = 16 where per-tap MMAs would be issue/smem bound)
-enum { kConv1x1 = 0, kConv3x3Taps = 1, kConv3x3Fold = 2 };
+//       | kConv7x7 (Cin = 3 padded to 8: K = 16 is a PAIR of horizontally adjacent pixels x 8 channels; 7 dy x 4 dx-pairs = 28 MMAs,
+//         A rows are 16-byte pixels in a no-swizzle layout whose second K core-matrix is simply the next pixel, LBO = 16 B)
+enum { kConv1x1 = 0, kConv3x3Taps = 1, kConv3x3Fold = 2, kConv7x7 = 3 };
 
 struct UmmaTmaps { CUtensorMap m[kUmmaMaxKChunks]; };   // one tiled map per K-chunk (its tensor, its box width)
 
@@ -273,7 +277,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
   constexpr bool FOLD = (MODE == kConv3x3Fold);
   constexpr bool K3 = (MODE != kConv1x1);
   constexpr int NMMA = FOLD ? 3 * NOUT : NOUT;                 // GEMM-N of one MMA = TMEM columns per tile
-  constexpr int NTAP = (MODE == kConv1x1) ? 1 : (FOLD ? 3 : 9);   // MMAs per K-slice
+  constexpr int NTAP = (MODE == kConv1x1 || MODE == kConv7x7) ? 1 : (FOLD ? 3 : 9);   // MMAs per K-step
   constexpr int G = kEpiGroups;
   static_assert(G * NMMA <= 512, "accumulators exceed TMEM");
   constexpr uint32_t kTmemCols = (G * NMMA <= 32) ? 32 : (G * NMMA <= 64) ? 64 : (G * NMMA <= 128) ? 128 : (G * NMMA <= 256) ? 256 : 512;
@@ -300,7 +304,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
   float* xchg = reinterpret_cast<float*>(bars + 2 * R + 2 * G + 2);
   // per-K-slice MMA operand table {A offset in 16-B units inside the item buffer, row bytes/16, descriptor hi word, dy shift/16}
   uint4* steps = reinterpret_cast<uint4*>(xchg + (size_t)G * 2 * 4 * 2 * NOUT);
-  int* slot_base_s = reinterpret_cast<int*>(steps + kMaxChunks);   // [R] written by the producer, read by the MMA warp
+  int* slot_base_s = reinterpret_cast<int*>(steps + kUmmaMaxSteps);   // [R] written by the producer, read by the MMA warp
   uint8_t* stage_all = reinterpret_cast<uint8_t*>(slot_base_s + 8);  // 1 KB of store staging per epilogue warp
 
   // ---- one-time setup ------------------------------------------------------------------------------
@@ -323,7 +327,11 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
   if (warp == kUmmaMmaWarp) {
     ptx::tmem_alloc(ptx::smem_u32(tmem_slot), kTmemCols);
     ptx::tmem_relinquish();
-    if (lane == 0) {
+    if (lane == 0 && MODE == kConv7x7) {
+      // step (dy, dx-pair): A start shifts by dy strip rows + 2*pair pixels; rows are 16-byte pixels (no swizzle, LBO = next pixel)
+      for (int dy = 0; dy < 7; ++dy)
+        for (int pr = 0; pr < 4; ++pr) steps[dy * 4 + pr] = make_uint4((uint32_t)(dy * p.pitch + 2 * pr), 1u, kUmmaDescHi, 0u);
+    } else if (lane == 0) {
       int ks = 0;
       for (int c = 0; c < p.n_chunks; ++c) {
         const uint32_t rb16 = (uint32_t)p.chunk_ch[c] >> 3;
@@ -360,11 +368,11 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
           const int n = item / per_crop;
           const int rem = item % per_crop;
           const int strip = rem / p.items_per_strip, j = rem % p.items_per_strip;
-          const int qlo = j * rows_per_item - 1 - p.pitch;      // first linear strip position any tap of this item reads
-          const int y_lo = (qlo + 2 * p.pitch) / p.pitch - 2;   // floor(qlo / pitch), qlo >= -pitch-1
+          const int qlo = j * rows_per_item - p.halo * (p.pitch + 1);   // first linear strip position any tap of this item reads
+          const int y_lo = (qlo + (p.halo + 1) * p.pitch) / p.pitch - (p.halo + 1);   // floor(qlo / pitch), qlo >= -halo*(pitch+1)
           slot_base_s[buf] = qlo - y_lo * p.pitch;               // slot of accumulator row 0 of tile 0 at tap (0,0); in [0, pitch)
           for (int c = 0; c < p.n_chunks; ++c)                   // box [rbox rows][pitch px][ch]; out-of-image = zero fill
-            ptx::tma_load_4d(dst0 + p.chunk_smem[c], &tm.m[p.chunk_map[c]], bar, p.chunk_coff[c], strip * p.TW - 1, y_lo, n);
+            ptx::tma_load_4d(dst0 + p.chunk_smem[c], &tm.m[p.chunk_map[c]], bar, p.chunk_coff[c], strip * p.TW - p.halo, y_lo, n);
           ptx::mbar_arrive_expect_tx(bar, item_bytes);            // after the slot_base store: release-orders it for the MMA warp
         } else {
           ptx::mbar_arrive_expect_tx(bar, item_bytes);
@@ -450,7 +458,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
         const int n = item / per_crop;
         const int rem = item - n * per_crop;
         const int strip = rem / p.items_per_strip, j = rem - strip * p.items_per_strip;
-        xbase = strip * p.TW - 1;                               // image x of strip column xs is xbase + xs
+        xbase = strip * p.TW - p.halo;                          // image x of strip column xs is xbase + xs
         tw = min(p.TW, p.W - strip * p.TW);
         const int q = j * rows_per_item - (FOLD ? 1 : 0) + row; // linear strip position of this thread's row in tile 0 (>= -1)
         y = (q + pitch) / pitch - 1;
@@ -466,7 +474,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
         if (mine) {
           if constexpr (K3) {
             // folded: rows 0 and 127 are the shuffle halo of the tile
-            if ((!FOLD || (row >= 1 && row <= 126)) && y >= 0 && y < p.H && xs >= 1 && xs <= tw) pix = px + (long long)y * p.W + (xbase + xs);
+            if ((!FOLD || (row >= 1 && row <= 126)) && y >= 0 && y < p.H && xs >= p.halo && xs < p.halo + tw) pix = px + (long long)y * p.W + (xbase + xs);
           } else {
             if (px < p.total_px) pix = px;
           }
@@ -643,7 +651,8 @@ inline const char* umma_make_tmap(CUtensorMap* out, const void* base, bool fp16,
                                   int box_px, int box_rows, long long total_px) {
   PFN_lpsr_tmapEncodeTiled enc = umma_encode_fn();
   if (!enc) return "cuTensorMapEncodeTiled entry point not found";
-  const CUtensorMapSwizzle sw = ch_box == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : ch_box == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  const CUtensorMapSwizzle sw = ch_box == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : ch_box == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : ch_box == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
   const CUtensorMapDataType dt = fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   CUresult r;
   if (k3) {
@@ -668,10 +677,14 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
   UmmaParams& p = plan.p;
   p = UmmaParams{};
   memset(&plan.tm, 0, sizeof plan.tm);
-  const bool k3 = (w.ks == 3), fold = umma_fold(w.ks, w.cout);
-  const int N = w.cout, NMMA = fold ? 3 * N : N, ntap = fold ? 3 : (k3 ? 9 : 1);
-  p.n_ks = w.cin / 16;
-  if (cp.n_chunks != p.n_ks) return "chunk table does not match Cin/16";
+  const bool c7 = (w.ks == 7);
+  const bool k3 = (w.ks == 3) || c7, fold = umma_fold(w.ks, w.cout);
+  const int N = w.cout, NMMA = fold ? 3 * N : N, ntap = fold ? 3 : (w.ks == 3 ? 9 : 1);
+  const int halo = c7 ? 3 : 1;
+  p.halo = halo;
+  p.n_ks = w.cin / 16;                                       // 7x7: 28 pixel-pair steps (UmmaWeights::cin = 448 pseudo channels)
+  if (p.n_ks > kUmmaMaxSteps) return "too many K-steps";
+  if (!c7 && cp.n_chunks != p.n_ks) return "chunk table does not match Cin/16";
   if (!fp32_out && (cp.out_pitch % 8 || cp.out_off % 8 || (cp.res && (cp.res_pitch % 8 || cp.res_off % 8)))) return "pitch/offset not 16-byte aligned";
   if (kEpiGroups * NMMA > 512) return "N too large for the TMEM accumulators";
   // ---- K-chunks: merge runs of 16-channel slices that are contiguous in the SAME tensor into TMA boxes of 64 / 32 / 16 ch
@@ -680,7 +693,13 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
   p.n_chunks = 0;
   auto base_of = [&](int k) { return cp.chunk_ptr[k] ? cp.chunk_ptr[k] : cp.in; };
   auto pitch_of = [&](int k) { return cp.chunk_ptr[k] ? cp.chunk_pitch[k] : cp.in_pitch; };
-  for (int k = 0; k < p.n_ks;) {
+  if (c7) {   // one box of 8 (3 real + 5 zero) channels per pixel
+    if (cp.in_pitch != 8 || reinterpret_cast<uintptr_t>(cp.in) % 16) return "7x7 input must be an 8-channel padded tensor";
+    p.n_chunks = 1;
+    p.chunk_ch[0] = 8; p.chunk_coff[0] = 0; p.chunk_map[0] = 0;
+    chunk_base[0] = cp.in; chunk_pitch[0] = 8;
+  }
+  for (int k = 0; !c7 && k < p.n_ks;) {
     int run = 1;
     while (k + run < p.n_ks && base_of(k + run) == base_of(k) && cp.chunk_off[k + run] == cp.chunk_off[k] + 16 * run) ++run;
     int off = cp.chunk_off[k];
@@ -714,7 +733,7 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
     p.debug = dbg;
   }
   const size_t w_bytes = ((size_t)ntap * w.cin * NMMA * 2 + 127) & ~(size_t)127;
-  const size_t fixed = w_bytes + (2 * kUmmaMaxBufs + 2 * kEpiGroups + 2) * 8 + kEpiGroups * 2 * 4 * 2 * N * 4 + 256 /*steps, slot_base*/ + 4 * kEpiGroups * 1024 /*store staging*/ + 1024 /*alignment slack*/ + 256;
+  const size_t fixed = w_bytes + (2 * kUmmaMaxBufs + 2 * kEpiGroups + 2) * 8 + kEpiGroups * 2 * 4 * 2 * N * 4 + 640 /*steps, slot_base*/ + 4 * kEpiGroups * 1024 /*store staging*/ + 1024 /*alignment slack*/ + 256;
   const size_t smem_cap = 227 * 1024 - fixed;
   auto item_buf_bytes = [&](size_t npx) {                      // every chunk is 1024-aligned inside the buffer
     size_t b = 0;
@@ -729,12 +748,12 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
     double best_cost = 1e30;
     int best_k = 0, best_ns = 0;
     for (int ns = 1; ns <= std::max(1, (cp.W + 15) / 16); ++ns) {
-      const int TW = (cp.W + ns - 1) / ns, pitch = TW + 2;
+      const int TW = (cp.W + ns - 1) / ns, pitch = TW + 2 * halo;
       if (pitch > 256) continue;                               // TMA box dimension limit
       if (ns > 1 && TW < 24) break;
       const long long lin = (long long)cp.H * pitch;
       for (int k = 1; k <= kUmmaMaxK; ++k) {
-        const int rbox = (k * ts + 3 * pitch + 1 + pitch - 1) / pitch;   // rows covering any item's tap footprint
+        const int rbox = (k * ts + (2 * halo + 1) * pitch + 2 * halo - 1 + pitch - 1) / pitch;   // rows covering any item's tap footprint
         if (rbox > 256) break;
         const size_t npx = (size_t)rbox * pitch;
         if (item_buf_bytes(npx) * 2 > smem_cap) break;
@@ -752,11 +771,11 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
     p.k = best_k;
     p.n_strips = best_ns;
     p.TW = (cp.W + best_ns - 1) / best_ns;
-    p.pitch = p.TW + 2;
+    p.pitch = p.TW + 2 * halo;
     const long long lin = (long long)cp.H * p.pitch;
     p.items_per_strip = (int)((lin + (long long)ts * p.k - 1) / ((long long)ts * p.k));
     p.n_items = p.items_per_strip * p.n_strips * cp.B;
-    p.rbox = (p.k * ts + 3 * p.pitch + 1 + p.pitch - 1) / p.pitch;
+    p.rbox = (p.k * ts + (2 * halo + 1) * p.pitch + 2 * halo - 1 + p.pitch - 1) / p.pitch;
     p.npx = p.rbox * p.pitch;
   } else {
     p.tstride = 128;
@@ -784,7 +803,7 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
   if (bufs < 2) return "tile does not fit in shared memory";
   if (bufs > kUmmaMaxBufs) bufs = kUmmaMaxBufs;
   p.n_bufs = bufs;
-  plan.smem_bytes = (size_t)bufs * off + w_bytes + (2 * bufs + 2 * kEpiGroups + 2) * 8 + kEpiGroups * 2 * 4 * 2 * N * 4 + 256 + 4 * kEpiGroups * 1024 + 1024 + 64;
+  plan.smem_bytes = (size_t)bufs * off + w_bytes + (2 * bufs + 2 * kEpiGroups + 2) * 8 + kEpiGroups * 2 * 4 * 2 * N * 4 + 640 + 4 * kEpiGroups * 1024 + 1024 + 64;
   plan.grid = std::min(p.n_items, num_sms);
   // ---- tensor maps, one per K-chunk
   for (int c = 0; c < p.n_chunks; ++c)
@@ -809,6 +828,7 @@ inline const char* umma_launch_inst(const UmmaPlan& plan, cudaStream_t st) {
 
 template <typename T>
 inline const char* umma_plan_launch(const UmmaPlan& plan, const UmmaWeights& w, cudaStream_t st) {
+  if (w.ks == 7) return w.cout == 32 ? umma_launch_inst<T, 32, kConv7x7>(plan, st) : "unsupported Cout";
   if (w.ks == 3) {
     if (w.cout == 16) return umma_launch_inst<T, 16, kConv3x3Fold>(plan, st);
     if (w.cout == 32) return umma_fold(3, 32) ? umma_launch_inst<T, 32, kConv3x3Fold>(plan, st) : umma_launch_inst<T, 32, kConv3x3Taps>(plan, st);
