@@ -17,7 +17,7 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "liblpsr_b200.so")
 SOURCES = ["engine.cu", "inst_f32.cu", "inst_bf16.cu", "inst_f16.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + os.environ.get("LPSR_NVCC_EXTRA", "").split()
 
 
 def _nvcc() -> str:

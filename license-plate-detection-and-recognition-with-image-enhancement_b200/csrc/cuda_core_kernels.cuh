@@ -130,82 +130,175 @@ __global__ void __launch_bounds__(kThreads) conv_direct_kernel(const ConvParams 
 // DConv + pixel (un)shuffle + ReLU (+ skip add)
 // ---------------------------------------------------------------------------------------------------
 enum { kShuffleDown = 0, kShuffleUp = 1 };
+template <typename A, typename B> struct IsSame { static constexpr bool value = false; };
+template <typename A> struct IsSame<A, A> { static constexpr bool value = true; };
+
+// Persistent CTAs (weights staged in shared memory once), tile = 16 rows x 32 columns, 2 pixels (rows ty, ty+8) per thread so
+// every depthwise-weight read feeds two pixels.  16-bit activations are staged as channel-PAIR planes (one 32-bit word = two
+// channels of one pixel): a tap read is a conflict-free 4-byte LDS that feeds two channels.
+constexpr int kDcTileH = 16, kDcTileW = 32, kDcSH = kDcTileH + 4, kDcSW = kDcTileW + 4, kDcPlane = kDcSH * kDcSW + 1;
+
+template <typename T, int CIN>
+constexpr size_t dconv_smem_bytes(int cout) {
+  return (sizeof(T) == 2 ? (size_t)(CIN / 2) * kDcPlane * 4 : (size_t)CIN * kDcPlane * 4) + 16 + (size_t)CIN * 25 * 4 + (size_t)CIN * 4 +
+         (size_t)CIN * cout * 4 + (size_t)cout * 4 + 64;
+}
 
 template <typename T, int CIN, int COUT, int MODE, bool ADD_RES>
-__global__ void __launch_bounds__(kThreads) dconv_fused_kernel(const DConvParams p) {
-  constexpr int KS = 5, R = 2, CCH = 12;
-  static_assert(CIN % CCH == 0, "AutoEncoder widths are multiples of 12");
-  constexpr int SH = kTileH + KS - 1, SW = kTileW + KS - 1;
-  constexpr int PLANE = (SH * SW) | 1;
-  __shared__ float s_in[CCH * PLANE];
-  __shared__ float s_dw[CIN * 26];               // 25 taps + bias per channel
-  __shared__ __align__(16) float s_pw[CIN * COUT];
-
+__global__ void __launch_bounds__(kThreads) dconv_fused_kernel(const DConvParams p, int tiles_x, int tiles_y) {
+  constexpr bool H16 = sizeof(T) == 2;
+  constexpr int NPL = H16 ? CIN / 2 : CIN;                       // staged planes
+  extern __shared__ __align__(16) uint8_t dc_smem[];
+  uint32_t* s_in = reinterpret_cast<uint32_t*>(dc_smem);          // [NPL][kDcPlane] (bf16x2 / fp16x2 words, or fp32)
+  float* s_dw = reinterpret_cast<float*>(s_in + (((size_t)NPL * kDcPlane + 3) & ~(size_t)3));   // [25][CIN] tap-major, 16-byte aligned
+  float* s_db = s_dw + CIN * 25;                                  // [CIN]
+  float* s_pw = s_db + CIN;                                       // [CIN][COUT]
+  float* s_pb = s_pw + CIN * COUT;                                // [COUT]
   const int tid = threadIdx.x;
-  const int tx = tid % kTileW, ty = tid / kTileW;
-  const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH, n = blockIdx.z;
-
-  for (int i = tid; i < CIN * 26; i += kThreads) {
-    const int c = i / 26, t = i % 26;
-    s_dw[i] = (t < 25) ? __ldg(p.dw_w + c * 25 + t) : __ldg(p.dw_b + c);
-  }
+  const int tx = tid % kDcTileW, ty = tid / kDcTileW;             // ty in 0..7; the thread also owns row ty + 8
+  for (int i = tid; i < CIN * 25; i += kThreads) s_dw[(i % 25) * CIN + i / 25] = __ldg(p.dw_w + i);
+  for (int i = tid; i < CIN; i += kThreads) s_db[i] = __ldg(p.dw_b + i);
   for (int i = tid; i < CIN * COUT; i += kThreads) s_pw[i] = __ldg(p.pw_w + i);
-
-  float acc[COUT];
-#pragma unroll
-  for (int co = 0; co < COUT; ++co) acc[co] = __ldg(p.pw_b + co);
+  for (int i = tid; i < COUT; i += kThreads) s_pb[i] = __ldg(p.pw_b + i);
 
   const T* src = static_cast<const T*>(p.in);
-  for (int ch = 0; ch < CIN / CCH; ++ch) {
-    __syncthreads();
-    for (int i = tid; i < CCH * SH * SW; i += kThreads) {
-      const int r = i / CCH, c = i % CCH;
-      const int yy = y0 + r / SW - R, xx = x0 + r % SW - R;
-      float v = 0.f;
-      if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W)
-        v = to_f32<T>(src[((size_t)(n * p.H + yy) * p.W + xx) * p.in_pitch + p.in_off + ch * CCH + c]);
-      s_in[c * PLANE + r] = v;
-    }
-    __syncthreads();
-#pragma unroll 1
-    for (int c = 0; c < CCH; ++c) {
-      const float* a_ptr = s_in + c * PLANE + ty * SW + tx;
-      const float* w = s_dw + (ch * CCH + c) * 26;
-      float d = w[25];
-#pragma unroll
-      for (int dy = 0; dy < KS; ++dy)
-#pragma unroll
-        for (int dx = 0; dx < KS; ++dx) d = fmaf(a_ptr[dy * SW + dx], w[dy * KS + dx], d);
-      const float* pw = s_pw + (ch * CCH + c) * COUT;
-#pragma unroll
-      for (int q = 0; q < COUT / 4; ++q) {
-        const float4 w4 = *reinterpret_cast<const float4*>(pw + q * 4);
-        acc[q * 4 + 0] = fmaf(d, w4.x, acc[q * 4 + 0]);
-        acc[q * 4 + 1] = fmaf(d, w4.y, acc[q * 4 + 1]);
-        acc[q * 4 + 2] = fmaf(d, w4.z, acc[q * 4 + 2]);
-        acc[q * 4 + 3] = fmaf(d, w4.w, acc[q * 4 + 3]);
-      }
-    }
-  }
-
-  const int y = y0 + ty, x = x0 + tx;
-  if (y >= p.H || x >= p.W) return;
   T* out = static_cast<T*>(p.out);
   const T* res = static_cast<const T*>(p.res);
-#pragma unroll
-  for (int co = 0; co < COUT; ++co) {
-    float v = fmaxf(acc[co], 0.f);  // ReLU commutes with the index remap (lpsr.py:73,80,89,96)
-    size_t dst;
-    if constexpr (MODE == kShuffleDown) dst = unshuffle2_dst(n, y, x, co, p.H, p.W, p.out_pitch, p.out_off);
-    else                                dst = shuffle2_dst(n, y, x, co, p.H, p.W, p.out_pitch, p.out_off);
-    if constexpr (ADD_RES) {
-      // res has the same geometry as the (shuffled) output; only pitch/offset may differ
-      size_t rdst;
-      if constexpr (MODE == kShuffleDown) rdst = unshuffle2_dst(n, y, x, co, p.H, p.W, p.res_pitch, p.res_off);
-      else                                rdst = shuffle2_dst(n, y, x, co, p.H, p.W, p.res_pitch, p.res_off);
-      v += to_f32<T>(res[rdst]);
+  const int n_tiles = tiles_x * tiles_y * p.B;
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int n = t / (tiles_x * tiles_y), r0 = t % (tiles_x * tiles_y);
+    const int y0 = (r0 / tiles_x) * kDcTileH, x0 = (r0 % tiles_x) * kDcTileW;
+    __syncthreads();                                              // previous tile fully consumed (also covers the weight staging)
+    // ---- stage the haloed input tile (zero outside the image = padding 'same')
+    if constexpr (H16) {
+      constexpr int G8 = CIN / 4;                                 // 4-channel (8-byte) groups per pixel: CIN = 12 or 48
+      for (int i = tid; i < kDcSH * kDcSW * G8; i += kThreads) {
+        const int px = i % (kDcSH * kDcSW), g = i / (kDcSH * kDcSW);
+        const int yy = y0 + px / kDcSW - 2, xx = x0 + px % kDcSW - 2;
+        uint2 v = make_uint2(0u, 0u);
+        if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W)
+          v = *reinterpret_cast<const uint2*>(src + ((size_t)(n * p.H + yy) * p.W + xx) * p.in_pitch + p.in_off + g * 4);
+        s_in[(size_t)(2 * g) * kDcPlane + px] = v.x;
+        s_in[(size_t)(2 * g + 1) * kDcPlane + px] = v.y;
+      }
+    } else {
+      for (int i = tid; i < kDcSH * kDcSW * CIN; i += kThreads) {
+        const int px = i / CIN, c = i % CIN;
+        const int yy = y0 + px / kDcSW - 2, xx = x0 + px % kDcSW - 2;
+        float v = 0.f;
+        if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) v = to_f32<T>(src[((size_t)(n * p.H + yy) * p.W + xx) * p.in_pitch + p.in_off + c]);
+        s_in[(size_t)c * kDcPlane + px] = __float_as_uint(v);
+      }
     }
-    out[dst] = from_f32<T>(v);
+    __syncthreads();
+    float acc0[COUT], acc1[COUT];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) { acc0[co] = s_pb[co]; acc1[co] = s_pb[co]; }
+    const uint32_t* base = s_in + ty * kDcSW + tx;
+#pragma unroll 1
+    for (int pl = 0; pl < NPL; ++pl) {
+      const uint32_t* a = base + (size_t)pl * kDcPlane;
+      if constexpr (H16) {
+        const int c = 2 * pl;
+        float d00 = s_db[c], d01 = s_db[c + 1], d10 = d00, d11 = d01;       // [pixel][channel of the pair]
+#pragma unroll
+        for (int dy = 0; dy < 5; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 5; ++dx) {
+            const float2 w = *reinterpret_cast<const float2*>(s_dw + (dy * 5 + dx) * CIN + c);
+            const uint32_t u0 = a[dy * kDcSW + dx], u1 = a[(dy + 8) * kDcSW + dx];
+            float l0, h0, l1, h1;
+            if constexpr (IsSame<T, __nv_bfloat16>::value) {
+              l0 = __uint_as_float(u0 << 16); h0 = __uint_as_float(u0 & 0xffff0000u);
+              l1 = __uint_as_float(u1 << 16); h1 = __uint_as_float(u1 & 0xffff0000u);
+            } else {
+              const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&u0)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&u1));
+              l0 = f0.x; h0 = f0.y; l1 = f1.x; h1 = f1.y;
+            }
+            d00 = fmaf(l0, w.x, d00); d01 = fmaf(h0, w.y, d01);
+            d10 = fmaf(l1, w.x, d10); d11 = fmaf(h1, w.y, d11);
+          }
+        const float* pw0 = s_pw + c * COUT;
+#pragma unroll
+        for (int q = 0; q < COUT / 4; ++q) {
+          const float4 wa = *reinterpret_cast<const float4*>(pw0 + q * 4), wb = *reinterpret_cast<const float4*>(pw0 + COUT + q * 4);
+          acc0[q * 4 + 0] = fmaf(d01, wb.x, fmaf(d00, wa.x, acc0[q * 4 + 0])); acc1[q * 4 + 0] = fmaf(d11, wb.x, fmaf(d10, wa.x, acc1[q * 4 + 0]));
+          acc0[q * 4 + 1] = fmaf(d01, wb.y, fmaf(d00, wa.y, acc0[q * 4 + 1])); acc1[q * 4 + 1] = fmaf(d11, wb.y, fmaf(d10, wa.y, acc1[q * 4 + 1]));
+          acc0[q * 4 + 2] = fmaf(d01, wb.z, fmaf(d00, wa.z, acc0[q * 4 + 2])); acc1[q * 4 + 2] = fmaf(d11, wb.z, fmaf(d10, wa.z, acc1[q * 4 + 2]));
+          acc0[q * 4 + 3] = fmaf(d01, wb.w, fmaf(d00, wa.w, acc0[q * 4 + 3])); acc1[q * 4 + 3] = fmaf(d11, wb.w, fmaf(d10, wa.w, acc1[q * 4 + 3]));
+        }
+      } else {
+        const int c = pl;
+        float d0 = s_db[c], d1 = d0;
+#pragma unroll
+        for (int dy = 0; dy < 5; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 5; ++dx) {
+            const float w = s_dw[(dy * 5 + dx) * CIN + c];
+            d0 = fmaf(__uint_as_float(a[dy * kDcSW + dx]), w, d0);
+            d1 = fmaf(__uint_as_float(a[(dy + 8) * kDcSW + dx]), w, d1);
+          }
+        const float* pw0 = s_pw + c * COUT;
+#pragma unroll
+        for (int q = 0; q < COUT / 4; ++q) {
+          const float4 wa = *reinterpret_cast<const float4*>(pw0 + q * 4);
+          acc0[q * 4 + 0] = fmaf(d0, wa.x, acc0[q * 4 + 0]); acc1[q * 4 + 0] = fmaf(d1, wa.x, acc1[q * 4 + 0]);
+          acc0[q * 4 + 1] = fmaf(d0, wa.y, acc0[q * 4 + 1]); acc1[q * 4 + 1] = fmaf(d1, wa.y, acc1[q * 4 + 1]);
+          acc0[q * 4 + 2] = fmaf(d0, wa.z, acc0[q * 4 + 2]); acc1[q * 4 + 2] = fmaf(d1, wa.z, acc1[q * 4 + 2]);
+          acc0[q * 4 + 3] = fmaf(d0, wa.w, acc0[q * 4 + 3]); acc1[q * 4 + 3] = fmaf(d1, wa.w, acc1[q * 4 + 3]);
+        }
+      }
+    }
+    // ---- ReLU + pixel (un)shuffle address map (+ AutoEncoder skip add), two pixels per thread
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int y = y0 + ty + half * 8, x = x0 + tx;
+      if (y >= p.H || x >= p.W) continue;
+      if constexpr (MODE == kShuffleUp && sizeof(T) == 2 && (COUT / 4) % 4 == 0) {
+        // PixelShuffle: for a fixed sub-position (i,j) the COUT/4 output channels of pixel (2y+i, 2x+j) are contiguous:
+        // 8-byte vector stores (and skip loads) instead of COUT scattered 2-byte ones; same address map (shuffle2_dst)
+        constexpr int CO = COUT / 4;
+#pragma unroll
+        for (int ij = 0; ij < 4; ++ij) {
+          const size_t dst = shuffle2_dst(n, y, x, ij, p.H, p.W, p.out_pitch, p.out_off);      // channel c' = 0 of sub-position ij
+          const size_t rdst = ADD_RES ? shuffle2_dst(n, y, x, ij, p.H, p.W, p.res_pitch, p.res_off) : 0;
+#pragma unroll
+          for (int c4 = 0; c4 < CO; c4 += 4) {
+            float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = fmaxf(half ? acc1[(c4 + k) * 4 + ij] : acc0[(c4 + k) * 4 + ij], 0.f);
+            if constexpr (ADD_RES) {
+              const uint2 rr = *reinterpret_cast<const uint2*>(res + rdst + c4);
+              const T* re = reinterpret_cast<const T*>(&rr);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) v[k] += to_f32<T>(re[k]);
+            }
+            uint2 o;
+            T* oe = reinterpret_cast<T*>(&o);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) oe[k] = from_f32<T>(v[k]);
+            *reinterpret_cast<uint2*>(out + dst + c4) = o;
+          }
+          // output tensor padded to a wider pitch (16-channel operand of the tensor-core conv_out): zero the pad channels
+          for (int c4 = CO; c4 + 4 <= p.out_pitch - p.out_off; c4 += 4) *reinterpret_cast<uint2*>(out + dst + c4) = make_uint2(0u, 0u);
+        }
+      } else {
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) {
+          float v = fmaxf(half ? acc1[co] : acc0[co], 0.f);         // ReLU commutes with the index remap (lpsr.py:73,80,89,96)
+          size_t dst;
+          if constexpr (MODE == kShuffleDown) dst = unshuffle2_dst(n, y, x, co, p.H, p.W, p.out_pitch, p.out_off);
+          else                                dst = shuffle2_dst(n, y, x, co, p.H, p.W, p.out_pitch, p.out_off);
+          if constexpr (ADD_RES) {
+            size_t rdst;
+            if constexpr (MODE == kShuffleDown) rdst = unshuffle2_dst(n, y, x, co, p.H, p.W, p.res_pitch, p.res_off);
+            else                                rdst = shuffle2_dst(n, y, x, co, p.H, p.W, p.res_pitch, p.res_off);
+            v += to_f32<T>(res[rdst]);
+          }
+          out[dst] = from_f32<T>(v);
+        }
+      }
+    }
   }
 }
 

@@ -2,6 +2,7 @@
 // the launch plan of one LPSR forward (reference: my_models/lpsr.py:269-274) and the op-level entry points.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -185,16 +186,15 @@ int pack_all(lpsr_handle* h) {
     ok &= umma_pack_weights(h->sfe1_u, pw.data(), W(h, "rdn.shallowF1.bias").data(), 1, 448, F, h->cfg.precision == LPSR_PREC_FP16,
                             [&](const std::vector<uint16_t>& v) { return arena_put(h, v); }, [&](const std::vector<float>& v) { return arena_put(h, v); });
     h->sfe1_u.ks = 7;
-    // AutoEncoder conv_out 12 -> 3 padded to 8 output channels (zeros) so the 7x7 reads 16-byte pixels
+    // AutoEncoder conv_out 12 -> 3 on tensor cores: input (c0 + decoder) is written as a 16-channel padded tensor, the output
+    // as a 16-channel padded tensor whose first 8 channels (3 real) are the 16-byte pixels the 7x7 reads
     const std::vector<float>& wo = W(h, "auto_encoder.conv_out.weight");   // [C][E][3][3]
-    std::vector<float> p8((size_t)9 * E * 8, 0.f);
+    std::vector<float> p16((size_t)9 * 16 * 16, 0.f);
     for (int co = 0; co < C; ++co)
       for (int ci = 0; ci < E; ++ci)
-        for (int t = 0; t < 9; ++t) p8[((size_t)t * E + ci) * 8 + co] = wo[((size_t)co * E + ci) * 9 + t];
-    h->ae_out8.ks = 3; h->ae_out8.cin = E; h->ae_out8.cout = 8;
-    h->ae_out8.w = arena_put(h, p8);
-    h->ae_out8.b = nullptr;
-    ok &= h->ae_out8.w != nullptr;
+        for (int t = 0; t < 9; ++t) p16[((size_t)t * 16 + ci) * 16 + co] = wo[((size_t)co * E + ci) * 9 + t];
+    ok &= umma_pack_weights(h->ae_out_u, p16.data(), nullptr, 3, 16, 16, h->cfg.precision == LPSR_PREC_FP16,
+                            [&](const std::vector<uint16_t>& v) { return arena_put(h, v); }, [&](const std::vector<float>& v) { return arena_put(h, v); });
   }
   ok &= pack_conv(h, h->sfe2, "rdn.shallowF2", F, F, 3, true);
   for (int r = 0; r < 2; ++r) {
@@ -263,8 +263,8 @@ WsLayout ws_layout(const lpsr_handle* h, int B, int H, int W) {
   L.e0 = take(BP / 4 * 48, es);
   L.e1 = take(BP / 16 * 48, es);
   L.d0 = take(BP / 4 * 12, es);
-  L.s = take(BP * 12, es);
-  L.ae = take(BP * 8, es);   // AutoEncoder output: 3 channels (pitch 3), or padded to 8 channels for the tensor-core 7x7
+  L.s = take(BP * 16, es);   // c0 + decoder output: 12 channels, pitch 16 (zero padded) on the tensor-core path
+  L.ae = take(BP * 16, es);  // AutoEncoder output: 3 channels (pitch 3), or padded to 16 channels on the tensor-core path
   L.sfe1 = take(BP * 32, es);
   L.x0 = take(BP * 32, es);
   for (int r = 0; r < 2; ++r)
@@ -380,7 +380,12 @@ int lpsr_destroy(lpsr_handle* h) {
   if (h->host_x) cudaFree(h->host_x);
   if (h->host_y) cudaFree(h->host_y);
   if (h->host_ws) cudaFree(h->host_ws);
-  if (h->host_stream) cudaStreamDestroy(h->host_stream);
+  if (h->host_stream) {
+    cudaStreamDestroy(h->host_stream);
+    cudaStreamDestroy(h->copy_in_stream);
+    cudaStreamDestroy(h->copy_out_stream);
+    for (int i = 0; i < 2 * kHostChunksMax; ++i) cudaEventDestroy(h->host_ev[i]);
+  }
   delete h;
   return LPSR_OK;
 }
@@ -484,9 +489,20 @@ int lpsr_forward_host(lpsr_handle* h, const float* x_host, float* y_host, int32_
   int rc = check_shape(h, B, H, W);
   if (rc) return rc;
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-  if (!h->host_stream) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking));
-  const WsLayout L = ws_layout(h, B, H, W);
-  const size_t xb = (size_t)B * 3 * H * W * 4, yb = (size_t)B * h->cfg.out_channels * L.P * 4;
+  if (!h->host_stream) {
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking));
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_in_stream, cudaStreamNonBlocking));
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_out_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2 * kHostChunksMax; ++i) CUDA_TRY(h, cudaEventCreateWithFlags(&h->host_ev[i], cudaEventDisableTiming));
+  }
+  // Large batches are cut into chunks so the H2D copy of chunk i+1 and the D2H copy of chunk i-1 (separate copy streams)
+  // overlap the forward of chunk i (compute stream); crops are independent, so chunking does not change any result
+  // except through the batch-size independent pooling slices (bit-identical).
+  int nchunk = B >= 512 ? 4 : (B >= 128 ? 2 : 1);
+  if (nchunk > kHostChunksMax) nchunk = kHostChunksMax;
+  const int cb = (B + nchunk - 1) / nchunk;                 // crops per chunk
+  const WsLayout L = ws_layout(h, cb, H, W);
+  const size_t x_crop = (size_t)3 * H * W * 4, y_crop = (size_t)h->cfg.out_channels * L.P * 4;
   auto grow = [&](void** p, size_t* cap, size_t need) -> cudaError_t {
     if (*cap >= need) return cudaSuccess;
     if (*p) cudaFree(*p);
@@ -495,13 +511,26 @@ int lpsr_forward_host(lpsr_handle* h, const float* x_host, float* y_host, int32_
     if (e == cudaSuccess) *cap = need;
     return e;
   };
-  CUDA_TRY(h, grow(&h->host_x, &h->host_x_cap, xb));
-  CUDA_TRY(h, grow(&h->host_y, &h->host_y_cap, yb));
+  CUDA_TRY(h, grow(&h->host_x, &h->host_x_cap, x_crop * B));
+  CUDA_TRY(h, grow(&h->host_y, &h->host_y_cap, y_crop * B));
   CUDA_TRY(h, grow(&h->host_ws, &h->host_ws_cap, L.total));
-  CUDA_TRY(h, cudaMemcpyAsync(h->host_x, x_host, xb, cudaMemcpyHostToDevice, h->host_stream));
-  rc = lpsr_forward(h, static_cast<const float*>(h->host_x), static_cast<float*>(h->host_y), B, H, W, h->host_ws, h->host_ws_cap, h->host_stream);
-  if (rc) return rc;
-  CUDA_TRY(h, cudaMemcpyAsync(y_host, h->host_y, yb, cudaMemcpyDeviceToHost, h->host_stream));
+  char* dx = static_cast<char*>(h->host_x);
+  char* dy = static_cast<char*>(h->host_y);
+  const char* hx = reinterpret_cast<const char*>(x_host);
+  char* hy = reinterpret_cast<char*>(y_host);
+  for (int i = 0, lo = 0; lo < B; ++i, lo += cb) {
+    const int n = std::min(cb, B - lo);
+    CUDA_TRY(h, cudaMemcpyAsync(dx + x_crop * lo, hx + x_crop * lo, x_crop * n, cudaMemcpyHostToDevice, h->copy_in_stream));
+    CUDA_TRY(h, cudaEventRecord(h->host_ev[2 * i], h->copy_in_stream));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->host_stream, h->host_ev[2 * i], 0));
+    rc = lpsr_forward(h, reinterpret_cast<const float*>(dx + x_crop * lo), reinterpret_cast<float*>(dy + y_crop * lo), n, H, W, h->host_ws,
+                      h->host_ws_cap, h->host_stream);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaEventRecord(h->host_ev[2 * i + 1], h->host_stream));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->copy_out_stream, h->host_ev[2 * i + 1], 0));
+    CUDA_TRY(h, cudaMemcpyAsync(hy + y_crop * lo, dy + y_crop * lo, y_crop * n, cudaMemcpyDeviceToHost, h->copy_out_stream));
+  }
+  CUDA_TRY(h, cudaStreamSynchronize(h->copy_out_stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->host_stream));
   return LPSR_OK;
 }
@@ -513,7 +542,7 @@ int lpsr_debug_read_tap(lpsr_handle* h, const char* name, float* dst, int64_t ds
   struct Tap { const char* name; size_t off; int pitch, choff, C, div; };
   const Tap taps[] = {
       {"ae.c0", L.c0, 12, 0, 12, 1},      {"ae.enc0", L.e0, 48, 0, 48, 2},   {"ae.enc1", L.e1, 48, 0, 48, 4},
-      {"ae.dec0", L.d0, 12, 0, 12, 2},    {"ae.sum", L.s, 12, 0, 12, 1},     {"ae.out", L.ae, h->sfe1_u.packed ? 8 : 3, 0, 3, 1},
+      {"ae.dec0", L.d0, 12, 0, 12, 2},    {"ae.sum", L.s, h->sfe1_u.packed ? 16 : 12, 0, 12, 1},     {"ae.out", L.ae, h->sfe1_u.packed ? 16 : 3, 0, 3, 1},
       {"rdn.sfe1", L.sfe1, 32, 0, 32, 1}, {"rdn.sfe2", L.x0, 32, 0, 32, 1},
       {"rdn.block0", L.f[0], 32, 0, 32, 1}, {"rdn.block1", L.f[1], 32, 0, 32, 1},
       {"rdn.block2", L.f[2], 32, 0, 32, 1}, {"rdn.block3", L.f[3], 32, 0, 32, 1},

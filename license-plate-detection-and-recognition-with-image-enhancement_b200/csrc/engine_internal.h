@@ -39,6 +39,8 @@ struct DConvW { float *dw_w, *dw_b, *pw_w, *pw_b; int cin, cout; };
 
 }  // namespace lpsr
 
+constexpr int kHostChunksMax = 4;   // lpsr_forward_host: H2D / forward / D2H pipeline depth
+
 struct lpsr_handle {
   lpsr_config cfg{};
   int sm = 0;
@@ -51,12 +53,13 @@ struct lpsr_handle {
   lpsr::ConvW ae_in, ae_out, sfe1, sfe2, rdb[2][4], lff[2], csar_c1, csar_c2, csar_sa1, csar_sa2, csar_co, gff0, gff1, fin;
   lpsr::UmmaWeights fin_u;   // final conv with Cout padded 1 -> 16 for the tensor-core path
   lpsr::UmmaWeights sfe1_u;  // shallowF1 7x7 as 28 pixel-pair K-steps over an 8-channel padded input (tensor-core path)
-  lpsr::ConvW ae_out8;       // AutoEncoder conv_out with Cout padded 3 -> 8 (writes the 8-channel padded tensor sfe1_u reads)
+  lpsr::UmmaWeights ae_out_u; // AutoEncoder conv_out 12 -> 3 on tensor cores: Cin padded to 16, Cout padded to 16 (zeros)
   lpsr::DConvW dc[4];
   float *ca_w1 = nullptr, *ca_b1 = nullptr, *ca_w2 = nullptr, *ca_b2 = nullptr;
   float *sa_w1 = nullptr, *sa_b1 = nullptr, *sa_w2 = nullptr, *sa_b2 = nullptr, *co_w = nullptr, *co_b = nullptr;
   // host-call path (lpsr_forward_host)
-  cudaStream_t host_stream = nullptr;
+  cudaStream_t host_stream = nullptr, copy_in_stream = nullptr, copy_out_stream = nullptr;
+  cudaEvent_t host_ev[8] = {};
   void* host_x = nullptr; void* host_y = nullptr; void* host_ws = nullptr;
   size_t host_x_cap = 0, host_y_cap = 0, host_ws_cap = 0;
   char err[512] = "";

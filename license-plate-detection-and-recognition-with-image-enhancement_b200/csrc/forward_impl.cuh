@@ -102,8 +102,16 @@ void launch_dconv(Ctx& c, const DConvW& w, const void* in, int in_pitch, void* o
   p.out = out; p.out_pitch = out_pitch; p.out_off = 0;
   p.res = res; p.res_pitch = res_pitch; p.res_off = 0;
   p.B = B; p.H = H; p.W = Wd;
-  dim3 grid((Wd + kTileW - 1) / kTileW, (H + kTileH - 1) / kTileH, B);
-  dconv_fused_kernel<T, CIN, COUT, MODE, ADD><<<grid, kThreads, 0, c.st>>>(p);
+  const int tiles_x = (Wd + kDcTileW - 1) / kDcTileW, tiles_y = (H + kDcTileH - 1) / kDcTileH;
+  const size_t smem = dconv_smem_bytes<T, CIN>(COUT);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(dconv_fused_kernel<T, CIN, COUT, MODE, ADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
+  const long long n_tiles = (long long)tiles_x * tiles_y * B;
+  const int grid = (int)std::min<long long>(n_tiles, (long long)c.h->num_sms * 2);   // persistent: weights staged once per CTA
+  dconv_fused_kernel<T, CIN, COUT, MODE, ADD><<<grid, kThreads, smem, c.st>>>(p, tiles_x, tiles_y);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) c.rc = fail(c.h, LPSR_ERR_CUDA, "dconv_fused<%d,%d> launch: %s", CIN, COUT, cudaGetErrorString(e));
 }
@@ -222,11 +230,22 @@ int forward_impl(lpsr_handle* h, const float* x, float* y, int B, int H, int W, 
   c.tag = "ae.dec0";
   launch_dconv<T, 48, 48, kShuffleUp, false>(c, h->dc[2], e1, 48, d0, 12, nullptr, 0, B, Hp / 4, Wp / 4);    // -> [12,H/2,W/2]
   c.tag = "ae.dec1";
-  launch_dconv<T, 12, 48, kShuffleUp, true>(c, h->dc[3], d0, 12, s, 12, c0, 12, B, Hp / 2, Wp / 2);          // -> c0 + [12,H,W]
+  const bool sfe1_tc = (sizeof(T) == 2) && h->sfe1_u.packed && h->ae_out_u.packed;
+  const int s_pitch = sfe1_tc ? 16 : 12;                       // tensor-core conv_out reads a 16-channel (zero padded) operand
+  launch_dconv<T, 12, 48, kShuffleUp, true>(c, h->dc[3], d0, 12, s, s_pitch, c0, 12, B, Hp / 2, Wp / 2);     // -> c0 + [12,H,W]
   c.tag = "ae.conv_out";
-  const bool sfe1_tc = (sizeof(T) == 2) && h->sfe1_u.packed;
-  if (sfe1_tc) launch_direct<T, 3, 12, 8, false, false>(c, conv_params(h->ae_out8, s, 12, 0, 12, ae, 8, 0, B, Hp, Wp, false));
-  else         launch_direct<T, 3, 12, 3, false, false>(c, conv_params(h->ae_out, s, 12, 0, 12, ae, 3, 0, B, Hp, Wp, false));
+  if constexpr (sizeof(T) == 2) {
+    if (sfe1_tc) {
+      c.begin("umma_conv");
+      if (!c.dry && c.rc == LPSR_OK) {
+        ConvW wo;
+        wo.ks = 3; wo.cin = 16; wo.cout = 16;
+        const char* msg = umma_conv_launch<T>(h->ae_out_u, conv_params(wo, s, 16, 0, 16, ae, 16, 0, B, Hp, Wp, false), h->num_sms, c.st);
+        if (msg) c.rc = fail(h, LPSR_ERR_CUDA, "umma_conv ae.conv_out launch: %s", msg);
+      }
+    }
+  }
+  if (!sfe1_tc) launch_direct<T, 3, 12, 3, false, false>(c, conv_params(h->ae_out, s, 12, 0, 12, ae, 3, 0, B, Hp, Wp, false));
 
   // ---- RDN (lpsr.py:214-225) ---------------------------------------------------------------------------
   c.tag = "rdn.shallowF1";
@@ -236,7 +255,7 @@ int forward_impl(lpsr_handle* h, const float* x, float* y, int B, int H, int W, 
       if (!c.dry && c.rc == LPSR_OK) {
         ConvW w7;
         w7.ks = 7; w7.cin = 448; w7.cout = 32;
-        const char* msg = umma_conv_launch<T>(h->sfe1_u, conv_params(w7, {Seg{ae, 8, 0, 8}}, 8, sfe1, 32, 0, B, Hp, Wp, false), h->num_sms, c.st);
+        const char* msg = umma_conv_launch<T>(h->sfe1_u, conv_params(w7, {Seg{ae, 16, 0, 8}}, 8, sfe1, 32, 0, B, Hp, Wp, false), h->num_sms, c.st);
         if (msg) c.rc = fail(h, LPSR_ERR_CUDA, "umma_conv 7x7 launch: %s", msg);
       }
     }

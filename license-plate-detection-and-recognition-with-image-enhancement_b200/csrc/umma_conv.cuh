@@ -448,6 +448,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
     uint32_t my_par = 0;                                        // parity of this group's tmem_full barrier
     int turn = 0;                                               // which group owns the next tile (round robin, same order as the MMA warp)
     const int pitch = p.pitch, tstride = p.tstride, k_tiles = p.k;
+    const int adv_y = K3 ? tstride / pitch : 0, adv_x = K3 ? tstride - adv_y * pitch : 0;   // one tile further along the strip
     for (int ii = 0; ii < n_my_items; ++ii) {
       const int item = blockIdx.x + ii * gridDim.x;
       // per item: one division per thread; per tile the row position advances incrementally
@@ -480,8 +481,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
           }
         }
         if constexpr (K3) {                                     // advance to the next tile (1-2 strip rows for the usual pitch ~ 100)
-          xs += tstride;
-          while (xs >= pitch) { xs -= pitch; ++y; }
+          xs += adv_x;
+          y += adv_y;
+          if (xs >= pitch) { xs -= pitch; ++y; }
         } else {
           px += 128;
         }
@@ -694,10 +696,10 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
   auto base_of = [&](int k) { return cp.chunk_ptr[k] ? cp.chunk_ptr[k] : cp.in; };
   auto pitch_of = [&](int k) { return cp.chunk_ptr[k] ? cp.chunk_pitch[k] : cp.in_pitch; };
   if (c7) {   // one box of 8 (3 real + 5 zero) channels per pixel
-    if (cp.in_pitch != 8 || reinterpret_cast<uintptr_t>(cp.in) % 16) return "7x7 input must be an 8-channel padded tensor";
+    if (cp.in_pitch % 8 || reinterpret_cast<uintptr_t>(cp.in) % 16) return "7x7 input must be a tensor padded to a multiple of 8 channels";
     p.n_chunks = 1;
     p.chunk_ch[0] = 8; p.chunk_coff[0] = 0; p.chunk_map[0] = 0;
-    chunk_base[0] = cp.in; chunk_pitch[0] = 8;
+    chunk_base[0] = cp.in; chunk_pitch[0] = cp.in_pitch;
   }
   for (int k = 0; !c7 && k < p.n_ks;) {
     int run = 1;
@@ -745,8 +747,13 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
     p.tstride = ts;
     // choose strip width TW (equalised over W) and tiles per item k by a cost model:
     //   MMA/epilogue work ~ computed rows per output pixel; staging traffic ~ staged slots per output pixel
+    // Several item loads must be in flight while one item is consumed (TMA latency ~ several thousand clocks): prefer plans
+    // whose item buffer fits `want_bufs` times; relax only if nothing fits.
+    static int want_bufs_env = -1;
+    if (want_bufs_env < 0) { const char* e = getenv("LPSR_UMMA_BUFS"); want_bufs_env = e ? atoi(e) : 2; }
     double best_cost = 1e30;
     int best_k = 0, best_ns = 0;
+    for (int want_bufs = std::min(std::max(want_bufs_env, 2), kUmmaMaxBufs); want_bufs >= 2 && !best_k; --want_bufs)
     for (int ns = 1; ns <= std::max(1, (cp.W + 15) / 16); ++ns) {
       const int TW = (cp.W + ns - 1) / ns, pitch = TW + 2 * halo;
       if (pitch > 256) continue;                               // TMA box dimension limit
@@ -756,7 +763,7 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
         const int rbox = (k * ts + (2 * halo + 1) * pitch + 2 * halo - 1 + pitch - 1) / pitch;   // rows covering any item's tap footprint
         if (rbox > 256) break;
         const size_t npx = (size_t)rbox * pitch;
-        if (item_buf_bytes(npx) * 2 > smem_cap) break;
+        if (item_buf_bytes(npx) * want_bufs > smem_cap) break;
         const long long items_strip = (lin + (long long)ts * k - 1) / ((long long)ts * k);
         const long long items = items_strip * ns * cp.B;
         const double work = (double)items_strip * k * 128 / (double)(cp.H * TW);
@@ -782,7 +789,7 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
     int best_k = 1;
     double best_cost = 1e30;
     for (int k = 1; k <= kUmmaMaxK; ++k) {
-      if (item_buf_bytes((size_t)128 * k) * 2 > smem_cap) break;
+      if (item_buf_bytes((size_t)128 * k) * 4 > smem_cap && k > 1) break;
       const long long items = (p.total_px + 128LL * k - 1) / (128LL * k);
       const long long waves = (items + num_sms - 1) / num_sms;
       const double cost = (double)(waves * num_sms) * k * 128 / (double)p.total_px + 0.04 / k;
