@@ -101,6 +101,13 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic():
+    """DRAM bytes per forward of the tensor-core conv launches / CSAR tail launches from the committed `ncu --set full`
+    capture (profiles/r1_ncu_traffic.json, written by tools/ncu_traffic.py); scaled linearly with the batch."""
+    p = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else None
+
+
 def load_shipped_weights():
     return dict(np.load(os.path.join(ROOT, "tests", "golden", "weights_best_model.npz")))
 
@@ -255,11 +262,15 @@ def run_ours(args):
     n_tail = sum(1 for n_ in names if ".tail:" in n_)
     tail_bytes = 2.0 * B * P * CSAR_TAIL_ELEMS_PER_PIXEL * esz
     total_prof_ms = sum(fam_ms.values())
+    tr = ncu_traffic()
+    scale = (B * P) / float(tr["batch"] * tr["pixels_per_crop"]) if tr else 0.0
     if n_umma:
         ach = umma_flops / (umma_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": f"umma_conv_kernel (tcgen05 implicit-GEMM conv, {n_umma} launches/forward)",
                     "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                    "peak_kind": f"bf16 dense sustained, of {pk['src']}", "traffic": None,
+                    "peak_kind": f"bf16 dense sustained, of {pk['src']}",
+                    "traffic": (tr["umma_dram_bytes_per_forward"] * scale) if tr else None,
+                    "traffic_note": "sum of dram__bytes_read+write over the family's launches of one forward (ncu --set full, profiles/), scaled to this batch",
                     "algorithmic_flops_per_forward": umma_flops, "kernel_ms_per_forward": umma_ms,
                     "share_of_step": umma_ms / total_prof_ms}
     else:   # fp32 mode: FFMA direct convolution dominates; still reported against the bf16 tensor peak
@@ -271,7 +282,8 @@ def run_ours(args):
                     "traffic": None, "share_of_step": d_ms / total_prof_ms}
     roofline_csar = {"bound": "hbm", "kernel": f"CSAR tail (pool + channel gate + spatial MLP + gating + conv_out + residual; {n_tail} launches/forward)", "achieved": tail_bytes / (tail_ms * 1e-3) / 1e9,
                      "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": tail_bytes / (tail_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
-                     "peak_kind": f"copy bandwidth, of {pk['src']}", "traffic": None, "kernel_ms_per_forward": tail_ms}
+                     "peak_kind": f"copy bandwidth, of {pk['src']}", "traffic": (tr["tail_dram_bytes_per_forward"] * scale) if tr else None,
+                     "algorithmic_bytes_per_forward": tail_bytes, "kernel_ms_per_forward": tail_ms}
     conv_frac_whole = value / world * P * DENSE_FLOP_PER_PIXEL / 1e12 / pk["tf_sustained"]
 
     # ---------------- end to end through the C-ABI host-buffer call --------------------------------------------------

@@ -127,6 +127,60 @@ __global__ void __launch_bounds__(kThreads) conv_direct_kernel(const ConvParams 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// AutoEncoder conv_in: 3x3, 3 -> 12, no bias, reads the caller's NCHW fp32 tensor directly (zero beyond (inH,inW) is the
+// pad-to-multiple-of-4 of lpsr.py:107-111 and the conv's own zero padding), writes NHWC T.  One thread per output pixel,
+// 27 coalesced loads (consecutive threads = consecutive x), weights in shared memory; no tile staging needed at Cin = 3.
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads) ae_conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w /*[9][3][12]*/,
+                                                              T* __restrict__ out, int B, int H, int W, int inH, int inW) {
+  __shared__ __align__(16) float s_w[9 * 3 * 12];
+  for (int i = threadIdx.x; i < 9 * 3 * 12; i += kThreads) s_w[i] = __ldg(w + i);
+  __syncthreads();
+  const long long total = (long long)B * H * W;
+  for (long long pix = blockIdx.x * (long long)kThreads + threadIdx.x; pix < total; pix += (long long)gridDim.x * kThreads) {
+    const int xx = (int)(pix % W), yy = (int)((pix / W) % H), n = (int)(pix / ((long long)W * H));
+    float acc[12];
+#pragma unroll
+    for (int co = 0; co < 12; ++co) acc[co] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* plane = x + ((size_t)n * 3 + c) * inH * inW;
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+        const int y = yy + dy - 1;
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const int xq = xx + dx - 1;
+          const float a = (y >= 0 && y < inH && xq >= 0 && xq < inW) ? __ldg(plane + (size_t)y * inW + xq) : 0.f;
+          const float4* wp = reinterpret_cast<const float4*>(s_w + ((dy * 3 + dx) * 3 + c) * 12);
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const float4 w4 = wp[q];
+            acc[q * 4 + 0] = fmaf(a, w4.x, acc[q * 4 + 0]);
+            acc[q * 4 + 1] = fmaf(a, w4.y, acc[q * 4 + 1]);
+            acc[q * 4 + 2] = fmaf(a, w4.z, acc[q * 4 + 2]);
+            acc[q * 4 + 3] = fmaf(a, w4.w, acc[q * 4 + 3]);
+          }
+        }
+      }
+    }
+    T* o = out + (size_t)pix * 12;
+    if constexpr (sizeof(T) == 2) {
+      uint2 v[3];
+      T* e = reinterpret_cast<T*>(v);
+#pragma unroll
+      for (int co = 0; co < 12; ++co) e[co] = from_f32<T>(acc[co]);
+#pragma unroll
+      for (int q = 0; q < 3; ++q) reinterpret_cast<uint2*>(o)[q] = v[q];
+    } else {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) reinterpret_cast<float4*>(o)[q] = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // DConv + pixel (un)shuffle + ReLU (+ skip add)
 // ---------------------------------------------------------------------------------------------------
 enum { kShuffleDown = 0, kShuffleUp = 1 };

@@ -498,7 +498,7 @@ int lpsr_forward_host(lpsr_handle* h, const float* x_host, float* y_host, int32_
   // Large batches are cut into chunks so the H2D copy of chunk i+1 and the D2H copy of chunk i-1 (separate copy streams)
   // overlap the forward of chunk i (compute stream); crops are independent, so chunking does not change any result
   // except through the batch-size independent pooling slices (bit-identical).
-  int nchunk = B >= 512 ? 4 : (B >= 128 ? 2 : 1);
+  int nchunk = B >= 1024 ? 8 : (B >= 512 ? 4 : (B >= 128 ? 2 : 1));
   if (nchunk > kHostChunksMax) nchunk = kHostChunksMax;
   const int cb = (B + nchunk - 1) / nchunk;                 // crops per chunk
   const WsLayout L = ws_layout(h, cb, H, W);

@@ -39,7 +39,7 @@ struct DConvW { float *dw_w, *dw_b, *pw_w, *pw_b; int cin, cout; };
 
 }  // namespace lpsr
 
-constexpr int kHostChunksMax = 4;   // lpsr_forward_host: H2D / forward / D2H pipeline depth
+constexpr int kHostChunksMax = 8;   // lpsr_forward_host: H2D / forward / D2H pipeline depth
 
 struct lpsr_handle {
   lpsr_config cfg{};
@@ -59,7 +59,7 @@ struct lpsr_handle {
   float *sa_w1 = nullptr, *sa_b1 = nullptr, *sa_w2 = nullptr, *sa_b2 = nullptr, *co_w = nullptr, *co_b = nullptr;
   // host-call path (lpsr_forward_host)
   cudaStream_t host_stream = nullptr, copy_in_stream = nullptr, copy_out_stream = nullptr;
-  cudaEvent_t host_ev[8] = {};
+  cudaEvent_t host_ev[16] = {};
   void* host_x = nullptr; void* host_y = nullptr; void* host_ws = nullptr;
   size_t host_x_cap = 0, host_y_cap = 0, host_ws_cap = 0;
   char err[512] = "";

@@ -219,9 +219,14 @@ int forward_impl(lpsr_handle* h, const float* x, float* y, int B, int H, int W, 
   // ---- AutoEncoder (lpsr.py:106-117) ------------------------------------------------------------------
   c.tag = "ae.conv_in";
   {  // conv_in 3->12 reads the caller's NCHW fp32 tensor; zero beyond (H,W) == pad-to-4 (lpsr.py:107-111)
-    ConvParams p = conv_params(h->ae_in, x, 0, 0, 3, c0, 12, 0, B, Hp, Wp, false);
-    p.inH = H; p.inW = W;
-    launch_direct<T, 3, 3, 12, true, false>(c, p);
+    c.begin("ae_conv_in");
+    if (!c.dry && c.rc == LPSR_OK) {
+      const long long total = (long long)B * Hp * Wp;
+      const int grid = (int)std::min<long long>((total + kThreads - 1) / kThreads, (long long)h->num_sms * 16);
+      ae_conv_in_kernel<T><<<grid, kThreads, 0, st>>>(x, h->ae_in.w, c0, B, Hp, Wp, H, W);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) c.rc = fail(h, LPSR_ERR_CUDA, "ae_conv_in launch: %s", cudaGetErrorString(e));
+    }
   }
   c.tag = "ae.enc0";
   launch_dconv<T, 12, 12, kShuffleDown, false>(c, h->dc[0], c0, 12, e0, 48, nullptr, 0, B, Hp, Wp);          // -> [48,H/2,W/2]

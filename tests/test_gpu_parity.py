@@ -180,17 +180,18 @@ def test_batch_composition_independence_full_size(models):
         yb = m(base.repeat(128, 1, 1, 1))
         assert yb.shape == (1024, 1, 64, 192)
         d = (yb.view(128, 8, 1, 64, 192) - y8.unsqueeze(0)).abs().max()
-        assert float(d) <= 2e-6 if prec == "fp32" else float(d) <= 1e-3      # pooled sums are sliced differently per B
+        assert float(d) == 0.0        # bit-identical: tiling, pooling slices and accumulation order do not depend on B
         assert torch.isfinite(yb).all() and float(yb.min()) > 0 and float(yb.max()) < 1   # sigmoid range
 
 
-def test_forward_host_equals_forward(models):
-    x = torch.rand(5, 3, 32, 192, generator=torch.Generator().manual_seed(4))
+@pytest.mark.parametrize("batch", [5, 130, 520])     # 1, 2 and 4 pipelined chunks inside lpsr_forward_host
+def test_forward_host_equals_forward(models, batch):
+    x = torch.rand(batch, 3, 32, 96, generator=torch.Generator().manual_seed(4))
     for prec in ("fp32", "bf16"):
         m = models[prec]
         y_dev = m(x.to(DEV)).cpu()
         y_host = m.forward_host(x.pin_memory())
-        assert torch.equal(y_dev, y_host)
+        assert torch.equal(y_dev, y_host)            # chunking must not change a single bit (crops are independent)
 
 
 def test_call_site_semantics(models):
