@@ -251,7 +251,7 @@ def run_ours(args):
         per_kernel.setdefault(kind, [0.0, 0])
         per_kernel[kind][0] += t
         per_kernel[kind][1] += names.count(name)
-    is_umma = lambda n_: n_.split(":")[1].startswith("umma_conv")
+    is_umma = lambda n_: n_.split(":")[1].startswith("umma_conv") or n_.endswith(":csar_tail_umma")
     umma_ms = sum(t for n_, t in fam_ms.items() if is_umma(n_))
     umma_tags = {n_.split(":")[0] for n_ in names if is_umma(n_)}
     umma_flops = 2.0 * B * P * sum(v for k, v in UMMA_MAC_PER_PIXEL.items() if k in umma_tags)

@@ -1,0 +1,255 @@
+// csar_tail_umma.cuh -- the CSAR tail as ONE tensor-core kernel (16-bit modes).  sm_100a only.
+//
+// Reference (lpsr.py:138-153, 180-186), per pixel with x_in = conv_in(x):
+//     hid = relu(W3 x_in + b3)              32 -> 64     (SpatialAttention conv 0)
+//     s_s = sigmoid(W4 hid + b4)            64 -> 32     (SpatialAttention conv 2)
+//     out = x + Wo [x_in^2 * s_c ; x_in * s_s] + bo      64 -> 32  (gating, conv_out, residual; s_c per crop)
+// Three chained GEMMs on 128-pixel tiles; the 64-channel hidden map and the 64-channel gated concat never leave the SM:
+//     TMA(x_in tile) -> MMA1 -> TMEM -> epilogue (bias, ReLU, 16-bit) -> smem A2 -> MMA2 -> TMEM -> epilogue (sigmoid, gates)
+//     -> smem A3 -> MMA3 -> TMEM -> epilogue (+bias, +x) -> coalesced store.
+// HBM traffic is the algorithmic 96 elements/pixel (read x_in, read x, write out) plus a second (L2-hot) read of x_in for
+// the gates; the three-launch version it replaces moves 352 elements/pixel.
+// Warp roles: G groups x 4 epilogue warps (group g owns tile slot g: its smem operands and 128 TMEM columns), one MMA warp,
+// one TMA producer warp.  The MMA warp walks the G slots phase by phase (MMA1 for all slots, MMA2, MMA3), so while one
+// group is in an epilogue phase the tensor core works for the others.
+#pragma once
+#include "umma_conv.cuh"
+
+namespace lpsr {
+
+constexpr int kTailGroups = 3;
+constexpr int kTailThreads = (4 * kTailGroups + 2) * 32;
+
+struct TailUmmaParams {
+  const void* x_in;            // [BP][32] dense
+  const void* res; int res_pitch, res_off;
+  void* out; int out_pitch, out_off;
+  const uint16_t* w3; const float* b3;   // 1x1 32->64, packed [32/8][64][8]
+  const uint16_t* w4; const float* b4;   // 1x1 64->32, packed [64/8][32][8]
+  const uint16_t* wo; const float* bo;   // 1x1 64->32
+  const float* s_c;            // [B][32]
+  long long total_px;
+  int px_per_crop;
+  int n_tiles;
+};
+
+struct TailTmap { CUtensorMap m; };
+
+template <typename T>
+__global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const __grid_constant__ TailUmmaParams p, const __grid_constant__ TailTmap tm) {
+  constexpr int G = kTailGroups;
+  constexpr uint32_t kA1 = 128 * 64, kA2 = 128 * 128, kSlot = kA1 + 2 * kA2;     // bytes: x_in tile, hidden tile, gated tile
+  constexpr uint32_t kW3 = 32 * 64 * 2, kW4 = 64 * 32 * 2;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* slots = smem;                                       // G slots, each 1024-aligned (40 KB)
+  uint8_t* w3_s = smem + (size_t)G * kSlot;
+  uint8_t* w4_s = w3_s + kW3;
+  uint8_t* wo_s = w4_s + kW4;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wo_s + kW4);
+  // per slot: 0 a1_full, 1 h_full, 2 a2_ready, 3 s_full, 4 a3_ready, 5 o_full, 6 slot_free
+  const uint32_t bar0 = ptx::smem_u32(bars);
+  auto bar = [&](int slot, int which) { return bar0 + 8u * (uint32_t)(slot * 7 + which); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7 * G);
+  uint8_t* stage_all = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(bars + 7 * G + 2) + 15) & ~(uintptr_t)15);   // 1 KB per epilogue warp
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (uint32_t i = threadIdx.x; i < kW3 / 16; i += kTailThreads) reinterpret_cast<uint4*>(w3_s)[i] = __ldg(reinterpret_cast<const uint4*>(p.w3) + i);
+  for (uint32_t i = threadIdx.x; i < kW4 / 16; i += kTailThreads) {
+    reinterpret_cast<uint4*>(w4_s)[i] = __ldg(reinterpret_cast<const uint4*>(p.w4) + i);
+    reinterpret_cast<uint4*>(wo_s)[i] = __ldg(reinterpret_cast<const uint4*>(p.wo) + i);
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < G; ++s) {
+      ptx::mbar_init(bar(s, 0), 1);
+      ptx::mbar_init(bar(s, 1), 1);
+      ptx::mbar_init(bar(s, 2), 128);
+      ptx::mbar_init(bar(s, 3), 1);
+      ptx::mbar_init(bar(s, 4), 128);
+      ptx::mbar_init(bar(s, 5), 1);
+      ptx::mbar_init(bar(s, 6), 128);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 4 * G) {
+    ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_my = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
+
+  if (warp == 4 * G + 1) {
+    // =================================== TMA producer ==============================================
+    if (ptx::elect_one()) {
+      ptx::prefetch_tmap(&tm.m);
+      for (int t = 0; t < n_my; ++t) {
+        const int s = t % G;
+        ptx::mbar_wait(bar(s, 6), (((uint32_t)(t / G)) & 1u) ^ 1u);        // slot free
+        ptx::mbar_arrive_expect_tx(bar(s, 0), kA1);
+        const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
+        ptx::tma_load_2d(ptx::smem_u32(slots + (size_t)s * kSlot), &tm.m, bar(s, 0), 0, (int)(tile * 128));
+      }
+    }
+  } else if (warp == 4 * G) {
+    // =================================== MMA issuer ================================================
+    const bool leader = ptx::elect_one();
+    constexpr uint32_t idesc64 = umma_idesc_f16(IsBf16<T>::value, 64), idesc32 = umma_idesc_f16(IsBf16<T>::value, 32);
+    const uint32_t w3_lo = umma_desc_lo(ptx::smem_u32(w3_s), 64 * 16), w4_lo = umma_desc_lo(ptx::smem_u32(w4_s), 32 * 16),
+                   wo_lo = umma_desc_lo(ptx::smem_u32(wo_s), 32 * 16);
+    const uint32_t a1_hi = umma_desc_hi_swizzled(64);
+    for (int base = 0; base < n_my; base += G) {
+      const uint32_t par = ((uint32_t)(base / G)) & 1u;
+#pragma unroll 1
+      for (int phase = 0; phase < 3; ++phase) {
+#pragma unroll 1
+        for (int s = 0; s < G && base + s < n_my; ++s) {
+          ptx::mbar_wait(bar(s, phase * 2), par);                          // a1_full / a2_ready / a3_ready
+          ptx::tc_fence_after();
+          if (leader) {
+            const uint32_t slot16 = ptx::smem_u32(slots + (size_t)s * kSlot) >> 4;
+            const uint32_t d = tmem_base + (uint32_t)(s * 128);
+            if (phase == 0) {          // hid = x_in (128x32, swizzle-64B rows) * W3^T -> 64 columns
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks)
+                ptx::tc_mma_f16_lohi(d, (slot16 + 2u * ks) | (1u << 16), a1_hi, w3_lo + (uint32_t)(ks * 2 * 64), kUmmaDescHi, idesc64, (uint32_t)ks);
+            } else {                   // 128x64 planar operand ([8 cg][128 rows][16 B]) * W^T -> 32 columns
+              const uint32_t a16 = slot16 + ((phase == 1 ? kA1 : kA1 + kA2) >> 4);
+              const uint32_t w_lo = phase == 1 ? w4_lo : wo_lo;
+              const uint32_t dd = d + (phase == 1 ? 64u : 96u);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                ptx::tc_mma_f16_lohi(dd, (a16 + (uint32_t)(ks * 2 * 128)) | (128u << 16), kUmmaDescHi, w_lo + (uint32_t)(ks * 2 * 32), kUmmaDescHi, idesc32,
+                                     (uint32_t)ks);
+            }
+            ptx::tc_commit(bar(s, phase * 2 + 1));                         // h_full / s_full / o_full
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // =================================== epilogue groups ==========================================
+    const int g = warp >> 2, wq = warp & 3, row = wq * 32 + lane;
+    uint8_t* slot = slots + (size_t)g * kSlot;
+    uint8_t* a2 = slot + kA1;
+    uint8_t* a3 = a2 + kA2;
+    uint8_t* stage = stage_all + (size_t)warp * 1024;
+    const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(g * 128);
+    const T* xin = static_cast<const T*>(p.x_in);
+    const T* res = static_cast<const T*>(p.res);
+    T* out = static_cast<T*>(p.out);
+    uint32_t par = 0;
+    for (int t = g; t < n_my; t += G, par ^= 1u) {
+      const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
+      const long long pix = tile * 128 + row;
+      const bool valid = pix < p.total_px;
+      // operands that do not depend on the tensor core: x_in row (gates), residual row, channel gates of this crop
+      uint4 xraw[4], rraw[4];
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          xraw[i] = *reinterpret_cast<const uint4*>(xin + (size_t)pix * 32 + i * 8);
+          rraw[i] = *reinterpret_cast<const uint4*>(res + (size_t)pix * p.res_pitch + p.res_off + i * 8);
+        }
+      }
+      const float* sc = p.s_c + (size_t)(valid ? pix / p.px_per_crop : 0) * 32;
+      // ---- phase 1: hidden = relu(acc + b3) -> A2
+      ptx::mbar_wait(bar(g, 1), par);
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        float v[16];
+        ptx::tc_ld16(taddr + c0, v);
+        uint4 lo, hi;
+        T* e0 = reinterpret_cast<T*>(&lo);
+        T* e1 = reinterpret_cast<T*>(&hi);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          e0[c] = from_f32<T>(fmaxf(v[c] + __ldg(p.b3 + c0 + c), 0.f));
+          e1[c] = from_f32<T>(fmaxf(v[8 + c] + __ldg(p.b3 + c0 + 8 + c), 0.f));
+        }
+        *reinterpret_cast<uint4*>(a2 + ((size_t)(c0 / 8) * 128 + row) * 16) = lo;
+        *reinterpret_cast<uint4*>(a2 + ((size_t)(c0 / 8 + 1) * 128 + row) * 16) = hi;
+      }
+      ptx::fence_proxy_async();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(bar(g, 2));
+      // ---- phase 2: s_s = sigmoid(acc + b4); gated concat [x_in^2 * s_c | x_in * s_s] -> A3
+      ptx::mbar_wait(bar(g, 3), par);
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < 32; c0 += 16) {
+        float v[16];
+        ptx::tc_ld16(taddr + 64 + c0, v);
+        const T* xe = reinterpret_cast<const T*>(xraw) + c0;
+        uint4 g1lo, g1hi, g2lo, g2hi;
+        T* q1 = reinterpret_cast<T*>(&g1lo); T* q2 = reinterpret_cast<T*>(&g1hi);
+        T* q3 = reinterpret_cast<T*>(&g2lo); T* q4 = reinterpret_cast<T*>(&g2hi);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const float x = valid ? to_f32<T>(xe[c]) : 0.f;
+          const float ss = __fdividef(1.f, 1.f + __expf(-(v[c] + __ldg(p.b4 + c0 + c))));
+          const float a = x * (x * __ldg(sc + c0 + c)), b = x * ss;
+          if (c < 8) { q1[c] = from_f32<T>(a); q3[c] = from_f32<T>(b); }
+          else       { q2[c - 8] = from_f32<T>(a); q4[c - 8] = from_f32<T>(b); }
+        }
+        *reinterpret_cast<uint4*>(a3 + ((size_t)(c0 / 8) * 128 + row) * 16) = g1lo;
+        *reinterpret_cast<uint4*>(a3 + ((size_t)(c0 / 8 + 1) * 128 + row) * 16) = g1hi;
+        *reinterpret_cast<uint4*>(a3 + ((size_t)(4 + c0 / 8) * 128 + row) * 16) = g2lo;
+        *reinterpret_cast<uint4*>(a3 + ((size_t)(4 + c0 / 8 + 1) * 128 + row) * 16) = g2hi;
+      }
+      ptx::fence_proxy_async();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(bar(g, 4));
+      // ---- phase 3: out = x + acc + bo
+      ptx::mbar_wait(bar(g, 5), par);
+      ptx::tc_fence_after();
+      const int pix32 = valid ? (int)pix : -1;
+#pragma unroll
+      for (int c0 = 0; c0 < 32; c0 += 16) {
+        float v[16];
+        ptx::tc_ld16(taddr + 96 + c0, v);
+        if (c0 == 16) {                                                   // accumulators are in registers: free the slot
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(bar(g, 6));
+        }
+        const T* re = reinterpret_cast<const T*>(rraw) + c0;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] += __ldg(p.bo + c0 + c) + (valid ? to_f32<T>(re[c]) : 0.f);
+        store_chunk16_coalesced<T>(out, p.out_pitch, p.out_off + c0, pix32, v, stage, lane);
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 4 * G) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+template <typename T>
+inline const char* csar_tail_umma_launch(const TailUmmaParams& pin, bool fp16, int num_sms, cudaStream_t st) {
+  TailUmmaParams p = pin;
+  if (p.total_px >= (1LL << 31)) return "batch too large for 32-bit pixel indices";
+  if (p.res_pitch % 8 || p.res_off % 8 || p.out_pitch % 8 || p.out_off % 8) return "pitch/offset not 16-byte aligned";
+  p.n_tiles = (int)((p.total_px + 127) / 128);
+  TailTmap tm;
+  if (const char* msg = umma_make_tmap(&tm.m, p.x_in, fp16, 32, 32, false, 0, 0, 0, 128, 0, p.total_px)) return msg;
+  constexpr size_t kSlot = 128 * 64 + 2 * 128 * 128;
+  const size_t smem = 1024 + kTailGroups * kSlot + 32 * 64 * 2 + 2 * 64 * 32 * 2 + (7 * kTailGroups + 2) * 8 + 4 * kTailGroups * 1024 + 64;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(csar_tail_umma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+    configured = true;
+  }
+  csar_tail_umma_kernel<T><<<std::min(p.n_tiles, num_sms), kTailThreads, smem, st>>>(p, tm);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+template <> inline const char* csar_tail_umma_launch<float>(const TailUmmaParams&, bool, int, cudaStream_t) { return "16-bit only"; }
+
+}  // namespace lpsr

@@ -7,6 +7,7 @@
 #include "cuda_core_kernels.cuh"
 #include "engine_internal.h"
 #include "umma_conv.cuh"
+#include "csar_tail_umma.cuh"
 
 namespace lpsr {
 
@@ -148,6 +149,26 @@ void csar_block(Ctx& c, const WsLayout& L, char* ws, int B, size_t in_t, size_t 
         channel_gate_kernel<<<B, 32, 0, c.st>>>(pool, L.S, L.P, h->ca_w1, h->ca_b1, h->ca_w2, h->ca_b2, sc);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) c.rc = fail(h, LPSR_ERR_CUDA, "channel_gate launch: %s", cudaGetErrorString(e));
+      }
+      static int fused = -1;
+      if (fused < 0) { const char* e = getenv("LPSR_TAIL_FUSED"); fused = (e && e[0] == '0') ? 0 : 1; }
+      if (fused) {   // one kernel: three chained GEMMs, hidden and gated maps stay in shared memory / TMEM
+        c.begin("csar_tail_umma");
+        if (!c.dry && c.rc == LPSR_OK) {
+          TailUmmaParams tp{};
+          tp.x_in = xin;
+          tp.res = xres; tp.res_pitch = 32; tp.res_off = 0;
+          tp.out = yout; tp.out_pitch = 32; tp.out_off = 0;
+          tp.w3 = h->csar_sa1.u.w; tp.b3 = h->csar_sa1.u.bias;
+          tp.w4 = h->csar_sa2.u.w; tp.b4 = h->csar_sa2.u.bias;
+          tp.wo = h->csar_co.u.w; tp.bo = h->csar_co.u.bias;
+          tp.s_c = sc;
+          tp.total_px = (long long)B * L.P;
+          tp.px_per_crop = L.P;
+          const char* msg = csar_tail_umma_launch<T>(tp, h->cfg.precision == LPSR_PREC_FP16, h->num_sms, c.st);
+          if (msg) c.rc = fail(h, LPSR_ERR_CUDA, "csar_tail_umma launch: %s", msg);
+        }
+        return;
       }
       dense_conv<T>(c, h->csar_sa1, conv_params(h->csar_sa1, xin, 32, 0, 16, hid, 64, 0, B, L.Hp, L.Wp, true));
       c.begin("umma_conv_gate");
