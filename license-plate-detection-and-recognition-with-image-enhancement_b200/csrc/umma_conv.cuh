@@ -46,11 +46,11 @@ namespace lpsr {
 #define LPSR_UMMA_EPI_GROUPS 3
 #endif
 constexpr int kEpiGroups = LPSR_UMMA_EPI_GROUPS;   // epilogue groups == TMEM tile accumulators in flight
-constexpr int kUmmaThreads = (4 * kEpiGroups + 2) * 32;   // G x 4 epilogue warps, 1 MMA warp, 1 TMA producer warp
+constexpr int kUmmaThreads = (5 * kEpiGroups + 1) * 32;   // G x 4 epilogue warps, G MMA warps (one per accumulator), 1 TMA producer warp
 constexpr int kUmmaMaxKChunks = 8;      // TMA boxes (K-chunks of 16/32/64 channels) per item
 constexpr int kUmmaMaxSteps = 32;       // K-steps (MMAs per tap) per tile: Cin/16, or 28 pixel-pair steps of the 7x7 conv
-constexpr int kUmmaMmaWarp = 4 * kEpiGroups;
-constexpr int kUmmaFirstLoaderWarp = 4 * kEpiGroups + 1;
+constexpr int kUmmaMmaWarp = 4 * kEpiGroups;               // first of the G MMA warps
+constexpr int kUmmaFirstLoaderWarp = 5 * kEpiGroups;
 constexpr int kUmmaMaxK = 16;           // max M-tiles per item
 constexpr int kUmmaMaxBufs = 4;         // item buffers in the shared-memory ring
 
@@ -81,6 +81,7 @@ struct UmmaParams {
   const float* gate;                         // s_c [B][32]
   int out_off2;
   int px_per_crop;
+  long long* trace;                 // LPSR_UMMA_TRACE (profiling experiments): clock64 stamps of CTA 0 [role][tile][stamp]
   int debug;                        // LPSR_UMMA_DEBUG bitmask (profiling experiments only): 1 skip MMAs, 2 skip stores, 4 skip TMA loads
 };
 
@@ -231,7 +232,7 @@ __device__ __forceinline__ uint32_t umma_desc_hi_swizzled(uint32_t rowbytes) {
 template <typename T> struct IsBf16 { static constexpr bool value = false; };
 template <> struct IsBf16<__nv_bfloat16> { static constexpr bool value = true; };
 
-enum { kEpiPlain = 0, kEpiGate = 1, kEpiFinalSigmoid = 2 };   // 2: out channel 0 -> sigmoid -> fp32 [pixel] (final conv, lpsr.py:273-274)
+enum { kEpiPlain = 0, kEpiGate = 1, kEpiFinalSigmoid = 2, kEpiRelu = 3, kEpiResidual = 4 };   // FinalSigmoid: channel 0 -> sigmoid -> fp32 [pixel] (lpsr.py:273-274)
 
 // ---------------------------------------------------------------------------------------------------
 // the kernel
@@ -271,7 +272,9 @@ enum { kConv1x1 = 0, kConv3x3Taps = 1, kConv3x3Fold = 2, kConv7x7 = 3 };
 
 struct UmmaTmaps { CUtensorMap m[kUmmaMaxKChunks]; };   // one tiled map per K-chunk (its tensor, its box width)
 
-template <typename T, int NOUT, int MODE>
+// EPI (epilogue, compile time so the per-tile instruction stream carries no dead branches):
+//   kEpiPlain: +bias | kEpiRelu: +bias, ReLU | kEpiResidual: +bias, +residual | kEpiGate: CSAR gates | kEpiFinalSigmoid
+template <typename T, int NOUT, int MODE, int EPI>
 __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid_constant__ UmmaParams p, const __grid_constant__ UmmaTmaps tm) {
   static_assert(sizeof(T) == 2, "16-bit operands");
   constexpr bool FOLD = (MODE == kConv3x3Fold);
@@ -316,7 +319,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
   if (threadIdx.x == 0) {
     for (int s = 0; s < R; ++s) {
       ptx::mbar_init(full_bar(s), 1);                           // the producer's arrive.expect_tx; TMA completes the bytes
-      ptx::mbar_init(empty_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), G);                          // one tcgen05.commit per MMA warp and item
     }
     for (int a = 0; a < G; ++a) {
       ptx::mbar_init(tfull_bar(a), 1);
@@ -384,10 +387,12 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
         }
       }
     }
-  } else if (warp == kUmmaMmaWarp) {
-    // =================================== MMA issuer ================================================
-    // The whole warp runs the (uniform) control flow and waits; one elected lane issues MMAs and commits.  The per-tile
-    // path is kept to a handful of instructions: everything shape dependent sits in the `steps` table.
+  } else if (warp >= kUmmaMmaWarp) {
+    // =================================== MMA issuers ===============================================
+    // One MMA warp per accumulator / epilogue group: warp g issues the tiles whose turn is g.  The serial latency of one
+    // tile (barrier wake-up, descriptor set-up, MMA issue, commit: ~1000 clk measured) then overlaps G ways instead of
+    // bounding the whole CTA.  Each warp runs the (uniform) control flow; one elected lane issues MMAs and commits.
+    const int mg = warp - kUmmaMmaWarp;
     const bool leader = ptx::elect_one();
     constexpr uint32_t idesc = umma_idesc_f16(IsBf16<T>::value, NMMA);
     const uint32_t w_lo = umma_desc_lo(ptx::smem_u32(w_smem), (uint32_t)NMMA * 16);
@@ -397,7 +402,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
     const uint32_t tstride = (uint32_t)p.tstride;
     const bool no_mma = (p.debug & 1) != 0;
     __syncwarp();
-    uint32_t acc = 0, acc_par = 1;                            // accumulator ring position and the parity to wait for
+    const uint32_t acc = (uint32_t)mg;
+    uint32_t acc_par = 1;                                     // parity to wait for on this warp's tmem_empty barrier
+    int turn = 0;
     int buf = 0;
     uint32_t buf_par = 0;
     for (int ii = 0; ii < n_my_items; ++ii) {
@@ -405,7 +412,10 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
       ptx::tc_fence_after();
       uint32_t slot = K3 ? (uint32_t)slot_base_s[buf] : 0u;
       const uint32_t buf16 = a_smem16 + (uint32_t)buf * buf16_sz;
-      for (int m = 0; m < k_tiles; ++m) {
+      for (int m = 0; m < k_tiles; ++m, slot += tstride) {
+        const bool mine = (turn == mg);
+        if (++turn == G) turn = 0;
+        if (!mine) continue;
         ptx::mbar_wait(tempty_bar(acc), acc_par);             // the epilogue group drained this accumulator
         ptx::tc_fence_after();
         if (leader) {
@@ -426,81 +436,86 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
             }
           }
           ptx::tc_commit(tfull_bar(acc));                     // this tile's accumulator is complete
-          if (m == k_tiles - 1) ptx::tc_commit(empty_bar(buf));   // item buffer reusable once all MMAs retire
         }
         __syncwarp();
-        slot += tstride;
-        if (++acc == (uint32_t)G) { acc = 0; acc_par ^= 1u; }
+        acc_par ^= 1u;
       }
+      if (leader) ptx::tc_commit(empty_bar(buf));             // this warp's MMAs on the item buffer have retired (count G)
+      __syncwarp();
       if (++buf == R) { buf = 0; buf_par ^= 1u; }
     }
   } else {
-    // =================================== epilogue (two groups) ======================================
+    // =================================== epilogue groups ============================================
     const int grp = warp >> 2, wq = warp & 3;                   // group == TMEM accumulator (0..G-1), wq == TMEM lane quadrant
     const int row = wq * 32 + lane;                             // accumulator row
     constexpr int CH = 16;                                      // output channels handled per pass (bounds registers)
     constexpr int NRES = NOUT <= 32 ? NOUT * 2 / 16 : 1;        // raw residual registers (uint4) prefetched per tile
+    constexpr int NB = NOUT <= 32 ? NOUT : 1;
     T* out = static_cast<T*>(p.out);
     const T* res = static_cast<const T*>(p.res);
     float* xg = xchg + (size_t)grp * (2 * 4 * 2 * NOUT);
     uint8_t* stage = stage_all + (size_t)warp * 1024;
     const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(grp * NMMA);
-    uint32_t my_par = 0;                                        // parity of this group's tmem_full barrier
-    int turn = 0;                                               // which group owns the next tile (round robin, same order as the MMA warp)
-    const int pitch = p.pitch, tstride = p.tstride, k_tiles = p.k;
+    // everything the per-tile path needs lives in registers
+    const int pitch = p.pitch, tstride = p.tstride, k_tiles = p.k, Himg = p.H, Wimg = p.W, halo = p.halo, TWs = p.TW;
+    const int ips = p.items_per_strip, per_crop = p.n_strips * p.items_per_strip, crop_px = p.H * p.W;
+    const int out_pitch = p.out_pitch, out_off = p.out_off, res_pitch = p.res_pitch, res_off = p.res_off;
+    const int total_px32 = (int)p.total_px;
+    const bool skip_store = (p.debug & 2) != 0;
     const int adv_y = K3 ? tstride / pitch : 0, adv_x = K3 ? tstride - adv_y * pitch : 0;   // one tile further along the strip
+    float bias_r[NB];
+    if constexpr (NOUT <= 32) {
+#pragma unroll
+      for (int c = 0; c < NB; ++c) bias_r[c] = __ldg(p.bias + c);
+    }
+    uint32_t my_par = 0;                                        // parity of this group's tmem_full barrier
+    int turn = 0;                                               // which group owns the next tile (same round robin as the MMA warps)
     for (int ii = 0; ii < n_my_items; ++ii) {
       const int item = blockIdx.x + ii * gridDim.x;
-      // per item: one division per thread; per tile the row position advances incrementally
-      int y = 0, xs = 0, tw = 0, xbase = 0;                     // K3: strip row / strip column (halo included) of this thread's row
-      long long px = 0;                                         // 1x1: pixel index of this thread's row; K3: first pixel of the crop
+      // per item: one division per thread; per tile the row position advances incrementally (32-bit pixel indices)
+      int y = 0, xs = 0, tw = 0, xbase = 0, px = 0;             // K3: strip row / column of this thread's row, crop base; 1x1: pixel index
       if constexpr (K3) {
-        const int per_crop = p.n_strips * p.items_per_strip;
         const int n = item / per_crop;
         const int rem = item - n * per_crop;
-        const int strip = rem / p.items_per_strip, j = rem - strip * p.items_per_strip;
-        xbase = strip * p.TW - p.halo;                          // image x of strip column xs is xbase + xs
-        tw = min(p.TW, p.W - strip * p.TW);
+        const int strip = rem / ips, j = rem - strip * ips;
+        xbase = strip * TWs - halo;                             // image x of strip column xs is xbase + xs
+        tw = min(TWs, Wimg - strip * TWs) + halo;               // valid strip columns are [halo, tw)
         const int q = j * rows_per_item - (FOLD ? 1 : 0) + row; // linear strip position of this thread's row in tile 0 (>= -1)
         y = (q + pitch) / pitch - 1;
         xs = q - y * pitch;
-        px = (long long)n * p.H * p.W;
+        px = n * crop_px + xbase;
       } else {
-        px = (long long)item * rows_per_item + row;
+        px = item * rows_per_item + row;
       }
       for (int m = 0; m < k_tiles; ++m) {
         const bool mine = (turn == grp);
         if (++turn == G) turn = 0;
-        long long pix = -1;
-        if (mine) {
-          if constexpr (K3) {
-            // folded: rows 0 and 127 are the shuffle halo of the tile
-            if ((!FOLD || (row >= 1 && row <= 126)) && y >= 0 && y < p.H && xs >= p.halo && xs < p.halo + tw) pix = px + (long long)y * p.W + (xbase + xs);
-          } else {
-            if (px < p.total_px) pix = px;
-          }
-        }
-        if constexpr (K3) {                                     // advance to the next tile (1-2 strip rows for the usual pitch ~ 100)
-          xs += adv_x;
+        int pix = -1;
+        if constexpr (K3) {
+          // folded: rows 0 and 127 are the shuffle halo of the tile
+          if ((!FOLD || (row >= 1 && row <= 126)) && (unsigned)y < (unsigned)Himg && xs >= halo && xs < tw) pix = px + y * Wimg + xs;
+          xs += adv_x;                                          // advance to the next tile
           y += adv_y;
           if (xs >= pitch) { xs -= pitch; ++y; }
         } else {
+          if (px < total_px32) pix = px;
           px += 128;
         }
         if (!mine) continue;
         // operands that do not depend on the accumulator are requested before waiting for it
         uint4 rsd_raw[NRES];                                    // raw 16-bit residual: converted only after the accumulator arrived
-        const bool has_res = (p.mode == kEpiPlain && res != nullptr && pix >= 0);
-        if constexpr (NOUT <= 32) {
-          if (has_res) {
+        if constexpr (EPI == kEpiResidual && NOUT <= 32) {
+          if (pix >= 0) {
 #pragma unroll
-            for (int i = 0; i < NRES; ++i) rsd_raw[i] = *reinterpret_cast<const uint4*>(res + (size_t)pix * p.res_pitch + p.res_off + i * 8);
+            for (int i = 0; i < NRES; ++i) rsd_raw[i] = *reinterpret_cast<const uint4*>(res + (size_t)pix * res_pitch + res_off + i * 8);
           }
         }
         ptx::mbar_wait(tfull_bar(grp), my_par);
         ptx::tc_fence_after();
         float* xb = xg + (size_t)my_par * (4 * 2 * NOUT);
         my_par ^= 1u;
+        const bool valid = pix >= 0 && !skip_store;
+        const int pix32 = valid ? pix : -1;
 #pragma unroll
         for (int cc = 0; cc < NOUT; cc += CH) {
           float v[CH];
@@ -547,49 +562,57 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
 #pragma unroll
             for (int c = 0; c < CH; ++c) v[c] += lf[c] + rg[c];
           } else {
-#pragma unroll
-            for (int c0 = 0; c0 < CH; c0 += 16) ptx::tc_ld16_nowait(taddr + cc + c0, &v[c0]);
+            ptx::tc_ld16_nowait(taddr + cc, v);
             ptx::tc_wait_ld();
             if (cc + CH >= NOUT) {
               ptx::tc_fence_before();
               ptx::mbar_arrive(tempty_bar(grp));
             }
           }
-          const bool valid = pix >= 0 && !(p.debug & 2);
-          float g1[CH];                                         // gate mode: channel-branch output
-          if (valid) {
+          if constexpr (NOUT <= 32) {
+#pragma unroll
+            for (int c = 0; c < CH; ++c) v[c] += bias_r[cc + c];
+          } else {
 #pragma unroll
             for (int c = 0; c < CH; c += 4) {
               const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cc + c));
               v[c] += b4.x; v[c + 1] += b4.y; v[c + 2] += b4.z; v[c + 3] += b4.w;
             }
-            if (p.mode == kEpiGate) {
-              // CSAR gates (1x1, NOUT = 32): spatial branch x_in * sigmoid(.), channel branch x_in^2 * s_c
-              if constexpr (NOUT == 32 && MODE == kConv1x1) {
-                float xi[CH];
-                load_vec<T, CH>(static_cast<const T*>(p.aux) + (size_t)pix * p.aux_pitch + p.aux_off + cc, xi);
-                const float4* sc4 = reinterpret_cast<const float4*>(p.gate + (size_t)(pix / p.px_per_crop) * NOUT + cc);
+          }
+          if constexpr (EPI == kEpiFinalSigmoid) {
+            // final conv (Cout = 1, padded to 16): channel 0 only, fp32; lanes are consecutive pixels -> coalesced 4-byte stores
+            if (valid) static_cast<float*>(p.out)[pix] = __fdividef(1.f, 1.f + __expf(-v[0]));
+          } else if constexpr (EPI == kEpiGate) {
+            // CSAR gates (1x1, NOUT = 32): spatial branch x_in * sigmoid(.), channel branch x_in^2 * s_c
+            float g1[CH];
+            if (valid) {
+              float xi[CH];
+              load_vec<T, CH>(static_cast<const T*>(p.aux) + (size_t)pix * p.aux_pitch + p.aux_off + cc, xi);
+              const float4* sc4 = reinterpret_cast<const float4*>(p.gate + (size_t)(pix / p.px_per_crop) * NOUT + cc);
 #pragma unroll
-                for (int c = 0; c < CH; c += 4) {
-                  const float4 s4 = __ldg(sc4 + c / 4);
-                  const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+              for (int c = 0; c < CH; c += 4) {
+                const float4 s4 = __ldg(sc4 + c / 4);
+                const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    // 16-bit modes: ex2.approx-based logistic (the result is rounded to bf16/fp16 anyway)
-                    v[c + j] = xi[c + j] * __fdividef(1.f, 1.f + __expf(-v[c + j]));
-                    g1[c + j] = xi[c + j] * (xi[c + j] * sv[j]);
-                  }
+                for (int j = 0; j < 4; ++j) {
+                  // 16-bit modes: ex2.approx-based logistic (the result is rounded to bf16/fp16 anyway)
+                  v[c + j] = xi[c + j] * __fdividef(1.f, 1.f + __expf(-v[c + j]));
+                  g1[c + j] = xi[c + j] * (xi[c + j] * sv[j]);
                 }
               }
-            } else {
-              if (p.relu) {
+            }
+            store_chunk16_coalesced<T>(out, out_pitch, out_off + cc, pix32, g1, stage, lane);
+            store_chunk16_coalesced<T>(out, out_pitch, p.out_off2 + cc, pix32, v, stage, lane);
+          } else {
+            if constexpr (EPI == kEpiRelu) {
 #pragma unroll
-                for (int c = 0; c < CH; ++c) v[c] = fmaxf(v[c], 0.f);
-              }
-              if (has_res) {
+              for (int c = 0; c < CH; ++c) v[c] = fmaxf(v[c], 0.f);
+            }
+            if constexpr (EPI == kEpiResidual) {
+              if (valid) {
                 float r[CH];
                 if constexpr (NOUT > 32) {
-                  load_vec<T, CH>(res + (size_t)pix * p.res_pitch + p.res_off + cc, r);
+                  load_vec<T, CH>(res + (size_t)pix * res_pitch + res_off + cc, r);
                 } else {
                   const T* re = reinterpret_cast<const T*>(rsd_raw) + cc;
 #pragma unroll
@@ -599,19 +622,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
                 for (int c = 0; c < CH; ++c) v[c] += r[c];
               }
             }
-          }
-          // all 32 lanes take part in the staged, coalesced store (rows without a pixel are skipped inside)
-          const int pix32 = valid ? (int)pix : -1;
-          if (p.mode == kEpiFinalSigmoid) {
-            // final conv (Cout = 1, padded to 16): channel 0 only, fp32; lanes are consecutive pixels -> coalesced 4-byte stores
-            if (valid) static_cast<float*>(p.out)[pix] = __fdividef(1.f, 1.f + __expf(-v[0]));
-          } else if (p.mode == kEpiGate) {
-            if constexpr (NOUT == 32 && MODE == kConv1x1) {
-              store_chunk16_coalesced<T>(out, p.out_pitch, p.out_off + cc, pix32, g1, stage, lane);
-              store_chunk16_coalesced<T>(out, p.out_pitch, p.out_off2 + cc, pix32, v, stage, lane);
-            }
-          } else {
-            store_chunk16_coalesced<T>(out, p.out_pitch, p.out_off + cc, pix32, v, stage, lane);
+            // all 32 lanes take part in the staged, coalesced store (rows without a pixel are skipped inside)
+            store_chunk16_coalesced<T>(out, out_pitch, out_off + cc, pix32, v, stage, lane);
           }
         }
       }
@@ -621,7 +633,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
   // ---- teardown -----------------------------------------------------------------------------------
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == kUmmaMmaWarp) ptx::tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == kUmmaMmaWarp) ptx::tmem_dealloc(tmem_base, kTmemCols);   // the warp that allocated
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -674,6 +686,8 @@ inline const char* umma_make_tmap(CUtensorMap* out, const void* base, bool fp16,
   }
   return r == CUDA_SUCCESS ? nullptr : "cuTensorMapEncodeTiled failed";
 }
+
+inline long long*& umma_trace_buffer() { static long long* b = nullptr; return b; }
 
 inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvParams& cp, int num_sms, bool fp16, bool fp32_out = false) {
   UmmaParams& p = plan.p;
@@ -733,6 +747,7 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("LPSR_UMMA_DEBUG"); dbg = e ? atoi(e) : 0; }
     p.debug = dbg;
+    p.trace = nullptr;
   }
   const size_t w_bytes = ((size_t)ntap * w.cin * NMMA * 2 + 127) & ~(size_t)127;
   const size_t fixed = w_bytes + (2 * kUmmaMaxBufs + 2 * kEpiGroups + 2) * 8 + kEpiGroups * 2 * 4 * 2 * N * 4 + 640 /*steps, slot_base*/ + 4 * kEpiGroups * 1024 /*store staging*/ + 1024 /*alignment slack*/ + 256;
@@ -820,30 +835,46 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
   return nullptr;
 }
 
-template <typename T, int N, int MODE>
+template <typename T, int N, int MODE, int EPI>
 inline const char* umma_launch_inst(const UmmaPlan& plan, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(umma_conv_kernel<T, N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(umma_conv_kernel<T, N, MODE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return cudaGetErrorString(e);
     configured = true;
   }
-  umma_conv_kernel<T, N, MODE><<<plan.grid, kUmmaThreads, plan.smem_bytes, st>>>(plan.p, plan.tm);
+  umma_conv_kernel<T, N, MODE, EPI><<<plan.grid, kUmmaThreads, plan.smem_bytes, st>>>(plan.p, plan.tm);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
+// epilogue selection: plain / ReLU / residual (mutually exclusive in this network) or the special modes
+template <typename T, int N, int MODE>
+inline const char* umma_launch_epi(const UmmaPlan& plan, cudaStream_t st) {
+  const UmmaParams& p = plan.p;
+  if (p.mode == kEpiPlain && p.relu && p.res) return "ReLU + residual epilogue is not instantiated";
+  if (p.mode == kEpiPlain && p.res) return umma_launch_inst<T, N, MODE, kEpiResidual>(plan, st);
+  if (p.mode == kEpiPlain && p.relu) return umma_launch_inst<T, N, MODE, kEpiRelu>(plan, st);
+  if (p.mode == kEpiPlain) return umma_launch_inst<T, N, MODE, kEpiPlain>(plan, st);
+  if constexpr (N == 32 && MODE == kConv1x1) {
+    if (p.mode == kEpiGate) return umma_launch_inst<T, N, MODE, kEpiGate>(plan, st);
+  }
+  if constexpr (N == 16 && MODE == kConv3x3Fold) {
+    if (p.mode == kEpiFinalSigmoid) return umma_launch_inst<T, N, MODE, kEpiFinalSigmoid>(plan, st);
+  }
+  return "epilogue mode not instantiated for this shape";
+}
+
 template <typename T>
 inline const char* umma_plan_launch(const UmmaPlan& plan, const UmmaWeights& w, cudaStream_t st) {
-  if (w.ks == 7) return w.cout == 32 ? umma_launch_inst<T, 32, kConv7x7>(plan, st) : "unsupported Cout";
+  if (w.ks == 7) return w.cout == 32 ? umma_launch_epi<T, 32, kConv7x7>(plan, st) : "unsupported Cout";
   if (w.ks == 3) {
-    if (w.cout == 16) return umma_launch_inst<T, 16, kConv3x3Fold>(plan, st);
-    if (w.cout == 32) return umma_fold(3, 32) ? umma_launch_inst<T, 32, kConv3x3Fold>(plan, st) : umma_launch_inst<T, 32, kConv3x3Taps>(plan, st);
-    if (w.cout == 64) return umma_launch_inst<T, 64, kConv3x3Taps>(plan, st);
+    if (w.cout == 16) return umma_launch_epi<T, 16, kConv3x3Fold>(plan, st);
+    if (w.cout == 32) return umma_launch_epi<T, 32, kConv3x3Taps>(plan, st);
   } else {
-    if (w.cout == 16) return umma_launch_inst<T, 16, kConv1x1>(plan, st);
-    if (w.cout == 32) return umma_launch_inst<T, 32, kConv1x1>(plan, st);
-    if (w.cout == 64) return umma_launch_inst<T, 64, kConv1x1>(plan, st);
+    if (w.cout == 16) return umma_launch_epi<T, 16, kConv1x1>(plan, st);
+    if (w.cout == 32) return umma_launch_epi<T, 32, kConv1x1>(plan, st);
+    if (w.cout == 64) return umma_launch_epi<T, 64, kConv1x1>(plan, st);
   }
   return "unsupported Cout";
 }

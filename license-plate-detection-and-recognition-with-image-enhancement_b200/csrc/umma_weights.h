@@ -31,7 +31,7 @@ inline bool umma_enabled() {
 inline bool umma_supported(int ks, int cin, int cout) {
   if (!umma_enabled() || cin % 16 != 0 || cin < 16 || cin > 16 * kMaxChunks) return false;
   if (ks == 1) return cout == 16 || cout == 32 || cout == 64;
-  if (ks == 3) return cout == 16 || cout == 32 || cout == 64;
+  if (ks == 3) return cout == 16 || cout == 32;
   return false;
 }
 
@@ -39,7 +39,8 @@ inline bool umma_supported(int ks, int cin, int cout) {
 inline bool umma_fold(int ks, int cout) {
   static int fold32 = -1;
   if (fold32 < 0) { const char* e = getenv("LPSR_FOLD32"); fold32 = (e && e[0] == '1') ? 1 : 0; }
-  return ks == 3 && (cout == 16 || (cout == 32 && fold32));
+  (void)fold32;
+  return ks == 3 && cout == 16;
 }
 
 inline uint16_t f32_to_bf16_bits(float f) {

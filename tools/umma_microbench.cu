@@ -9,15 +9,18 @@
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(128, 1) bench(int N, int n_acc, int iters, int a_shift_slots, int k_per_acc, long long* out, int rowbytes) {
+__global__ void __launch_bounds__(416, 1) bench(int N, int n_acc, int iters, int a_shift_slots, int k_per_acc, long long* out, int rowbytes, int interf, volatile int* stop_flag, float* sink) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t bar, bar2;
+  __shared__ uint64_t bar, bar2, bar3;
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < 48 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;  // fp16 1.0
+  __shared__ volatile int done;
+  if (threadIdx.x == 0) done = 0;
+  for (int i = threadIdx.x; i < 48 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;  // fp16 1.0
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar3)));
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   if (warp == 0) {
@@ -79,6 +82,40 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int n_acc, int iters, int
     }
     long long t1 = clock64();
     if (blockIdx.x == 0) { out[0] = t1 - t0; out[1] = t_issue - t0; }
+    done = 1;
+  } else if (warp >= 4 && interf) {
+    // interference warps (warps 4..12): run until the MMA thread is done
+    float acc = 0.f;
+    uint32_t bphase = 0;
+    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 384;   // columns away from the accumulators
+    uint32_t* sm32 = reinterpret_cast<uint32_t*>(smem + 50 * 1024);
+    while (!done) {
+      if (interf == 1) {
+        uint32_t r[16];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                       "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;");
+        acc += __uint_as_float(r[3]);
+      } else if (interf == 2) {
+        for (int k = 0; k < 8; ++k) { sm32[(threadIdx.x * 4 + k * 1024) & 1023] = threadIdx.x; acc += sm32[(threadIdx.x + k * 33) & 1023]; }
+      } else if (interf == 4) {
+        // bulk-async (TMA engine) copies global -> smem, 4 x 16 KB in flight, from one lane
+        if (warp == 4 && (threadIdx.x & 31) == 0) {
+          const uint32_t b2 = smem_u32(&bar3);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b2), "r"(65536) : "memory");
+          for (int k = 0; k < 4; ++k)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(smem + 56 * 1024 + k * 16384)), "l"(reinterpret_cast<const char*>(sink) + ((size_t)blockIdx.x * 4 + k) * 65536 + (size_t)(bphase & 7) * 1048576), "r"(16384), "r"(b2) : "memory");
+          uint32_t ok = 0;
+          while (!ok) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(b2), "r"(bphase & 1) : "memory");
+          ++bphase;
+        }
+      } else if (interf == 3) {
+        for (int k = 0; k < 4; ++k) sink[(size_t)blockIdx.x * 65536 + ((threadIdx.x * 8 + k * 4096) & 65535)] = acc;
+      }
+    }
+    if (acc == 123.456f) sink[0] = acc;
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
@@ -88,21 +125,23 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int n_acc, int iters, int
 int main() {
   long long* d_out;
   cudaMalloc(&d_out, 16);
-  cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
   const int iters = 4608;
   printf("%5s %6s %6s %6s %6s | %10s %10s\n", "N", "n_acc", "rowB", "k/acc", "shift", "clk/MMA", "issue/MMA");
-  for (int N : {16, 32, 48, 96, 256}) {
+  float* d_sink; cudaMalloc(&d_sink, (size_t)148 * 65536 * 4 + 16 * 1048576);
+  for (int interf : {0, 4})
+  for (int N : {32, 48}) {
     for (int n_acc : {2}) {
       if (n_acc * N > 512) continue;
-      for (int kpa : {1, 3}) {
+      for (int kpa : {3}) {
         for (int shift : {99}) {
-         for (int rowbytes : {16, 64}) {
-          bench<<<148, 128, 56 * 1024>>>(N, n_acc, iters, shift, kpa, d_out, rowbytes);
+         for (int rowbytes : {64}) {
+          bench<<<148, 416, 124 * 1024>>>(N, n_acc, iters, shift, kpa, d_out, rowbytes, interf, nullptr, d_sink);
           cudaError_t e = cudaDeviceSynchronize();
           if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
           long long h[2];
           cudaMemcpy(h, d_out, 16, cudaMemcpyDeviceToHost);
-          printf("%5d %6d %6d %6d %6d | %10.1f %10.1f\n", N, n_acc, rowbytes, kpa, shift, (double)h[0] / iters, (double)h[1] / iters);
+          printf("interf %d %5d %6d %6d %6d %6d | %10.1f %10.1f\n", interf, N, n_acc, rowbytes, kpa, shift, (double)h[0] / iters, (double)h[1] / iters);
          }
         }
       }
