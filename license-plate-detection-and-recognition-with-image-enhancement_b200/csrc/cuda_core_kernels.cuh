@@ -180,6 +180,47 @@ __global__ void __launch_bounds__(kThreads) ae_conv_in_kernel(const float* __res
   }
 }
 
+// Tensor-core AutoEncoder front end: the caller's NCHW fp32 crop, zero padded to (H, W) (lpsr.py:107-111), as the half-grid
+// "space-to-depth" operand [B][H/2][W/2][16]: channel (i*2 + j)*3 + c is input channel c of pixel (2y + i, 2x + j), 12..15 zero.
+// One thread per half-grid pixel: float2 loads (two horizontally adjacent pixels), one 32-byte store.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) ae_unshuffle_in_kernel(const float* __restrict__ x, T* __restrict__ out, int B, int H, int W,
+                                                                   int inH, int inW) {
+  const int Ho = H >> 1, Wo = W >> 1;
+  const long long total = (long long)B * Ho * Wo;
+  const bool vec = (inW % 2 == 0);                               // float2 alignment of every (even-x) pixel pair
+  for (long long pix = blockIdx.x * (long long)kThreads + threadIdx.x; pix < total; pix += (long long)gridDim.x * kThreads) {
+    const int xo = (int)(pix % Wo), yo = (int)((pix / Wo) % Ho), n = (int)(pix / ((long long)Wo * Ho));
+    uint4 q[2];
+    T* e = reinterpret_cast<T*>(q);
+#pragma unroll
+    for (int c = 12; c < 16; ++c) e[c] = from_f32<T>(0.f);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* plane = x + ((size_t)n * 3 + c) * inH * inW;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int y = 2 * yo + i, xq = 2 * xo;
+        float a = 0.f, b = 0.f;
+        if (y < inH) {
+          if (vec && xq + 1 < inW) {
+            const float2 t = __ldg(reinterpret_cast<const float2*>(plane + (size_t)y * inW + xq));
+            a = t.x; b = t.y;
+          } else {
+            if (xq < inW) a = __ldg(plane + (size_t)y * inW + xq);
+            if (xq + 1 < inW) b = __ldg(plane + (size_t)y * inW + xq + 1);
+          }
+        }
+        e[(i * 2 + 0) * 3 + c] = from_f32<T>(a);
+        e[(i * 2 + 1) * 3 + c] = from_f32<T>(b);
+      }
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + (size_t)pix * 16);
+    o[0] = q[0];
+    o[1] = q[1];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // DConv + pixel (un)shuffle + ReLU (+ skip add)
 // ---------------------------------------------------------------------------------------------------
@@ -539,14 +580,17 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict
   }
 }
 
+// unshuffled != 0: the [C,H,W] tensor is STORED as its PixelUnshuffle(2), [B][H/2][W/2][pitch] with channel c*4 + i*2 + j (the
+// tensor-core AutoEncoder keeps full-resolution tensors that way)
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int B, int C, int H, int W,
-                                    int pitch, int off) {
+                                    int pitch, int off, int unshuffled) {
   const size_t total = (size_t)B * C * H * W;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int x = (int)(i % W), y = (int)((i / W) % H), c = (int)((i / ((size_t)W * H)) % C);
     const int n = (int)(i / ((size_t)W * H * C));
-    dst[i] = to_f32<T>(src[((size_t)(n * H + y) * W + x) * pitch + off + c]);
+    const size_t s = unshuffled ? unshuffle2_dst(n, y, x, c, H, W, pitch, off) : ((size_t)(n * H + y) * W + x) * pitch + off + c;
+    dst[i] = to_f32<T>(src[s]);
   }
 }
 

@@ -143,6 +143,119 @@ bool pack_conv(lpsr_handle* h, ConvW& cw, const std::string& prefix, int cin, in
   return true;
 }
 
+// ---- tensor-core AutoEncoder weights ---------------------------------------------------------------------
+// One stage of the AutoEncoder as a dense ks x ks convolution on its own grid: w[co][ci][ks*ks], b[co]
+struct DenseConv {
+  int cin = 0, cout = 0, ks = 0;
+  std::vector<float> w, b;
+};
+
+// DConv (lpsr.py:8-28) = depthwise ks x ks (+bias) then pointwise 1x1 (+bias) with NO activation in between, i.e. one dense
+// conv: w[co][ci][t] = pw[co][ci] * dw[ci][t]; the depthwise bias is added at every pixel ('same' zero padding pads the INPUT),
+// so it folds exactly: b[co] = pw_b[co] + sum_ci pw[co][ci] * dw_b[ci]
+DenseConv compose_dconv(const lpsr_handle* h, const std::string& p, int cin, int cout, int ks) {
+  DenseConv d;
+  d.cin = cin; d.cout = cout; d.ks = ks;
+  const std::vector<float>&dw = W(h, p + "0.weight"), &dwb = W(h, p + "0.bias"), &pw = W(h, p + "1.weight"), &pwb = W(h, p + "1.bias");
+  d.w.resize((size_t)cout * cin * ks * ks);
+  d.b.resize(cout);
+  for (int co = 0; co < cout; ++co) {
+    double acc = pwb[co];
+    for (int ci = 0; ci < cin; ++ci) {
+      acc += (double)pw[(size_t)co * cin + ci] * dwb[ci];
+      for (int t = 0; t < ks * ks; ++t)
+        d.w[((size_t)co * cin + ci) * ks * ks + t] = pw[(size_t)co * cin + ci] * dw[(size_t)ci * ks * ks + t];
+    }
+    d.b[co] = (float)acc;
+  }
+  return d;
+}
+
+// The same convolution evaluated on the 2x COARSER grid (space-to-depth): a coarse pixel carries its 2x2 fine pixels as channels,
+// fine output row 2h + I reads fine rows 2h + I + dy - R = 2(h + th) + i, th in {-1,0,1} for any ks <= 5, so the coarse kernel is
+// 3x3 with w'[n(co,I,J)][k(ci,i,j)][th][tw] = w[co][ci][2th + i - I + R][2tw + j - J + R] (zero where that tap does not exist).
+// in_index / out_index give the operand's channel order (out_index < 0: column not produced by this launch).
+// Returns [9][cin_cols][cout_cols] fp32 (the layout umma_pack_weights takes) and the per-column bias.
+template <typename InIdx, typename OutIdx>
+void s2d_weights(const DenseConv& d, int cin_cols, int cout_cols, InIdx in_index, OutIdx out_index, std::vector<float>& pw,
+                 std::vector<float>& pb) {
+  const int R = d.ks / 2;
+  pw.assign((size_t)9 * cin_cols * cout_cols, 0.f);
+  pb.assign(cout_cols, 0.f);
+  for (int co = 0; co < d.cout; ++co)
+    for (int I = 0; I < 2; ++I)
+      for (int J = 0; J < 2; ++J) {
+        const int n = out_index(co, I, J);
+        if (n < 0) continue;
+        pb[n] = d.b.empty() ? 0.f : d.b[co];
+        for (int ci = 0; ci < d.cin; ++ci)
+          for (int i = 0; i < 2; ++i)
+            for (int j = 0; j < 2; ++j) {
+              const int k = in_index(ci, i, j);
+              for (int th = -1; th <= 1; ++th) {
+                const int dy = 2 * th + i - I + R;
+                if (dy < 0 || dy >= d.ks) continue;
+                for (int tw = -1; tw <= 1; ++tw) {
+                  const int dx = 2 * tw + j - J + R;
+                  if (dx < 0 || dx >= d.ks) continue;
+                  pw[((size_t)((th + 1) * 3 + (tw + 1)) * cin_cols + k) * cout_cols + n] = d.w[((size_t)co * d.cin + ci) * d.ks * d.ks + dy * d.ks + dx];
+                }
+              }
+            }
+      }
+}
+
+// dense conv at its own grid: [ks*ks][cin][cout_cols] (columns >= cout are zero)
+void plain_weights(const DenseConv& d, int cout_cols, std::vector<float>& pw, std::vector<float>& pb) {
+  pw.assign((size_t)d.ks * d.ks * d.cin * cout_cols, 0.f);
+  pb.assign(cout_cols, 0.f);
+  for (int co = 0; co < d.cout; ++co) {
+    pb[co] = d.b.empty() ? 0.f : d.b[co];
+    for (int ci = 0; ci < d.cin; ++ci)
+      for (int t = 0; t < d.ks * d.ks; ++t) pw[((size_t)t * d.cin + ci) * cout_cols + co] = d.w[((size_t)co * d.cin + ci) * d.ks * d.ks + t];
+  }
+}
+
+bool pack_ae_tensor_core(lpsr_handle* h) {
+  const bool fp16 = true;   // the AutoEncoder stages run fp16 operands in both 16-bit modes (ae_forward_tc)
+  auto put16 = [&](const std::vector<uint16_t>& v) { return arena_put(h, v); };
+  auto put32 = [&](const std::vector<float>& v) { return arena_put(h, v); };
+  auto unshuffle_idx = [](int c, int i, int j) { return c * 4 + i * 2 + j; };   // PixelUnshuffle / PixelShuffle channel order
+  std::vector<float> pw, pb;
+  bool ok = true;
+  // conv_in 3 -> 12 (3x3, no bias) on the half grid: operand = ae_unshuffle_in_kernel's [(i*2+j)*3 + c] (12 real of 16), output =
+  // PixelUnshuffle(c0): 48 channels
+  DenseConv cin;
+  cin.cin = 3; cin.cout = 12; cin.ks = 3; cin.w = W(h, "auto_encoder.conv_in.weight");
+  s2d_weights(cin, 16, 48, [](int c, int i, int j) { return (i * 2 + j) * 3 + c; }, unshuffle_idx, pw, pb);
+  ok &= umma_pack_weights(h->aet_in, pw.data(), nullptr, 3, 16, 48, fp16, put16, put32);
+  // encoder.0: DConv 12 -> 12 at full resolution + PixelUnshuffle == 48 -> 48 on the half grid (lpsr.py:71-73)
+  const DenseConv e0 = compose_dconv(h, "auto_encoder.encoder.0.dConv.", 12, 12, 5);
+  s2d_weights(e0, 48, 48, unshuffle_idx, unshuffle_idx, pw, pb);
+  ok &= umma_pack_weights(h->aet_enc0, pw.data(), pb.data(), 3, 48, 48, fp16, put16, put32);
+  // encoder.3: DConv 48 -> 12 on the half grid (5x5 taps); PixelUnshuffle + ReLU in the store (lpsr.py:74-80)
+  const DenseConv e1 = compose_dconv(h, "auto_encoder.encoder.3.dConv.", 48, 12, 5);
+  plain_weights(e1, 16, pw, pb);
+  ok &= umma_pack_weights(h->aet_enc1, pw.data(), pb.data(), 5, 48, 16, fp16, put16, put32);
+  // decoder.0: DConv 48 -> 48 on the quarter grid; its PixelShuffle is only a relabeling for the next stage (lpsr.py:83-89)
+  const DenseConv d0 = compose_dconv(h, "auto_encoder.decoder.0.dConv.", 48, 48, 5);
+  plain_weights(d0, 48, pw, pb);
+  ok &= umma_pack_weights(h->aet_dec0, pw.data(), pb.data(), 5, 48, 48, fp16, put16, put32);
+  // decoder.3: DConv 12 -> 48 on the half grid == 48 -> 4 x 48 on the quarter grid; one launch per output row parity I, columns
+  // J*48 + co are half-grid pixel (2h + I, 2w + J) whose 48 channels are PixelUnshuffle(full-resolution 12 channels) (lpsr.py:90-96)
+  const DenseConv d1 = compose_dconv(h, "auto_encoder.decoder.3.dConv.", 12, 48, 5);
+  for (int I0 = 0; I0 < 2; ++I0) {
+    s2d_weights(d1, 48, 96, unshuffle_idx, [I0](int co, int I, int J) { return I == I0 ? J * 48 + co : -1; }, pw, pb);
+    ok &= umma_pack_weights(h->aet_dec1[I0], pw.data(), pb.data(), 3, 48, 96, fp16, put16, put32);
+  }
+  // conv_out 12 -> 3 (3x3, no bias) on the half grid: columns (I*2+J)*4 + co (3 real of 4) -> 8-channel full-resolution pixels
+  DenseConv co;
+  co.cin = 12; co.cout = 3; co.ks = 3; co.w = W(h, "auto_encoder.conv_out.weight");
+  s2d_weights(co, 48, 16, unshuffle_idx, [](int c, int I, int J) { return (I * 2 + J) * 4 + c; }, pw, pb);
+  ok &= umma_pack_weights(h->aet_out, pw.data(), nullptr, 3, 48, 16, fp16, put16, put32);
+  return ok;
+}
+
 int pack_all(lpsr_handle* h) {
   const int C = h->cfg.num_channels, F = h->cfg.num_features, G = h->cfg.growth_rate, L = h->cfg.num_layers, E = 4 * C;
   if (!h->arena.base) {
@@ -196,6 +309,11 @@ int pack_all(lpsr_handle* h) {
         for (int t = 0; t < 9; ++t) p16[((size_t)t * 16 + ci) * 16 + co] = wo[((size_t)co * E + ci) * 9 + t];
     ok &= umma_pack_weights(h->ae_out_u, p16.data(), nullptr, 3, 16, 16, h->cfg.precision == LPSR_PREC_FP16,
                             [&](const std::vector<uint16_t>& v) { return arena_put(h, v); }, [&](const std::vector<float>& v) { return arena_put(h, v); });
+  }
+  h->ae_tc = false;
+  if (half_mode(h) && umma_enabled() && C == 3 && h->sfe1_u.packed && !getenv("LPSR_AE_CUDA_CORES")) {
+    ok &= pack_ae_tensor_core(h);
+    h->ae_tc = ok;
   }
   ok &= pack_conv(h, h->sfe2, "rdn.shallowF2", F, F, 3, true);
   for (int r = 0; r < 2; ++r) {
@@ -260,6 +378,7 @@ WsLayout ws_layout(const lpsr_handle* h, int B, int H, int W) {
   const size_t es = elem_size(h), BP = (size_t)B * L.P;
   size_t off = 0;
   auto take = [&](size_t elems, size_t esz) { size_t o = off; off = align_up(off + elems * esz, 256); return o; };
+  L.xu = take(BP / 4 * 16, es);   // tensor-core AutoEncoder: the input crop as a half-grid space-to-depth operand
   L.c0 = take(BP * 12, es);
   L.e0 = take(BP / 4 * 48, es);
   L.e1 = take(BP / 16 * 48, es);
@@ -321,10 +440,10 @@ static int pixel_remap(const float* x, float* y, int B, int C, int H, int W, voi
   nchw_to_nhwc_kernel<float><<<blocks, 256, 0, st>>>(x, a, B, C, H, W, C, 0);
   if (mode == kShuffleDown) {
     pixel_remap_nhwc_kernel<kShuffleDown><<<blocks, 256, 0, st>>>(a, b, B, C, H, W);
-    nhwc_to_nchw_kernel<float><<<blocks, 256, 0, st>>>(b, y, B, C * 4, H / 2, W / 2, C * 4, 0);
+    nhwc_to_nchw_kernel<float><<<blocks, 256, 0, st>>>(b, y, B, C * 4, H / 2, W / 2, C * 4, 0, 0);
   } else {
     pixel_remap_nhwc_kernel<kShuffleUp><<<blocks, 256, 0, st>>>(a, b, B, C, H, W);
-    nhwc_to_nchw_kernel<float><<<blocks, 256, 0, st>>>(b, y, B, C / 4, H * 2, W * 2, C / 4, 0);
+    nhwc_to_nchw_kernel<float><<<blocks, 256, 0, st>>>(b, y, B, C / 4, H * 2, W * 2, C / 4, 0, 0);
   }
   cudaError_t e = cudaStreamSynchronize(st);
   cudaFree(a);
@@ -540,15 +659,17 @@ int lpsr_debug_read_tap(lpsr_handle* h, const char* name, float* dst, int64_t ds
                         void* stream) {
   if (!h || !name || !dst || !wsv) return fail(h, LPSR_ERR_INVALID_ARG, "null argument");
   const WsLayout L = ws_layout(h, B, H, W);
-  struct Tap { const char* name; size_t off; int pitch, choff, C, div; };
+  struct Tap { const char* name; size_t off; int pitch, choff, C, div, unshuffled, ae_half; };
+  const bool tc = h->ae_tc;    // tensor-core AutoEncoder: full-resolution tensors are stored as their PixelUnshuffle on the half grid
   const Tap taps[] = {
-      {"ae.c0", L.c0, 12, 0, 12, 1},      {"ae.enc0", L.e0, 48, 0, 48, 2},   {"ae.enc1", L.e1, 48, 0, 48, 4},
-      {"ae.dec0", L.d0, 12, 0, 12, 2},    {"ae.sum", L.s, h->sfe1_u.packed ? 16 : 12, 0, 12, 1},     {"ae.out", L.ae, h->sfe1_u.packed ? 16 : 3, 0, 3, 1},
-      {"rdn.sfe1", L.sfe1, 32, 0, 32, 1}, {"rdn.sfe2", L.x0, 32, 0, 32, 1},
-      {"rdn.block0", L.f[0], 32, 0, 32, 1}, {"rdn.block1", L.f[1], 32, 0, 32, 1},
-      {"rdn.block2", L.f[2], 32, 0, 32, 1}, {"rdn.block3", L.f[3], 32, 0, 32, 1},
-      {"rdb0.growth3", L.grow[0][3], 16, 0, 16, 1},   {"csar3.x_in", L.xin, 32, 0, 32, 1},
-      {"rdn.gff0", L.g0, 32, 0, 32, 1},   {"rdn.out", L.g, 32, 0, 32, 1}};
+      {"ae.c0", L.c0, tc ? 48 : 12, 0, 12, 1, tc, tc},  {"ae.enc0", L.e0, 48, 0, 48, 2, 0, tc},   {"ae.enc1", L.e1, 48, 0, 48, 4, 0, tc},
+      {"ae.dec0", L.d0, tc ? 48 : 12, 0, 12, 2, tc, tc}, {"ae.sum", L.s, tc ? 48 : (h->sfe1_u.packed ? 16 : 12), 0, 12, 1, tc, tc},
+      {"ae.out", L.ae, tc ? 8 : (h->sfe1_u.packed ? 16 : 3), 0, 3, 1, 0, 0},
+      {"rdn.sfe1", L.sfe1, 32, 0, 32, 1, 0}, {"rdn.sfe2", L.x0, 32, 0, 32, 1, 0},
+      {"rdn.block0", L.f[0], 32, 0, 32, 1, 0}, {"rdn.block1", L.f[1], 32, 0, 32, 1, 0},
+      {"rdn.block2", L.f[2], 32, 0, 32, 1, 0}, {"rdn.block3", L.f[3], 32, 0, 32, 1, 0},
+      {"rdb0.growth3", L.grow[0][3], 16, 0, 16, 1, 0},   {"csar3.x_in", L.xin, 32, 0, 32, 1, 0},
+      {"rdn.gff0", L.g0, 32, 0, 32, 1, 0},   {"rdn.out", L.g, 32, 0, 32, 1, 0}};
   for (const Tap& t : taps) {
     if (strcmp(t.name, name)) continue;
     const int Ht = L.Hp / t.div, Wt = L.Wp / t.div;
@@ -556,10 +677,12 @@ int lpsr_debug_read_tap(lpsr_handle* h, const char* name, float* dst, int64_t ds
     if (dst_numel != need) return fail(h, LPSR_ERR_INVALID_ARG, "tap '%s' has %lld elements, buffer has %lld", name, (long long)need, (long long)dst_numel);
     char* ws = static_cast<char*>(wsv);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (t.ae_half)   // tensor-core AutoEncoder intermediates are fp16 in both 16-bit modes
+      return tap_copy_impl<__half>(h, ws + t.off, dst, B, t.C, Ht, Wt, t.pitch, t.choff, t.unshuffled, st);
     switch (h->cfg.precision) {
-      case LPSR_PREC_FP32: return tap_copy_impl<float>(h, ws + t.off, dst, B, t.C, Ht, Wt, t.pitch, t.choff, st);
-      case LPSR_PREC_BF16: return tap_copy_impl<__nv_bfloat16>(h, ws + t.off, dst, B, t.C, Ht, Wt, t.pitch, t.choff, st);
-      default: return tap_copy_impl<__half>(h, ws + t.off, dst, B, t.C, Ht, Wt, t.pitch, t.choff, st);
+      case LPSR_PREC_FP32: return tap_copy_impl<float>(h, ws + t.off, dst, B, t.C, Ht, Wt, t.pitch, t.choff, t.unshuffled, st);
+      case LPSR_PREC_BF16: return tap_copy_impl<__nv_bfloat16>(h, ws + t.off, dst, B, t.C, Ht, Wt, t.pitch, t.choff, t.unshuffled, st);
+      default: return tap_copy_impl<__half>(h, ws + t.off, dst, B, t.C, Ht, Wt, t.pitch, t.choff, t.unshuffled, st);
     }
     return LPSR_OK;
   }

@@ -54,6 +54,10 @@ struct lpsr_handle {
   lpsr::UmmaWeights fin_u;   // final conv with Cout padded 1 -> 16 for the tensor-core path
   lpsr::UmmaWeights sfe1_u;  // shallowF1 7x7 as 28 pixel-pair K-steps over an 8-channel padded input (tensor-core path)
   lpsr::UmmaWeights ae_out_u; // AutoEncoder conv_out 12 -> 3 on tensor cores: Cin padded to 16, Cout padded to 16 (zeros)
+  // Tensor-core AutoEncoder (16-bit modes): every stage is ONE dense convolution on the half / quarter grid, the pixel
+  // (un)shuffles are channel relabelings of space-to-depth operands (DESIGN.md "AutoEncoder on tensor cores")
+  bool ae_tc = false;
+  lpsr::UmmaWeights aet_in, aet_enc0, aet_enc1, aet_dec0, aet_dec1[2], aet_out;
   lpsr::DConvW dc[4];
   float *ca_w1 = nullptr, *ca_b1 = nullptr, *ca_w2 = nullptr, *ca_b2 = nullptr;
   float *sa_w1 = nullptr, *sa_b1 = nullptr, *sa_w2 = nullptr, *sa_b2 = nullptr, *co_w = nullptr, *co_b = nullptr;
@@ -93,7 +97,7 @@ inline size_t elem_size(const lpsr_handle* h) { return half_mode(h) ? 2 : 4; }
 // f[0..3] = block0..3 outputs (32 ch each; f[1] is also RDB#2's input).  Dense concatenation (lpsr.py:39-40) and the final
 // torch.cat (lpsr.py:224) are channel-chunk gather lists over these tensors (ConvParams::chunk_ptr), never copies.
 struct WsLayout {
-  size_t c0, e0, e1, d0, s, ae, sfe1, x0, f[4], grow[2][4], t, xin, g0, g, pool, hid, gate, sc, total;
+  size_t xu, c0, e0, e1, d0, s, ae, sfe1, x0, f[4], grow[2][4], t, xin, g0, g, pool, hid, gate, sc, total;
   int Hp, Wp, P, S;
 };
 
@@ -107,6 +111,7 @@ template <typename T>
 int op_conv_impl(lpsr_handle* h, const float* x, const float* w_oihw, const float* bias, float* y, int B, int Cin, int Cout, int ks,
                  int H, int W, int relu, cudaStream_t st);
 template <typename T>
-int tap_copy_impl(lpsr_handle* h, const void* src, float* dst, int B, int C, int H, int W, int pitch, int off, cudaStream_t st);
+int tap_copy_impl(lpsr_handle* h, const void* src, float* dst, int B, int C, int H, int W, int pitch, int off, int unshuffled,
+                  cudaStream_t st);
 
 }  // namespace lpsr

@@ -219,6 +219,72 @@ void rdb_block(Ctx& c, const WsLayout& L, char* ws, int B, int r, size_t x_t, si
                                                      Seg{g[3], 16, 0, 16}}, 16, out, 32, 0, B, L.Hp, L.Wp, false, x, 32, 0));
 }
 
+// AutoEncoder on tensor cores (16-bit modes).  Every stage is one dense convolution (DConv = depthwise x pointwise composed at pack
+// time) evaluated on the half (H/2 x W/2) or quarter grid, where PixelUnshuffle / PixelShuffle are channel relabelings:
+//   xu  [H/2][W/2][16]  = unshuffle(pad4(x))                       ae_unshuffle_in_kernel
+//   c0u [H/2][W/2][48]  = unshuffle(conv_in(x))                    3x3 taps on the half grid, K=16, N=48     (lpsr.py:67-69)
+//   e0  [H/2][W/2][48]  = relu(unshuffle(DConv(c0)))               3x3 taps on the half grid, K=48, N=48     (lpsr.py:71-73)
+//   e1  [H/4][W/4][48]  = relu(unshuffle(DConv(e0)))               5x5 taps on the half grid, N=12, unshuffling store (74-80)
+//   d0q [H/4][W/4][48]  = relu(DConv(e1)), shuffle pending         5x5 taps on the quarter grid, N=48        (lpsr.py:83-89)
+//   s   [H/2][W/2][48]  = c0u + relu(unshuffle(shuffle(DConv(shuffle(d0q)))))   3x3 taps on the quarter grid, two launches of
+//                         N=96 (row parity I), each storing half-grid pixels (2h+I, 2w+{0,1})               (lpsr.py:90-96,115)
+//   ae  [H][W][8]       = conv_out(c0 + d)                         folded 3x3 on the half grid, N=4x4, shuffling store (102-104,116)
+// Operands and intermediate tensors of the AutoEncoder are fp16 in BOTH 16-bit modes (its activations are O(1), and the extra three
+// mantissa bits matter: the trunk amplifies AutoEncoder rounding ~20x); only the last stage converts to the trunk's type T.
+template <typename T>
+void ae_forward_tc(Ctx& c, const WsLayout& L, char* ws, const float* x, int B, int H, int W) {
+  using TA = __half;
+  lpsr_handle* h = c.h;
+  TA* xu = reinterpret_cast<TA*>(ws + L.xu);
+  TA* c0u = reinterpret_cast<TA*>(ws + L.c0);
+  TA* e0 = reinterpret_cast<TA*>(ws + L.e0);
+  TA* e1 = reinterpret_cast<TA*>(ws + L.e1);
+  TA* d0q = reinterpret_cast<TA*>(ws + L.d0);
+  TA* s = reinterpret_cast<TA*>(ws + L.s);
+  T* ae = reinterpret_cast<T*>(ws + L.ae);
+  const int H2 = L.Hp / 2, W2 = L.Wp / 2, H4 = L.Hp / 4, W4 = L.Wp / 4;
+  auto run = [&](const char* what, const UmmaWeights& u, const ConvParams& p, const UmmaGate* g) {
+    c.begin("umma_conv_ae");
+    if (c.dry || c.rc != LPSR_OK) return;
+    const char* msg = (g && g->epi == kEpiShuffle8) ? umma_conv_launch<TA, T>(u, p, h->num_sms, c.st, g) : umma_conv_launch<TA>(u, p, h->num_sms, c.st, g);
+    if (msg) c.rc = fail(h, LPSR_ERR_CUDA, "umma_conv %s launch: %s", what, msg);
+  };
+  auto shape = [](int ks, int cin, int cout) { ConvW w; w.ks = ks; w.cin = cin; w.cout = cout; return w; };
+  c.tag = "ae.conv_in";
+  c.begin("ae_unshuffle_in");
+  if (!c.dry && c.rc == LPSR_OK) {
+    const long long total = (long long)B * H2 * W2;
+    const int grid = (int)std::min<long long>((total + kThreads - 1) / kThreads, (long long)h->num_sms * 16);
+    ae_unshuffle_in_kernel<TA><<<grid, kThreads, 0, c.st>>>(x, xu, B, L.Hp, L.Wp, H, W);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) c.rc = fail(h, LPSR_ERR_CUDA, "ae_unshuffle_in launch: %s", cudaGetErrorString(e));
+  }
+  run("ae.conv_in", h->aet_in, conv_params(shape(3, 16, 48), xu, 16, 0, 16, c0u, 48, 0, B, H2, W2, false), nullptr);
+  c.tag = "ae.enc0";
+  run("ae.enc0", h->aet_enc0, conv_params(shape(3, 48, 48), c0u, 48, 0, 16, e0, 48, 0, B, H2, W2, true), nullptr);
+  c.tag = "ae.enc1";
+  {
+    UmmaGate g{};
+    g.epi = kEpiUnshuffleRelu;
+    run("ae.enc1", h->aet_enc1, conv_params(shape(5, 48, 16), e0, 48, 0, 16, e1, 48, 0, B, H2, W2, true), &g);
+  }
+  c.tag = "ae.dec0";
+  run("ae.dec0", h->aet_dec0, conv_params(shape(5, 48, 48), e1, 48, 0, 16, d0q, 48, 0, B, H4, W4, true), nullptr);
+  c.tag = "ae.dec1";
+  for (int I = 0; I < 2; ++I) {
+    UmmaGate g{};
+    g.epi = kEpiReluUp2Res;
+    g.up_row = I;
+    run("ae.dec1", h->aet_dec1[I], conv_params(shape(3, 48, 96), d0q, 48, 0, 16, s, 48, 0, B, H4, W4, true, c0u, 48, 0), &g);
+  }
+  c.tag = "ae.conv_out";
+  {
+    UmmaGate g{};
+    g.epi = kEpiShuffle8;
+    run("ae.conv_out", h->aet_out, conv_params(shape(3, 48, 16), s, 48, 0, 16, ae, 8, 0, B, H2, W2, false), &g);
+  }
+}
+
 template <typename T>
 int forward_impl(lpsr_handle* h, const float* x, float* y, int B, int H, int W, char* ws, cudaStream_t st, bool dry, int* n_launch,
                  LaunchProfile* prof) {
@@ -238,6 +304,13 @@ int forward_impl(lpsr_handle* h, const float* x, float* y, int B, int H, int W, 
   const int Hp = L.Hp, Wp = L.Wp;
 
   // ---- AutoEncoder (lpsr.py:106-117) ------------------------------------------------------------------
+  bool ae_tc = false;
+  if constexpr (sizeof(T) == 2) ae_tc = h->ae_tc;
+  const bool sfe1_tc = (sizeof(T) == 2) && h->sfe1_u.packed && h->ae_out_u.packed;
+  const int ae_pitch = ae_tc ? 8 : 16;                         // 16-byte pixels (3 real channels) straight from the tensor-core conv_out
+  if (ae_tc) {
+    if constexpr (sizeof(T) == 2) ae_forward_tc<T>(c, L, ws, x, B, H, W);
+  } else {
   c.tag = "ae.conv_in";
   {  // conv_in 3->12 reads the caller's NCHW fp32 tensor; zero beyond (H,W) == pad-to-4 (lpsr.py:107-111)
     c.begin("ae_conv_in");
@@ -256,7 +329,6 @@ int forward_impl(lpsr_handle* h, const float* x, float* y, int B, int H, int W, 
   c.tag = "ae.dec0";
   launch_dconv<T, 48, 48, kShuffleUp, false>(c, h->dc[2], e1, 48, d0, 12, nullptr, 0, B, Hp / 4, Wp / 4);    // -> [12,H/2,W/2]
   c.tag = "ae.dec1";
-  const bool sfe1_tc = (sizeof(T) == 2) && h->sfe1_u.packed && h->ae_out_u.packed;
   const int s_pitch = sfe1_tc ? 16 : 12;                       // tensor-core conv_out reads a 16-channel (zero padded) operand
   launch_dconv<T, 12, 48, kShuffleUp, true>(c, h->dc[3], d0, 12, s, s_pitch, c0, 12, B, Hp / 2, Wp / 2);     // -> c0 + [12,H,W]
   c.tag = "ae.conv_out";
@@ -272,6 +344,7 @@ int forward_impl(lpsr_handle* h, const float* x, float* y, int B, int H, int W, 
     }
   }
   if (!sfe1_tc) launch_direct<T, 3, 12, 3, false, false>(c, conv_params(h->ae_out, s, 12, 0, 12, ae, 3, 0, B, Hp, Wp, false));
+  }
 
   // ---- RDN (lpsr.py:214-225) ---------------------------------------------------------------------------
   c.tag = "rdn.shallowF1";
@@ -281,7 +354,7 @@ int forward_impl(lpsr_handle* h, const float* x, float* y, int B, int H, int W, 
       if (!c.dry && c.rc == LPSR_OK) {
         ConvW w7;
         w7.ks = 7; w7.cin = 448; w7.cout = 32;
-        const char* msg = umma_conv_launch<T>(h->sfe1_u, conv_params(w7, {Seg{ae, 16, 0, 8}}, 8, sfe1, 32, 0, B, Hp, Wp, false), h->num_sms, c.st);
+        const char* msg = umma_conv_launch<T>(h->sfe1_u, conv_params(w7, {Seg{ae, ae_pitch, 0, 8}}, 8, sfe1, 32, 0, B, Hp, Wp, false), h->num_sms, c.st);
         if (msg) c.rc = fail(h, LPSR_ERR_CUDA, "umma_conv 7x7 launch: %s", msg);
       }
     }
@@ -373,7 +446,7 @@ int op_conv_impl(lpsr_handle* h, const float* x, const float* w_oihw, const floa
   dense_conv<T>(c, cw, conv_params(cw, in, Cin, 0, 16, out, Cout, 0, B, H, W, relu != 0));
   if (c.rc == LPSR_OK) {
     const int blocks2 = (int)std::min<size_t>(8192, (npix * Cout + 255) / 256);
-    nhwc_to_nchw_kernel<T><<<blocks2, 256, 0, st>>>(out, y, B, Cout, H, W, Cout, 0);
+    nhwc_to_nchw_kernel<T><<<blocks2, 256, 0, st>>>(out, y, B, Cout, H, W, Cout, 0, 0);
   }
   cudaError_t e = cudaStreamSynchronize(st);
   cudaFree(scratch);
@@ -384,10 +457,10 @@ int op_conv_impl(lpsr_handle* h, const float* x, const float* w_oihw, const floa
 
 
 template <typename T>
-int tap_copy_impl(lpsr_handle* h, const void* src, float* dst, int B, int C, int H, int W, int pitch, int off, cudaStream_t st) {
+int tap_copy_impl(lpsr_handle* h, const void* src, float* dst, int B, int C, int H, int W, int pitch, int off, int unshuffled, cudaStream_t st) {
   const long long need = (long long)B * C * H * W;
   const int blocks = (int)std::min<long long>(4096, (need + 255) / 256);
-  nhwc_to_nchw_kernel<T><<<blocks, 256, 0, st>>>(static_cast<const T*>(src), dst, B, C, H, W, pitch, off);
+  nhwc_to_nchw_kernel<T><<<blocks, 256, 0, st>>>(static_cast<const T*>(src), dst, B, C, H, W, pitch, off, unshuffled);
   CUDA_TRY(h, cudaGetLastError());
   return LPSR_OK;
 }
@@ -397,6 +470,6 @@ int tap_copy_impl(lpsr_handle* h, const void* src, float* dst, int B, int C, int
                                LaunchProfile*);                                                                         \
   template int op_conv_impl<T>(lpsr_handle*, const float*, const float*, const float*, float*, int, int, int, int, int, \
                                int, int, cudaStream_t);                                                                 \
-  template int tap_copy_impl<T>(lpsr_handle*, const void*, float*, int, int, int, int, int, int, cudaStream_t);
+  template int tap_copy_impl<T>(lpsr_handle*, const void*, float*, int, int, int, int, int, int, int, cudaStream_t);
 
 }  // namespace lpsr

@@ -232,7 +232,12 @@ __device__ __forceinline__ uint32_t umma_desc_hi_swizzled(uint32_t rowbytes) {
 template <typename T> struct IsBf16 { static constexpr bool value = false; };
 template <> struct IsBf16<__nv_bfloat16> { static constexpr bool value = true; };
 
-enum { kEpiPlain = 0, kEpiGate = 1, kEpiFinalSigmoid = 2, kEpiRelu = 3, kEpiResidual = 4 };   // FinalSigmoid: channel 0 -> sigmoid -> fp32 [pixel] (lpsr.py:273-274)
+// Epilogues.  FinalSigmoid: channel 0 -> sigmoid -> fp32 [pixel] (lpsr.py:273-274).  The last three serve the AutoEncoder, whose
+// PixelUnshuffle / PixelShuffle (lpsr.py:72,79,88,95) are folded into the convolutions around them:
+//   UnshuffleRelu: 12 real channels of pixel (y,x) -> ReLU -> channel c*4 + (y&1)*2 + (x&1) of pixel (y/2, x/2) of a half-size tensor
+//   ReluUp2Res   : N = 2 x 48: column block J is pixel (2y + I, 2x + J) of a double-size tensor (I = out_off2): ReLU, + residual
+//   Shuffle8     : N = 4 sub-pixels x 4 (3 real): sub-pixel (I,J) -> 8-channel (16-byte) pixel (2y + I, 2x + J)
+enum { kEpiPlain = 0, kEpiGate = 1, kEpiFinalSigmoid = 2, kEpiRelu = 3, kEpiResidual = 4, kEpiUnshuffleRelu = 5, kEpiReluUp2Res = 6, kEpiShuffle8 = 7 };
 
 // ---------------------------------------------------------------------------------------------------
 // the kernel
@@ -268,19 +273,24 @@ __device__ __forceinline__ void store_chunk16_coalesced(T* __restrict__ out, int
 //       | kConv3x3Fold (dx folded into N = 3*Cout: used for Cout = 16 where per-tap MMAs would be issue/smem bound)
 //       | kConv7x7 (Cin = 3 padded to 8: K = 16 is a PAIR of horizontally adjacent pixels x 8 channels; 7 dy x 4 dx-pairs = 28 MMAs,
 //         A rows are 16-byte pixels in a no-swizzle layout whose second K core-matrix is simply the next pixel, LBO = 16 B)
-enum { kConv1x1 = 0, kConv3x3Taps = 1, kConv3x3Fold = 2, kConv7x7 = 3 };
+//       | kConv5x5Taps (25 taps, halo 2: the AutoEncoder's depthwise 5x5 + pointwise 1x1 pairs composed into one dense conv)
+enum { kConv1x1 = 0, kConv3x3Taps = 1, kConv3x3Fold = 2, kConv7x7 = 3, kConv5x5Taps = 4 };
 
 struct UmmaTmaps { CUtensorMap m[kUmmaMaxKChunks]; };   // one tiled map per K-chunk (its tensor, its box width)
 
 // EPI (epilogue, compile time so the per-tile instruction stream carries no dead branches):
 //   kEpiPlain: +bias | kEpiRelu: +bias, ReLU | kEpiResidual: +bias, +residual | kEpiGate: CSAR gates | kEpiFinalSigmoid
-template <typename T, int NOUT, int MODE, int EPI>
+// TOUT: element type of the Shuffle8 output (the AutoEncoder runs fp16 operands in both 16-bit modes; its last stage writes the
+// trunk's type)
+template <typename T, int NOUT, int MODE, int EPI, typename TOUT = T>
 __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid_constant__ UmmaParams p, const __grid_constant__ UmmaTmaps tm) {
   static_assert(sizeof(T) == 2, "16-bit operands");
   constexpr bool FOLD = (MODE == kConv3x3Fold);
   constexpr bool K3 = (MODE != kConv1x1);
   constexpr int NMMA = FOLD ? 3 * NOUT : NOUT;                 // GEMM-N of one MMA = TMEM columns per tile
-  constexpr int NTAP = (MODE == kConv1x1 || MODE == kConv7x7) ? 1 : (FOLD ? 3 : 9);   // MMAs per K-step
+  constexpr int KSZ = (MODE == kConv5x5Taps) ? 5 : 3;          // taps per kernel row (per-tap / folded modes)
+  constexpr int NTAP = (MODE == kConv1x1 || MODE == kConv7x7) ? 1 : (FOLD ? 3 : KSZ * KSZ);   // MMAs per K-step
+  constexpr int XCH = FOLD ? kEpiGroups * 2 * 4 * 2 * NOUT : 0;                 // floats of warp-boundary exchange (folded epilogue only)
   constexpr int G = kEpiGroups;
   static_assert(G * NMMA <= 512, "accumulators exceed TMEM");
   constexpr uint32_t kTmemCols = (G * NMMA <= 32) ? 32 : (G * NMMA <= 64) ? 64 : (G * NMMA <= 128) ? 128 : (G * NMMA <= 256) ? 256 : 512;
@@ -306,7 +316,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * R + 2 * G);
   float* xchg = reinterpret_cast<float*>(bars + 2 * R + 2 * G + 2);
   // per-K-slice MMA operand table {A offset in 16-B units inside the item buffer, row bytes/16, descriptor hi word, dy shift/16}
-  uint4* steps = reinterpret_cast<uint4*>(xchg + (size_t)G * 2 * 4 * 2 * NOUT);
+  uint4* steps = reinterpret_cast<uint4*>(xchg + XCH);
   int* slot_base_s = reinterpret_cast<int*>(steps + kUmmaMaxSteps);   // [R] written by the producer, read by the MMA warp
   uint8_t* stage_all = reinterpret_cast<uint8_t*>(slot_base_s + 8);  // 1 KB of store staging per epilogue warp
 
@@ -429,7 +439,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
 #pragma unroll
               for (int t = 0; t < NTAP; ++t) {
                 // tap -> start shift in 16-byte units: folded: dy rows (dx lives in N); per-tap: dy rows + dx pixels
-                const uint32_t shift = FOLD ? (uint32_t)t * e.w : (uint32_t)(t / 3) * e.w + (uint32_t)(t % 3) * e.y;
+                const uint32_t shift = FOLD ? (uint32_t)t * e.w : (uint32_t)(t / KSZ) * e.w + (uint32_t)(t % KSZ) * e.y;
                 ptx::tc_mma_f16_lohi(d, a0 + shift, e.z, b_lo + (uint32_t)t * cgn, kUmmaDescHi, idesc, (uint32_t)(ks | t));
               }
               b_lo += 2 * NMMA;                               // next K-slice of the weights
@@ -474,8 +484,10 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
       const int item = blockIdx.x + ii * gridDim.x;
       // per item: one division per thread; per tile the row position advances incrementally (32-bit pixel indices)
       int y = 0, xs = 0, tw = 0, xbase = 0, px = 0;             // K3: strip row / column of this thread's row, crop base; 1x1: pixel index
+      int nn = 0;                                               // crop of this item (shuffling epilogues)
       if constexpr (K3) {
         const int n = item / per_crop;
+        nn = n;
         const int rem = item - n * per_crop;
         const int strip = rem / ips, j = rem - strip * ips;
         xbase = strip * TWs - halo;                             // image x of strip column xs is xbase + xs
@@ -491,9 +503,11 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
         const bool mine = (turn == grp);
         if (++turn == G) turn = 0;
         int pix = -1;
+        [[maybe_unused]] int yy = 0, xx = 0;                    // image coordinates of this row's pixel (shuffling epilogues)
         if constexpr (K3) {
           // folded: rows 0 and 127 are the shuffle halo of the tile
           if ((!FOLD || (row >= 1 && row <= 126)) && (unsigned)y < (unsigned)Himg && xs >= halo && xs < tw) pix = px + y * Wimg + xs;
+          yy = y; xx = xbase + xs;
           xs += adv_x;                                          // advance to the next tile
           y += adv_y;
           if (xs >= pitch) { xs -= pitch; ++y; }
@@ -582,6 +596,44 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
           if constexpr (EPI == kEpiFinalSigmoid) {
             // final conv (Cout = 1, padded to 16): channel 0 only, fp32; lanes are consecutive pixels -> coalesced 4-byte stores
             if (valid) static_cast<float*>(p.out)[pix] = __fdividef(1.f, 1.f + __expf(-v[0]));
+          } else if constexpr (EPI == kEpiUnshuffleRelu) {
+            // PixelUnshuffle(2) + ReLU folded into the store: 2-byte scatter, the 2x2 neighbours fill the rest of each 96-byte pixel
+            static_assert(EPI != kEpiUnshuffleRelu || NOUT == 16, "12 real channels in one chunk");
+            if (valid) {
+              T* o = out + unshuffle2_dst(nn, yy, xx, 0, Himg, Wimg, out_pitch, out_off);   // + c*4: the address map of PixelUnshuffle(2)
+#pragma unroll
+              for (int c = 0; c < 12; ++c) o[c * 4] = from_f32<T>(fmaxf(v[c], 0.f));
+            }
+          } else if constexpr (EPI == kEpiReluUp2Res) {
+            // this launch produces row 2y + I of the double-size tensor; column block J = cc / 48 is pixel 2x + J
+            static_assert(EPI != kEpiReluUp2Res || NOUT == 96, "two 48-channel pixels per row");
+            const int up = valid ? ((nn * 2 * Himg + 2 * yy + p.out_off2) * 2 * Wimg + 2 * xx + cc / 48) : -1;
+            if (valid) {
+              float r[CH];
+              load_vec<T, CH>(res + (size_t)up * res_pitch + res_off + cc % 48, r);
+#pragma unroll
+              for (int c = 0; c < CH; ++c) v[c] = fmaxf(v[c], 0.f) + r[c];
+            }
+            store_chunk16_coalesced<T>(out, out_pitch, out_off + cc % 48, up, v, stage, lane);
+          } else if constexpr (EPI == kEpiShuffle8) {
+            // PixelShuffle-like store of 4 sub-pixels x 3 channels into 8-channel (16-byte) pixels; J = 0,1 are adjacent: 32-byte runs
+            static_assert(EPI != kEpiShuffle8 || NOUT == 16, "4 sub-pixels x 4 columns");
+            if (valid) {
+#pragma unroll
+              for (int I = 0; I < 2; ++I) {
+                uint4 q[2];
+#pragma unroll
+                for (int J = 0; J < 2; ++J) {
+                  TOUT* e = reinterpret_cast<TOUT*>(&q[J]);
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) e[c] = from_f32<TOUT>(c < 3 ? v[(I * 2 + J) * 4 + c] : 0.f);
+                }
+                static_assert(sizeof(TOUT) == sizeof(T), "same element size");
+                uint4* o = reinterpret_cast<uint4*>(out + (size_t)((nn * 2 * Himg + 2 * yy + I) * 2 * Wimg + 2 * xx) * out_pitch + out_off);
+                o[0] = q[0];
+                *reinterpret_cast<uint4*>(reinterpret_cast<T*>(o) + out_pitch) = q[1];
+              }
+            }
           } else if constexpr (EPI == kEpiGate) {
             // CSAR gates (1x1, NOUT = 32): spatial branch x_in * sigmoid(.), channel branch x_in^2 * s_c
             float g1[CH];
@@ -694,9 +746,10 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
   p = UmmaParams{};
   memset(&plan.tm, 0, sizeof plan.tm);
   const bool c7 = (w.ks == 7);
-  const bool k3 = (w.ks == 3) || c7, fold = umma_fold(w.ks, w.cout);
-  const int N = w.cout, NMMA = fold ? 3 * N : N, ntap = fold ? 3 : (w.ks == 3 ? 9 : 1);
-  const int halo = c7 ? 3 : 1;
+  const bool k3 = (w.ks == 3) || (w.ks == 5) || c7, fold = umma_fold(w.ks, w.cout);
+  const int N = w.cout, NMMA = fold ? 3 * N : N, ntap = fold ? 3 : ((w.ks == 3 || w.ks == 5) ? w.ks * w.ks : 1);
+  const int halo = w.ks / 2;
+  const size_t xch_bytes = fold ? (size_t)kEpiGroups * 2 * 4 * 2 * N * 4 : 0;
   p.halo = halo;
   p.n_ks = w.cin / 16;                                       // 7x7: 28 pixel-pair steps (UmmaWeights::cin = 448 pseudo channels)
   if (p.n_ks > kUmmaMaxSteps) return "too many K-steps";
@@ -750,7 +803,7 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
     p.trace = nullptr;
   }
   const size_t w_bytes = ((size_t)ntap * w.cin * NMMA * 2 + 127) & ~(size_t)127;
-  const size_t fixed = w_bytes + (2 * kUmmaMaxBufs + 2 * kEpiGroups + 2) * 8 + kEpiGroups * 2 * 4 * 2 * N * 4 + 640 /*steps, slot_base*/ + 4 * kEpiGroups * 1024 /*store staging*/ + 1024 /*alignment slack*/ + 256;
+  const size_t fixed = w_bytes + (2 * kUmmaMaxBufs + 2 * kEpiGroups + 2) * 8 + xch_bytes + 640 /*steps, slot_base*/ + 4 * kEpiGroups * 1024 /*store staging*/ + 1024 /*alignment slack*/ + 256;
   const size_t smem_cap = 227 * 1024 - fixed;
   auto item_buf_bytes = [&](size_t npx) {                      // every chunk is 1024-aligned inside the buffer
     size_t b = 0;
@@ -825,7 +878,7 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
   if (bufs < 2) return "tile does not fit in shared memory";
   if (bufs > kUmmaMaxBufs) bufs = kUmmaMaxBufs;
   p.n_bufs = bufs;
-  plan.smem_bytes = (size_t)bufs * off + w_bytes + (2 * bufs + 2 * kEpiGroups + 2) * 8 + kEpiGroups * 2 * 4 * 2 * N * 4 + 640 + 4 * kEpiGroups * 1024 + 1024 + 64;
+  plan.smem_bytes = (size_t)bufs * off + w_bytes + (2 * bufs + 2 * kEpiGroups + 2) * 8 + xch_bytes + 640 + 4 * kEpiGroups * 1024 + 1024 + 64;
   plan.grid = std::min(p.n_items, num_sms);
   // ---- tensor maps, one per K-chunk
   for (int c = 0; c < p.n_chunks; ++c)
@@ -835,15 +888,15 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
   return nullptr;
 }
 
-template <typename T, int N, int MODE, int EPI>
+template <typename T, int N, int MODE, int EPI, typename TOUT = T>
 inline const char* umma_launch_inst(const UmmaPlan& plan, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(umma_conv_kernel<T, N, MODE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(umma_conv_kernel<T, N, MODE, EPI, TOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return cudaGetErrorString(e);
     configured = true;
   }
-  umma_conv_kernel<T, N, MODE, EPI><<<plan.grid, kUmmaThreads, plan.smem_bytes, st>>>(plan.p, plan.tm);
+  umma_conv_kernel<T, N, MODE, EPI, TOUT><<<plan.grid, kUmmaThreads, plan.smem_bytes, st>>>(plan.p, plan.tm);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
@@ -865,12 +918,23 @@ inline const char* umma_launch_epi(const UmmaPlan& plan, cudaStream_t st) {
   return "epilogue mode not instantiated for this shape";
 }
 
-template <typename T>
+template <typename T, typename TOUT = T>
 inline const char* umma_plan_launch(const UmmaPlan& plan, const UmmaWeights& w, cudaStream_t st) {
+  const int mode = plan.p.mode;
+  const bool plain = (mode == kEpiPlain && !plan.p.res);
   if (w.ks == 7) return w.cout == 32 ? umma_launch_epi<T, 32, kConv7x7>(plan, st) : "unsupported Cout";
+  if (w.ks == 5) {   // AutoEncoder stages (composed depthwise + pointwise)
+    if (w.cout == 16 && mode == kEpiUnshuffleRelu) return umma_launch_inst<T, 16, kConv5x5Taps, kEpiUnshuffleRelu>(plan, st);
+    if (w.cout == 48 && plain && plan.p.relu) return umma_launch_inst<T, 48, kConv5x5Taps, kEpiRelu>(plan, st);
+    return "5x5 conv: shape/epilogue not instantiated";
+  }
   if (w.ks == 3) {
+    if (w.cout == 16 && mode == kEpiShuffle8) return umma_launch_inst<T, 16, kConv3x3Fold, kEpiShuffle8, TOUT>(plan, st);
     if (w.cout == 16) return umma_launch_epi<T, 16, kConv3x3Fold>(plan, st);
     if (w.cout == 32) return umma_launch_epi<T, 32, kConv3x3Taps>(plan, st);
+    if (w.cout == 48 && plain) return plan.p.relu ? umma_launch_inst<T, 48, kConv3x3Taps, kEpiRelu>(plan, st)
+                                                  : umma_launch_inst<T, 48, kConv3x3Taps, kEpiPlain>(plan, st);
+    if (w.cout == 96 && mode == kEpiReluUp2Res) return umma_launch_inst<T, 96, kConv3x3Taps, kEpiReluUp2Res>(plan, st);
   } else {
     if (w.cout == 16) return umma_launch_epi<T, 16, kConv1x1>(plan, st);
     if (w.cout == 32) return umma_launch_epi<T, 32, kConv1x1>(plan, st);
@@ -885,13 +949,19 @@ struct UmmaGate {
   const float* s_c;        // [B][32] channel gates
   int out_off_spatial;     // channel offset of x_in * sigmoid(.) in the output buffer (x_in^2 * s_c goes to ConvParams::out_off)
   int final_sigmoid;       // 1: kEpiFinalSigmoid instead (ConvParams::out is a float [B*H*W] tensor)
+  int epi = 0;             // kEpiUnshuffleRelu / kEpiReluUp2Res / kEpiShuffle8: the AutoEncoder's shuffling stores (else 0)
+  int up_row = 0;          // kEpiReluUp2Res: row parity I produced by this launch
 };
 
-template <typename T>
+template <typename T, typename TOUT = T>
 inline const char* umma_conv_launch(const UmmaWeights& w, const ConvParams& cp, int num_sms, cudaStream_t st, const UmmaGate* gate = nullptr) {
   UmmaPlan plan;
   if (const char* msg = umma_plan(plan, w, cp, num_sms, !IsBf16<T>::value, gate && gate->final_sigmoid)) return msg;
-  if (gate && gate->final_sigmoid) {
+  if (gate && gate->epi) {
+    plan.p.mode = gate->epi;
+    plan.p.out_off2 = gate->up_row;
+    if (gate->epi == kEpiReluUp2Res && (!cp.res || cp.res_pitch % 8 || cp.res_off % 8)) return "up2 epilogue needs an aligned residual";
+  } else if (gate && gate->final_sigmoid) {
     if (w.ks != 3 || w.cout != 16) return "final epilogue needs the folded 3x3 conv with Cout padded to 16";
     plan.p.mode = kEpiFinalSigmoid;
   } else if (gate) {
@@ -902,10 +972,10 @@ inline const char* umma_conv_launch(const UmmaWeights& w, const ConvParams& cp, 
     plan.p.gate = gate->s_c;
     plan.p.out_off2 = gate->out_off_spatial;
   }
-  return umma_plan_launch<T>(plan, w, st);
+  return umma_plan_launch<T, TOUT>(plan, w, st);
 }
 
-template <> inline const char* umma_conv_launch<float>(const UmmaWeights&, const ConvParams&, int, cudaStream_t, const UmmaGate*) {
+template <> inline const char* umma_conv_launch<float, float>(const UmmaWeights&, const ConvParams&, int, cudaStream_t, const UmmaGate*) {
   return "tensor-core path is 16-bit only";
 }
 

@@ -58,7 +58,7 @@ inline uint16_t f32_to_f16_bits(float f) {
 }
 
 // pw: fp32 [taps][cin][cout] (tap = dy*3+dx) -> device 16-bit, tcgen05 no-swizzle K-major core-matrix order:
-//   1x1: [cin/8][cout][8]    3x3 per-tap: [tap][cin/8][cout][8]    3x3 folded (Cout=16): [dy][cin/8][dx*cout + co][8]
+//   1x1: [cin/8][cout][8]    3x3 / 5x5 per-tap: [tap][cin/8][cout][8]    3x3 folded (Cout=16): [dy][cin/8][dx*cout + co][8]
 template <typename PutU16, typename PutF32>
 bool umma_pack_weights(UmmaWeights& u, const float* pw, const float* bias, int ks, int cin, int cout, bool fp16, PutU16 put16, PutF32 put32) {
   const int taps = ks * ks, cg = cin / 8;
@@ -69,7 +69,7 @@ bool umma_pack_weights(UmmaWeights& u, const float* pw, const float* bias, int k
       for (int n = 0; n < cout; ++n)
         for (int j = 0; j < 8; ++j) v[((size_t)g * cout + n) * 8 + j] = cvt(pw[((size_t)g * 8 + j) * cout + n]);
   } else if (!umma_fold(ks, cout)) {
-    for (int t = 0; t < 9; ++t)
+    for (int t = 0; t < taps; ++t)
       for (int g = 0; g < cg; ++g)
         for (int n = 0; n < cout; ++n)
           for (int j = 0; j < 8; ++j) v[(((size_t)t * cg + g) * cout + n) * 8 + j] = cvt(pw[((size_t)t * cin + g * 8 + j) * cout + n]);
