@@ -34,6 +34,9 @@ UNIT = "crops/s"
 DENSE_FLOP_PER_PIXEL = 297_104          # dense-conv FLOPs per pixel (roofline numerator, whole forward)
 # MACs per pixel of the layers the tensor-core kernel executes (K x N per layer, SURVEY 8a GEMM view)
 UMMA_MAC_PER_PIXEL = {
+    # AutoEncoder (reference arithmetic: depthwise 5x5 + pointwise 1x1 per DConv, per full-resolution pixel)
+    "ae.conv_in": 27 * 12, "ae.enc0": 25 * 12 + 12 * 12, "ae.enc1": (25 * 48 + 48 * 12) / 4, "ae.dec0": (25 * 48 + 48 * 48) / 16,
+    "ae.dec1": (25 * 12 + 12 * 48) / 4,
     "ae.conv_out": 108 * 3, "rdn.shallowF1": 147 * 32, "rdn.shallowF2": 288 * 32, "rdn.gff0": 128 * 32, "rdn.gff1": 288 * 32, "final_conv": 288 * 1,
     "rdb0": (288 + 432 + 576 + 720) * 16 + 96 * 32, "rdb2": (288 + 432 + 576 + 720) * 16 + 96 * 32,
     "csar1.conv_in": 2 * 288 * 32, "csar3.conv_in": 2 * 288 * 32,

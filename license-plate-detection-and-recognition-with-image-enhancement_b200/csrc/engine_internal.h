@@ -56,6 +56,7 @@ struct lpsr_handle {
   lpsr::UmmaWeights ae_out_u; // AutoEncoder conv_out 12 -> 3 on tensor cores: Cin padded to 16, Cout padded to 16 (zeros)
   // Tensor-core AutoEncoder (16-bit modes): every stage is ONE dense convolution on the half / quarter grid, the pixel
   // (un)shuffles are channel relabelings of space-to-depth operands (DESIGN.md "AutoEncoder on tensor cores")
+  lpsr::UmmaWeights rdb_fused[2];   // last dense layer + lff + residual of each RDB as one tensor-core launch (16-bit modes)
   bool ae_tc = false;
   lpsr::UmmaWeights aet_in, aet_enc0, aet_enc1, aet_dec0, aet_dec1[2], aet_out;
   lpsr::DConvW dc[4];

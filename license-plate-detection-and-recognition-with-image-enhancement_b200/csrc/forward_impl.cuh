@@ -212,6 +212,17 @@ void rdb_block(Ctx& c, const WsLayout& L, char* ws, int B, int r, size_t x_t, si
   dense_conv<T>(c, h->rdb[r][1], conv_params(h->rdb[r][1], {Seg{x, 32, 0, 32}, Seg{g[0], 16, 0, 16}}, 16, g[1], 16, 0, B, L.Hp, L.Wp, true));
   dense_conv<T>(c, h->rdb[r][2], conv_params(h->rdb[r][2], {Seg{x, 32, 0, 32}, Seg{g[0], 16, 0, 16}, Seg{g[1], 16, 0, 16}}, 16, g[2], 16, 0, B,
                                              L.Hp, L.Wp, true));
+  if constexpr (sizeof(T) == 2) {
+    if (h->rdb_fused[r].packed) {
+      // last dense layer + lff + alpha + residual in one launch: g3 stays in shared memory               (lpsr.py:31-40,52-61)
+      c.begin("umma_conv_lff");
+      if (c.dry || c.rc != LPSR_OK) return;
+      const char* msg = umma_conv_launch<T>(h->rdb_fused[r], conv_params(h->rdb[r][3], {Seg{x, 32, 0, 32}, Seg{g[0], 16, 0, 16}, Seg{g[1], 16, 0, 16},
+                                            Seg{g[2], 16, 0, 16}}, 16, out, 32, 0, B, L.Hp, L.Wp, false, x, 32, 0), h->num_sms, c.st);
+      if (msg) c.rc = fail(h, LPSR_ERR_CUDA, "umma_conv fused layer+lff launch: %s", msg);
+      return;
+    }
+  }
   dense_conv<T>(c, h->rdb[r][3], conv_params(h->rdb[r][3], {Seg{x, 32, 0, 32}, Seg{g[0], 16, 0, 16}, Seg{g[1], 16, 0, 16}, Seg{g[2], 16, 0, 16}},
                                              16, g[3], 16, 0, B, L.Hp, L.Wp, true));
   // x + alpha*lff(cat): alpha is folded into the packed lff weights/bias                               (lpsr.py:52-61)

@@ -274,7 +274,12 @@ __device__ __forceinline__ void store_chunk16_coalesced(T* __restrict__ out, int
 //       | kConv7x7 (Cin = 3 padded to 8: K = 16 is a PAIR of horizontally adjacent pixels x 8 channels; 7 dy x 4 dx-pairs = 28 MMAs,
 //         A rows are 16-byte pixels in a no-swizzle layout whose second K core-matrix is simply the next pixel, LBO = 16 B)
 //       | kConv5x5Taps (25 taps, halo 2: the AutoEncoder's depthwise 5x5 + pointwise 1x1 pairs composed into one dense conv)
-enum { kConv1x1 = 0, kConv3x3Taps = 1, kConv3x3Fold = 2, kConv7x7 = 3, kConv5x5Taps = 4 };
+//       | kConv3x3FoldLff (last dense layer of an RDB fused with the block's 1x1 local feature fusion + residual, lpsr.py:52-61:
+//         the dy = 1 MMAs carry 32 extra columns = lff over the layer's own 80 input channels (same A rows, no extra traffic); the
+//         epilogue turns the folded 48 columns into g3 = relu(conv + bias), writes it to shared memory as a K = 16 operand, one more
+//         MMA adds lff's g3 slice, and a second epilogue pass adds bias + x and stores the block output.  g3 never goes to HBM.)
+enum { kConv1x1 = 0, kConv3x3Taps = 1, kConv3x3Fold = 2, kConv7x7 = 3, kConv5x5Taps = 4, kConv3x3FoldLff = 5 };
+constexpr int kLffN = 32, kLffCols = 48 + kLffN;   // fused layer: TMEM columns per accumulator = 3*16 folded + 32 lff
 
 struct UmmaTmaps { CUtensorMap m[kUmmaMaxKChunks]; };   // one tiled map per K-chunk (its tensor, its box width)
 
@@ -285,9 +290,11 @@ struct UmmaTmaps { CUtensorMap m[kUmmaMaxKChunks]; };   // one tiled map per K-c
 template <typename T, int NOUT, int MODE, int EPI, typename TOUT = T>
 __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid_constant__ UmmaParams p, const __grid_constant__ UmmaTmaps tm) {
   static_assert(sizeof(T) == 2, "16-bit operands");
-  constexpr bool FOLD = (MODE == kConv3x3Fold);
+  constexpr bool LFF = (MODE == kConv3x3FoldLff);
+  constexpr bool FOLD = (MODE == kConv3x3Fold) || LFF;
+  static_assert(!LFF || NOUT == 16, "fused layer: growth rate 16");
   constexpr bool K3 = (MODE != kConv1x1);
-  constexpr int NMMA = FOLD ? 3 * NOUT : NOUT;                 // GEMM-N of one MMA = TMEM columns per tile
+  constexpr int NMMA = LFF ? kLffCols : (FOLD ? 3 * NOUT : NOUT);   // TMEM columns per tile (and weight rows per K core-matrix)
   constexpr int KSZ = (MODE == kConv5x5Taps) ? 5 : 3;          // taps per kernel row (per-tap / folded modes)
   constexpr int NTAP = (MODE == kConv1x1 || MODE == kConv7x7) ? 1 : (FOLD ? 3 : KSZ * KSZ);   // MMAs per K-step
   constexpr int XCH = FOLD ? kEpiGroups * 2 * 4 * 2 * NOUT : 0;                 // floats of warp-boundary exchange (folded epilogue only)
@@ -300,7 +307,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int CG = p.n_ks * 2;                                  // 8-channel groups of the whole K extent
-  const uint32_t w_bytes = (uint32_t)NTAP * CG * NMMA * 16;
+  const uint32_t w_main_bytes = (uint32_t)NTAP * CG * NMMA * 16;
+  const uint32_t w_bytes = w_main_bytes + (LFF ? 2u * kLffN * 16u : 0u);   // fused: + lff's g3 slice [2][32][8]
   const uint32_t buf_bytes = p.buf_bytes;                      // multiple of 1024
   uint8_t* a_smem = smem;                                      // item buffers first (1024-aligned)
   uint8_t* w_smem = smem + (size_t)p.n_bufs * buf_bytes;
@@ -313,12 +321,16 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
   auto empty_bar = [&](int s) { return bar0 + 8u * (R + s); };
   auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * R + a); };
   auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * R + G + a); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * R + 2 * G);
-  float* xchg = reinterpret_cast<float*>(bars + 2 * R + 2 * G + 2);
+  auto a2full_bar = [&](int a) { return bar0 + 8u * (2 * R + 2 * G + a); };      // fused layer: g3 operand of group a is in shared memory
+  auto tfull2_bar = [&](int a) { return bar0 + 8u * (2 * R + 3 * G + a); };      // fused layer: lff accumulator complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * R + 4 * G);
+  float* xchg = reinterpret_cast<float*>(bars + 2 * R + 4 * G + 2);
   // per-K-slice MMA operand table {A offset in 16-B units inside the item buffer, row bytes/16, descriptor hi word, dy shift/16}
   uint4* steps = reinterpret_cast<uint4*>(xchg + XCH);
   int* slot_base_s = reinterpret_cast<int*>(steps + kUmmaMaxSteps);   // [R] written by the producer, read by the MMA warp
   uint8_t* stage_all = reinterpret_cast<uint8_t*>(slot_base_s + 8);  // 1 KB of store staging per epilogue warp
+  // fused layer: per group a 4 KB K=16 operand, two planes of [128 rows][8 ch] (no-swizzle K-major: row stride 16 B, LBO = 2048 B)
+  uint8_t* a2_all = stage_all + (size_t)4 * G * 1024;
 
   // ---- one-time setup ------------------------------------------------------------------------------
   {
@@ -334,6 +346,10 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
     for (int a = 0; a < G; ++a) {
       ptx::mbar_init(tfull_bar(a), 1);
       ptx::mbar_init(tempty_bar(a), 128);
+      if constexpr (LFF) {
+        ptx::mbar_init(a2full_bar(a), 128);
+        ptx::mbar_init(tfull2_bar(a), 1);
+      }
     }
     ptx::fence_mbar_init();
   }
@@ -405,6 +421,10 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
     const int mg = warp - kUmmaMmaWarp;
     const bool leader = ptx::elect_one();
     constexpr uint32_t idesc = umma_idesc_f16(IsBf16<T>::value, NMMA);
+    constexpr uint32_t idesc48 = umma_idesc_f16(IsBf16<T>::value, 48), idesc32 = umma_idesc_f16(IsBf16<T>::value, kLffN);
+    const uint32_t w2_lo = umma_desc_lo(ptx::smem_u32(w_smem) + w_main_bytes, (uint32_t)kLffN * 16);
+    const uint32_t a2_lo = umma_desc_lo(ptx::smem_u32(a2_all) + (uint32_t)mg * 4096u, 2048u);
+    uint32_t a2_par = 0;
     const uint32_t w_lo = umma_desc_lo(ptx::smem_u32(w_smem), (uint32_t)NMMA * 16);
     const uint32_t cgn = (uint32_t)(CG * NMMA);               // weights: 16-byte units between taps
     const uint32_t a_smem16 = ptx::smem_u32(a_smem) >> 4, buf16_sz = buf_bytes >> 4;
@@ -439,8 +459,14 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
 #pragma unroll
               for (int t = 0; t < NTAP; ++t) {
                 // tap -> start shift in 16-byte units: folded: dy rows (dx lives in N); per-tap: dy rows + dx pixels
-                const uint32_t shift = FOLD ? (uint32_t)t * e.w : (uint32_t)(t / KSZ) * e.w + (uint32_t)(t % KSZ) * e.y;
-                ptx::tc_mma_f16_lohi(d, a0 + shift, e.z, b_lo + (uint32_t)t * cgn, kUmmaDescHi, idesc, (uint32_t)(ks | t));
+                if constexpr (LFF) {
+                  // dy = 1 goes first: its 80-column MMA (48 folded + 32 lff) initialises the whole accumulator
+                  const uint32_t dyv = t == 0 ? 1u : (t == 1 ? 0u : 2u);
+                  ptx::tc_mma_f16_lohi(d, a0 + dyv * e.w, e.z, b_lo + dyv * cgn, kUmmaDescHi, t == 0 ? idesc : idesc48, (uint32_t)(ks | t));
+                } else {
+                  const uint32_t shift = FOLD ? (uint32_t)t * e.w : (uint32_t)(t / KSZ) * e.w + (uint32_t)(t % KSZ) * e.y;
+                  ptx::tc_mma_f16_lohi(d, a0 + shift, e.z, b_lo + (uint32_t)t * cgn, kUmmaDescHi, idesc, (uint32_t)(ks | t));
+                }
               }
               b_lo += 2 * NMMA;                               // next K-slice of the weights
             }
@@ -448,6 +474,17 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
           ptx::tc_commit(tfull_bar(acc));                     // this tile's accumulator is complete
         }
         __syncwarp();
+        if constexpr (LFF) {
+          // second stage: the epilogue group has written g3 (K = 16) to shared memory; add lff's g3 slice to columns 48..79
+          ptx::mbar_wait(a2full_bar(acc), a2_par);
+          a2_par ^= 1u;
+          ptx::tc_fence_after();
+          if (leader) {
+            if (!no_mma) ptx::tc_mma_f16_lohi(tmem_base + acc * NMMA + 48, a2_lo, kUmmaDescHi, w2_lo, kUmmaDescHi, idesc32, 1u);
+            ptx::tc_commit(tfull2_bar(acc));
+          }
+          __syncwarp();
+        }
         acc_par ^= 1u;
       }
       if (leader) ptx::tc_commit(empty_bar(buf));             // this warp's MMAs on the item buffer have retired (count G)
@@ -459,7 +496,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
     const int grp = warp >> 2, wq = warp & 3;                   // group == TMEM accumulator (0..G-1), wq == TMEM lane quadrant
     const int row = wq * 32 + lane;                             // accumulator row
     constexpr int CH = 16;                                      // output channels handled per pass (bounds registers)
-    constexpr int NRES = NOUT <= 32 ? NOUT * 2 / 16 : 1;        // raw residual registers (uint4) prefetched per tile
+    constexpr int NRES = LFF ? kLffN * 2 / 16 : (NOUT <= 32 ? NOUT * 2 / 16 : 1);   // raw residual registers (uint4) prefetched per tile
     constexpr int NB = NOUT <= 32 ? NOUT : 1;
     T* out = static_cast<T*>(p.out);
     const T* res = static_cast<const T*>(p.res);
@@ -527,6 +564,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
         ptx::mbar_wait(tfull_bar(grp), my_par);
         ptx::tc_fence_after();
         float* xb = xg + (size_t)my_par * (4 * 2 * NOUT);
+        [[maybe_unused]] const uint32_t tile_par = my_par;
         my_par ^= 1u;
         const bool valid = pix >= 0 && !skip_store;
         const int pix32 = valid ? pix : -1;
@@ -539,7 +577,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
             ptx::tc_ld16_nowait(taddr + NOUT + cc, v);
             ptx::tc_ld16_nowait(taddr + 2 * NOUT + cc, rg);
             ptx::tc_wait_ld();
-            if (cc + CH >= NOUT) {
+            if (cc + CH >= NOUT && !LFF) {
               ptx::tc_fence_before();
               ptx::mbar_arrive(tempty_bar(grp));                // accumulator is in registers: hand TMEM back to the MMA warp
             }
@@ -593,7 +631,44 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
               v[c] += b4.x; v[c + 1] += b4.y; v[c + 2] += b4.z; v[c + 3] += b4.w;
             }
           }
-          if constexpr (EPI == kEpiFinalSigmoid) {
+          if constexpr (LFF) {
+            // ---- stage 1: g3 = relu(conv + bias) becomes the K = 16 operand of lff's last slice (planes of 8 channels, row = 16 B)
+            {
+              uint4 lo, hi;
+              T* e0 = reinterpret_cast<T*>(&lo);
+              T* e1 = reinterpret_cast<T*>(&hi);
+#pragma unroll
+              for (int c = 0; c < 8; ++c) { e0[c] = from_f32<T>(fmaxf(v[c], 0.f)); e1[c] = from_f32<T>(fmaxf(v[8 + c], 0.f)); }
+              uint8_t* a2 = a2_all + (size_t)grp * 4096;
+              *reinterpret_cast<uint4*>(a2 + row * 16) = lo;
+              *reinterpret_cast<uint4*>(a2 + 2048 + row * 16) = hi;
+            }
+            ptx::fence_proxy_async();                           // generic-proxy stores -> visible to the tensor core
+            ptx::mbar_arrive(a2full_bar(grp));
+            // ---- stage 2: columns 48..79 = lff(cat[x, g0..g3]); + bias + x -> block output
+            ptx::mbar_wait(tfull2_bar(grp), tile_par);
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int hh = 0; hh < kLffN / CH; ++hh) {
+              float o[CH];
+              ptx::tc_ld16_nowait(taddr + 48 + hh * CH, o);
+              ptx::tc_wait_ld();
+              if (hh == kLffN / CH - 1) {
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(tempty_bar(grp));
+              }
+              if (valid) {
+                const T* re = reinterpret_cast<const T*>(rsd_raw) + hh * CH;
+#pragma unroll
+                for (int c = 0; c < CH; c += 4) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + NOUT + hh * CH + c));
+                  o[c] += b4.x + to_f32<T>(re[c]); o[c + 1] += b4.y + to_f32<T>(re[c + 1]);
+                  o[c + 2] += b4.z + to_f32<T>(re[c + 2]); o[c + 3] += b4.w + to_f32<T>(re[c + 3]);
+                }
+              }
+              store_chunk16_coalesced<T>(out, out_pitch, out_off + hh * CH, pix32, o, stage, lane);
+            }
+          } else if constexpr (EPI == kEpiFinalSigmoid) {
             // final conv (Cout = 1, padded to 16): channel 0 only, fp32; lanes are consecutive pixels -> coalesced 4-byte stores
             if (valid) static_cast<float*>(p.out)[pix] = __fdividef(1.f, 1.f + __expf(-v[0]));
           } else if constexpr (EPI == kEpiUnshuffleRelu) {
@@ -747,7 +822,8 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
   memset(&plan.tm, 0, sizeof plan.tm);
   const bool c7 = (w.ks == 7);
   const bool k3 = (w.ks == 3) || (w.ks == 5) || c7, fold = umma_fold(w.ks, w.cout);
-  const int N = w.cout, NMMA = fold ? 3 * N : N, ntap = fold ? 3 : ((w.ks == 3 || w.ks == 5) ? w.ks * w.ks : 1);
+  const bool lff = w.fused_lff;
+  const int N = w.cout, NMMA = lff ? kLffCols : (fold ? 3 * N : N), ntap = fold ? 3 : ((w.ks == 3 || w.ks == 5) ? w.ks * w.ks : 1);
   const int halo = w.ks / 2;
   const size_t xch_bytes = fold ? (size_t)kEpiGroups * 2 * 4 * 2 * N * 4 : 0;
   p.halo = halo;
@@ -802,8 +878,9 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
     p.debug = dbg;
     p.trace = nullptr;
   }
-  const size_t w_bytes = ((size_t)ntap * w.cin * NMMA * 2 + 127) & ~(size_t)127;
-  const size_t fixed = w_bytes + (2 * kUmmaMaxBufs + 2 * kEpiGroups + 2) * 8 + xch_bytes + 640 /*steps, slot_base*/ + 4 * kEpiGroups * 1024 /*store staging*/ + 1024 /*alignment slack*/ + 256;
+  const size_t w_bytes = ((size_t)ntap * w.cin * NMMA * 2 + (lff ? 2 * kLffN * 16 : 0) + 127) & ~(size_t)127;
+  const size_t a2_bytes = lff ? (size_t)kEpiGroups * 4096 : 0;
+  const size_t fixed = w_bytes + (2 * kUmmaMaxBufs + 4 * kEpiGroups + 2) * 8 + xch_bytes + a2_bytes + 640 /*steps, slot_base*/ + 4 * kEpiGroups * 1024 /*store staging*/ + 1024 /*alignment slack*/ + 256;
   const size_t smem_cap = 227 * 1024 - fixed;
   auto item_buf_bytes = [&](size_t npx) {                      // every chunk is 1024-aligned inside the buffer
     size_t b = 0;
@@ -878,7 +955,7 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
   if (bufs < 2) return "tile does not fit in shared memory";
   if (bufs > kUmmaMaxBufs) bufs = kUmmaMaxBufs;
   p.n_bufs = bufs;
-  plan.smem_bytes = (size_t)bufs * off + w_bytes + (2 * bufs + 2 * kEpiGroups + 2) * 8 + xch_bytes + 640 + 4 * kEpiGroups * 1024 + 1024 + 64;
+  plan.smem_bytes = (size_t)bufs * off + w_bytes + (2 * bufs + 4 * kEpiGroups + 2) * 8 + xch_bytes + a2_bytes + 640 + 4 * kEpiGroups * 1024 + 1024 + 64;
   plan.grid = std::min(p.n_items, num_sms);
   // ---- tensor maps, one per K-chunk
   for (int c = 0; c < p.n_chunks; ++c)
@@ -929,6 +1006,8 @@ inline const char* umma_plan_launch(const UmmaPlan& plan, const UmmaWeights& w, 
     return "5x5 conv: shape/epilogue not instantiated";
   }
   if (w.ks == 3) {
+    if (w.fused_lff) return (mode == kEpiPlain && plan.p.res) ? umma_launch_inst<T, 16, kConv3x3FoldLff, kEpiResidual>(plan, st)
+                                                               : "fused dense layer + lff needs the residual";
     if (w.cout == 16 && mode == kEpiShuffle8) return umma_launch_inst<T, 16, kConv3x3Fold, kEpiShuffle8, TOUT>(plan, st);
     if (w.cout == 16) return umma_launch_epi<T, 16, kConv3x3Fold>(plan, st);
     if (w.cout == 32) return umma_launch_epi<T, 32, kConv3x3Taps>(plan, st);

@@ -17,6 +17,7 @@ struct UmmaWeights {
   int ks = 0, cin = 0, cout = 0;
   uint16_t* w = nullptr;   // 16-bit (bf16 or fp16): 1x1 [cin/8][cout][8]; 3x3 [dy][cin/8][dx*cout + co][8] (dx folded into N)
   float* bias = nullptr;   // [cout] (zeros if the conv has no bias)
+  bool fused_lff = false;  // kConv3x3FoldLff: w = [dy][cin/8][48 folded + 32 lff][8] then lff's g3 slice [2][32][8]; bias = [16] + [32]
 };
 
 inline bool umma_enabled() {
@@ -87,6 +88,38 @@ bool umma_pack_weights(UmmaWeights& u, const float* pw, const float* bias, int k
   u.w = put16(v);
   u.bias = put32(b);
   u.ks = ks; u.cin = cin; u.cout = cout;
+  u.packed = (u.w != nullptr && u.bias != nullptr);
+  return u.packed;
+}
+
+// Last dense layer of an RDB (3x3, cin -> 16, ReLU) fused with the block's local feature fusion (1x1 over cin + 16 channels -> 32,
+// alpha already folded in, lpsr.py:52-61).  w3: fp32 [9][cin][16]; wl: fp32 [cin + 16][32].
+template <typename PutU16, typename PutF32>
+bool umma_pack_fused_lff(UmmaWeights& u, const float* w3, const float* b3, const float* wl, const float* bl, int cin, bool fp16, PutU16 put16,
+                         PutF32 put32) {
+  const int cg = cin / 8, nf = 80;
+  std::vector<uint16_t> v((size_t)3 * cg * nf * 8 + 2 * 32 * 8, 0);
+  auto cvt = [&](float f) { return fp16 ? f32_to_f16_bits(f) : f32_to_bf16_bits(f); };
+  for (int dy = 0; dy < 3; ++dy)
+    for (int g = 0; g < cg; ++g)
+      for (int j = 0; j < 8; ++j) {
+        const int ci = g * 8 + j;
+        for (int dx = 0; dx < 3; ++dx)
+          for (int n = 0; n < 16; ++n) v[(((size_t)dy * cg + g) * nf + dx * 16 + n) * 8 + j] = cvt(w3[((size_t)(dy * 3 + dx) * cin + ci) * 16 + n]);
+        if (dy == 1)
+          for (int n = 0; n < 32; ++n) v[(((size_t)dy * cg + g) * nf + 48 + n) * 8 + j] = cvt(wl[(size_t)ci * 32 + n]);
+      }
+  const size_t base2 = (size_t)3 * cg * nf * 8;
+  for (int g = 0; g < 2; ++g)
+    for (int n = 0; n < 32; ++n)
+      for (int j = 0; j < 8; ++j) v[base2 + ((size_t)g * 32 + n) * 8 + j] = cvt(wl[(size_t)(cin + g * 8 + j) * 32 + n]);
+  std::vector<float> b(48, 0.f);
+  for (int n = 0; n < 16; ++n) b[n] = b3[n];
+  for (int n = 0; n < 32; ++n) b[16 + n] = bl[n];
+  u.w = put16(v);
+  u.bias = put32(b);
+  u.ks = 3; u.cin = cin; u.cout = 16;
+  u.fused_lff = true;
   u.packed = (u.w != nullptr && u.bias != nullptr);
   return u.packed;
 }
