@@ -63,11 +63,11 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
     for (int s = 0; s < G; ++s) {
       ptx::mbar_init(bar(s, 0), 1);
       ptx::mbar_init(bar(s, 1), 1);
-      ptx::mbar_init(bar(s, 2), 128);
+      ptx::mbar_init(bar(s, 2), 4);   // one arrival per epilogue warp
       ptx::mbar_init(bar(s, 3), 1);
-      ptx::mbar_init(bar(s, 4), 128);
+      ptx::mbar_init(bar(s, 4), 4);   // one arrival per epilogue warp
       ptx::mbar_init(bar(s, 5), 1);
-      ptx::mbar_init(bar(s, 6), 128);
+      ptx::mbar_init(bar(s, 6), 4);   // one arrival per epilogue warp
     }
     ptx::fence_mbar_init();
   }
@@ -177,7 +177,8 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
       }
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
-      ptx::mbar_arrive(bar(g, 2));
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar(g, 2));
       // ---- phase 2: s_s = sigmoid(acc + b4); gated concat [x_in^2 * s_c | x_in * s_s] -> A3
       ptx::mbar_wait(bar(g, 3), par);
       ptx::tc_fence_after();
@@ -204,7 +205,8 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
       }
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
-      ptx::mbar_arrive(bar(g, 4));
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar(g, 4));
       // ---- phase 3: out = x + acc + bo
       ptx::mbar_wait(bar(g, 5), par);
       ptx::tc_fence_after();
@@ -215,7 +217,8 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
         ptx::tc_ld16(taddr + 96 + c0, v);
         if (c0 == 16) {                                                   // accumulators are in registers: free the slot
           ptx::tc_fence_before();
-          ptx::mbar_arrive(bar(g, 6));
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(bar(g, 6));
         }
         const T* re = reinterpret_cast<const T*>(rraw) + c0;
 #pragma unroll

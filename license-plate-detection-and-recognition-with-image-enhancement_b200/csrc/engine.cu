@@ -720,11 +720,11 @@ int lpsr_op_pixel_shuffle2(const float* x, float* y, int32_t B, int32_t C, int32
   return pixel_remap(x, y, B, C, H, W, stream, kShuffleUp);
 }
 
-// profiling experiment hook (LPSR_UMMA_TRACE): copy the clock64 trace of the last traced tensor-core launch, 256 x 8 stamps
+// profiling experiment hook (LPSR_UMMA_TRACE): copy the clock64 trace of the last traced tensor-core launch, 512 x 8 stamps
 int lpsr_debug_umma_trace(long long* dst_host) {
   long long* t = umma_trace_buffer();
   if (!t || !dst_host) return LPSR_ERR_INVALID_ARG;
-  return cudaMemcpy(dst_host, t, 256 * 8 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? LPSR_OK : LPSR_ERR_CUDA;
+  return cudaMemcpy(dst_host, t, 512 * 8 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? LPSR_OK : LPSR_ERR_CUDA;
 }
 
 int lpsr_op_conv2d(lpsr_handle* h, const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t Cin, int32_t Cout,

@@ -229,6 +229,20 @@ __device__ __forceinline__ uint32_t umma_desc_hi_swizzled(uint32_t rowbytes) {
   return ((8u * rowbytes) >> 4) | (1u << 14) | (layout << 29);
 }
 
+// Profiling experiments only (build with LPSR_NVCC_EXTRA=-DLPSR_UMMA_TRACE_BUILD, run with LPSR_UMMA_TRACE=1): clock64 stamps of CTA 0,
+// [tile][8] = {MMA warp: before / after the tmem_empty wait, after commit; epilogue warp 0 of the group: before / after the tmem_full
+// wait, after the TMEM loads, tile done; MMA warp: clocks spent waiting for the item's TMA data (first tile of an item)}
+#ifdef LPSR_UMMA_TRACE_BUILD
+#define LPSR_DBG(bit) ((p.debug & (bit)) != 0)
+#else
+#define LPSR_DBG(bit) false
+#endif
+#ifdef LPSR_UMMA_TRACE_BUILD
+#define LPSR_TRACE(cond, ti, k, v) do { if (p.trace && blockIdx.x == 0 && (cond) && (ti) < 512) p.trace[(ti) * 8 + (k)] = (v); } while (0)
+#else
+#define LPSR_TRACE(cond, ti, k, v) do { } while (0)
+#endif
+
 template <typename T> struct IsBf16 { static constexpr bool value = false; };
 template <> struct IsBf16<__nv_bfloat16> { static constexpr bool value = true; };
 
@@ -246,16 +260,25 @@ enum { kEpiPlain = 0, kEpiGate = 1, kEpiFinalSigmoid = 2, kEpiRelu = 3, kEpiResi
 // consecutive pixels of the output tensor, but a per-thread 32-byte store makes every STG.128 touch 32 different sectors
 // half-way.  Instead the warp stages its 32 rows x 32 B in shared memory and re-reads them so that each of the two store
 // instructions writes one contiguous 512-byte run (lane -> row 16j + lane/2, 16-byte half lane%2).
-template <typename T>
+// two floats -> packed 16-bit pair (low half = a), optionally with ReLU folded into the conversion (cvt.rn.relu, one instruction)
+template <typename T, bool RELU>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if constexpr (IsBf16<T>::value && RELU) {
+    uint32_t r;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+  } else {
+    if constexpr (RELU) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+    T t[2] = {from_f32<T>(a), from_f32<T>(b)};
+    return *reinterpret_cast<uint32_t*>(t);
+  }
+}
+
+template <typename T, bool RELU = false>
 __device__ __forceinline__ void store_chunk16_coalesced(T* __restrict__ out, int pitch, int off, int pix, const float (&v)[16],
                                                         uint8_t* __restrict__ stage /*1 KB per warp*/, int lane) {
-  uint4 lo, hi;
-  {
-    T* e0 = reinterpret_cast<T*>(&lo);
-    T* e1 = reinterpret_cast<T*>(&hi);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) { e0[c] = from_f32<T>(v[c]); e1[c] = from_f32<T>(v[8 + c]); }
-  }
+  const uint4 lo = make_uint4(pack2<T, RELU>(v[0], v[1]), pack2<T, RELU>(v[2], v[3]), pack2<T, RELU>(v[4], v[5]), pack2<T, RELU>(v[6], v[7]));
+  const uint4 hi = make_uint4(pack2<T, RELU>(v[8], v[9]), pack2<T, RELU>(v[10], v[11]), pack2<T, RELU>(v[12], v[13]), pack2<T, RELU>(v[14], v[15]));
   __syncwarp();                                                  // previous use of the staging rows is finished
   *reinterpret_cast<uint4*>(stage + lane * 32) = lo;
   *reinterpret_cast<uint4*>(stage + lane * 32 + 16) = hi;
@@ -345,9 +368,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
     }
     for (int a = 0; a < G; ++a) {
       ptx::mbar_init(tfull_bar(a), 1);
-      ptx::mbar_init(tempty_bar(a), 128);
+      ptx::mbar_init(tempty_bar(a), 4);                          // one arrival per epilogue warp
       if constexpr (LFF) {
-        ptx::mbar_init(a2full_bar(a), 128);
+        ptx::mbar_init(a2full_bar(a), 4);
         ptx::mbar_init(tfull2_bar(a), 1);
       }
     }
@@ -438,16 +461,21 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
     int buf = 0;
     uint32_t buf_par = 0;
     for (int ii = 0; ii < n_my_items; ++ii) {
+      [[maybe_unused]] const long long tw0 = clock64();
       ptx::mbar_wait(full_bar(buf), buf_par);
       ptx::tc_fence_after();
+      [[maybe_unused]] const long long tw1 = clock64();
       uint32_t slot = K3 ? (uint32_t)slot_base_s[buf] : 0u;
       const uint32_t buf16 = a_smem16 + (uint32_t)buf * buf16_sz;
       for (int m = 0; m < k_tiles; ++m, slot += tstride) {
         const bool mine = (turn == mg);
         if (++turn == G) turn = 0;
         if (!mine) continue;
+        LPSR_TRACE(leader, ii * k_tiles + m, 0, clock64());
+        LPSR_TRACE(leader, ii * k_tiles + m, 7, m < G ? tw1 - tw0 : 0);
         ptx::mbar_wait(tempty_bar(acc), acc_par);             // the epilogue group drained this accumulator
         ptx::tc_fence_after();
+        LPSR_TRACE(leader, ii * k_tiles + m, 1, clock64());
         if (leader) {
           const uint32_t d = tmem_base + acc * NMMA;
           uint32_t b_lo = w_lo;
@@ -472,6 +500,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
             }
           }
           ptx::tc_commit(tfull_bar(acc));                     // this tile's accumulator is complete
+          LPSR_TRACE(true, ii * k_tiles + m, 2, clock64());
         }
         __syncwarp();
         if constexpr (LFF) {
@@ -510,13 +539,15 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
     const int total_px32 = (int)p.total_px;
     const bool skip_store = (p.debug & 2) != 0;
     const int adv_y = K3 ? tstride / pitch : 0, adv_x = K3 ? tstride - adv_y * pitch : 0;   // one tile further along the strip
+    const int advg_y = K3 ? (G * tstride) / pitch : 0, advg_x = K3 ? G * tstride - advg_y * pitch : 0;   // G tiles further (the group's next tile)
     float bias_r[NB];
     if constexpr (NOUT <= 32) {
 #pragma unroll
       for (int c = 0; c < NB; ++c) bias_r[c] = __ldg(p.bias + c);
     }
     uint32_t my_par = 0;                                        // parity of this group's tmem_full barrier
-    int turn = 0;                                               // which group owns the next tile (same round robin as the MMA warps)
+    int t0mod = 0;                                              // (index of the item's first tile in the CTA's tile sequence) % G: tiles are dealt
+                                                                // round robin to the groups, the same way the MMA warps count them
     for (int ii = 0; ii < n_my_items; ++ii) {
       const int item = blockIdx.x + ii * gridDim.x;
       // per item: one division per thread; per tile the row position advances incrementally (32-bit pixel indices)
@@ -536,23 +567,33 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
       } else {
         px = item * rows_per_item + row;
       }
-      for (int m = 0; m < k_tiles; ++m) {
-        const bool mine = (turn == grp);
-        if (++turn == G) turn = 0;
+      int m = grp - t0mod;                                      // the group's first tile of this item
+      if (m < 0) m += G;
+      t0mod += k_tiles % G;
+      if (t0mod >= G) t0mod -= G;
+      if constexpr (K3) {
+        for (int s = 0; s < m; ++s) {                           // at most G-1 single-tile steps
+          xs += adv_x;
+          y += adv_y;
+          if (xs >= pitch) { xs -= pitch; ++y; }
+        }
+      } else {
+        px += m * 128;
+      }
+      for (; m < k_tiles; m += G) {
         int pix = -1;
         [[maybe_unused]] int yy = 0, xx = 0;                    // image coordinates of this row's pixel (shuffling epilogues)
         if constexpr (K3) {
           // folded: rows 0 and 127 are the shuffle halo of the tile
           if ((!FOLD || (row >= 1 && row <= 126)) && (unsigned)y < (unsigned)Himg && xs >= halo && xs < tw) pix = px + y * Wimg + xs;
           yy = y; xx = xbase + xs;
-          xs += adv_x;                                          // advance to the next tile
-          y += adv_y;
+          xs += advg_x;                                         // advance to the group's next tile
+          y += advg_y;
           if (xs >= pitch) { xs -= pitch; ++y; }
         } else {
           if (px < total_px32) pix = px;
-          px += 128;
+          px += 128 * G;
         }
-        if (!mine) continue;
         // operands that do not depend on the accumulator are requested before waiting for it
         uint4 rsd_raw[NRES];                                    // raw 16-bit residual: converted only after the accumulator arrived
         if constexpr (EPI == kEpiResidual && NOUT <= 32) {
@@ -561,8 +602,10 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
             for (int i = 0; i < NRES; ++i) rsd_raw[i] = *reinterpret_cast<const uint4*>(res + (size_t)pix * res_pitch + res_off + i * 8);
           }
         }
+        LPSR_TRACE(wq == 0 && lane == 0, ii * k_tiles + m, 3, clock64());
         ptx::mbar_wait(tfull_bar(grp), my_par);
         ptx::tc_fence_after();
+        LPSR_TRACE(wq == 0 && lane == 0, ii * k_tiles + m, 4, clock64());
         float* xb = xg + (size_t)my_par * (4 * 2 * NOUT);
         [[maybe_unused]] const uint32_t tile_par = my_par;
         my_par ^= 1u;
@@ -573,14 +616,16 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
           float v[CH];
           if constexpr (FOLD) {
             float lf[CH], rg[CH];
-            ptx::tc_ld16_nowait(taddr + cc, lf);
+            if (!LPSR_DBG(64)) ptx::tc_ld16_nowait(taddr + cc, lf);
             ptx::tc_ld16_nowait(taddr + NOUT + cc, v);
-            ptx::tc_ld16_nowait(taddr + 2 * NOUT + cc, rg);
+            if (!LPSR_DBG(64)) ptx::tc_ld16_nowait(taddr + 2 * NOUT + cc, rg);
             ptx::tc_wait_ld();
             if (cc + CH >= NOUT && !LFF) {
               ptx::tc_fence_before();
-              ptx::mbar_arrive(tempty_bar(grp));                // accumulator is in registers: hand TMEM back to the MMA warp
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(tempty_bar(grp));  // accumulator is in registers: hand TMEM back to the MMA warp
             }
+            if (cc + CH >= NOUT) LPSR_TRACE(wq == 0 && lane == 0, ii * k_tiles + m, 5, clock64());
             // out[q] = D[q-1, dx=0] + D[q, dx=1] + D[q+1, dx=2]: neighbours by warp shuffle; across warp boundaries lane 31's
             // dx=0 partial / lane 0's dx=2 partial travel through a small smem exchange
             if (lane == 31) {
@@ -591,12 +636,14 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
 #pragma unroll
               for (int c = 0; c < CH; c += 4) *reinterpret_cast<float4*>(&xb[(wq * 2 + 1) * NOUT + cc + c]) = make_float4(rg[c], rg[c + 1], rg[c + 2], rg[c + 3]);
             }
+            if (!LPSR_DBG(8)) {
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
               lf[c] = __shfl_up_sync(0xffffffffu, lf[c], 1);
               rg[c] = __shfl_down_sync(0xffffffffu, rg[c], 1);
             }
-            ptx::bar_sync_named(1 + grp, 128);
+            }
+            if (!LPSR_DBG(16)) ptx::bar_sync_named(1 + grp, 128);
             if (lane == 0 && wq > 0) {
 #pragma unroll
               for (int c = 0; c < CH; c += 4) {
@@ -618,7 +665,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
             ptx::tc_wait_ld();
             if (cc + CH >= NOUT) {
               ptx::tc_fence_before();
-              ptx::mbar_arrive(tempty_bar(grp));
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(tempty_bar(grp));
+              LPSR_TRACE(wq == 0 && lane == 0, ii * k_tiles + m, 5, clock64());
             }
           }
           if constexpr (NOUT <= 32) {
@@ -644,7 +693,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
               *reinterpret_cast<uint4*>(a2 + 2048 + row * 16) = hi;
             }
             ptx::fence_proxy_async();                           // generic-proxy stores -> visible to the tensor core
-            ptx::mbar_arrive(a2full_bar(grp));
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(a2full_bar(grp));
             // ---- stage 2: columns 48..79 = lff(cat[x, g0..g3]); + bias + x -> block output
             ptx::mbar_wait(tfull2_bar(grp), tile_par);
             ptx::tc_fence_after();
@@ -655,7 +705,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
               ptx::tc_wait_ld();
               if (hh == kLffN / CH - 1) {
                 ptx::tc_fence_before();
-                ptx::mbar_arrive(tempty_bar(grp));
+                __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(tempty_bar(grp));
               }
               if (valid) {
                 const T* re = reinterpret_cast<const T*>(rsd_raw) + hh * CH;
@@ -731,10 +782,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
             store_chunk16_coalesced<T>(out, out_pitch, out_off + cc, pix32, g1, stage, lane);
             store_chunk16_coalesced<T>(out, out_pitch, p.out_off2 + cc, pix32, v, stage, lane);
           } else {
-            if constexpr (EPI == kEpiRelu) {
-#pragma unroll
-              for (int c = 0; c < CH; ++c) v[c] = fmaxf(v[c], 0.f);
-            }
+
             if constexpr (EPI == kEpiResidual) {
               if (valid) {
                 float r[CH];
@@ -750,9 +798,11 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
               }
             }
             // all 32 lanes take part in the staged, coalesced store (rows without a pixel are skipped inside)
-            store_chunk16_coalesced<T>(out, out_pitch, out_off + cc, pix32, v, stage, lane);
+            if (!LPSR_DBG(32)) store_chunk16_coalesced<T, EPI == kEpiRelu>(out, out_pitch, out_off + cc, pix32, v, stage, lane);
+            else if (v[0] == 123.456f) out[0] = from_f32<T>(v[1] + v[5] + v[9] + v[13]);
           }
         }
+        LPSR_TRACE(wq == 0 && lane == 0, ii * k_tiles + m, 6, clock64());
       }
     }
   }
@@ -877,6 +927,15 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
     if (dbg < 0) { const char* e = getenv("LPSR_UMMA_DEBUG"); dbg = e ? atoi(e) : 0; }
     p.debug = dbg;
     p.trace = nullptr;
+#ifdef LPSR_UMMA_TRACE_BUILD
+    static long long* trace = nullptr;
+    static int tr_on = -1;
+    if (tr_on < 0) {
+      tr_on = getenv("LPSR_UMMA_TRACE") ? 1 : 0;
+      if (tr_on) cudaMalloc(&trace, 512 * 8 * sizeof(long long));
+    }
+    if (tr_on) { cudaMemsetAsync(trace, 0, 512 * 8 * sizeof(long long)); p.trace = trace; umma_trace_buffer() = trace; }
+#endif
   }
   const size_t w_bytes = ((size_t)ntap * w.cin * NMMA * 2 + (lff ? 2 * kLffN * 16 : 0) + 127) & ~(size_t)127;
   const size_t a2_bytes = lff ? (size_t)kEpiGroups * 4096 : 0;
