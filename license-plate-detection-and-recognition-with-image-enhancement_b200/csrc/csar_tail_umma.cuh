@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
   auto bar = [&](int slot, int which) { return bar0 + 8u * (uint32_t)(slot * 7 + which); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7 * G);
   uint8_t* stage_all = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(bars + 7 * G + 2) + 15) & ~(uintptr_t)15);   // 1 KB per epilogue warp
+  float* bias_s = reinterpret_cast<float*>(stage_all + (size_t)4 * G * 1024);   // b3[64] | b4[32] | bo[32]: read as broadcast float4
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (uint32_t i = threadIdx.x; i < kW3 / 16; i += kTailThreads) reinterpret_cast<uint4*>(w3_s)[i] = __ldg(reinterpret_cast<const uint4*>(p.w3) + i);
@@ -59,6 +60,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
     reinterpret_cast<uint4*>(w4_s)[i] = __ldg(reinterpret_cast<const uint4*>(p.w4) + i);
     reinterpret_cast<uint4*>(wo_s)[i] = __ldg(reinterpret_cast<const uint4*>(p.wo) + i);
   }
+  if (threadIdx.x < 128) bias_s[threadIdx.x] = threadIdx.x < 64 ? __ldg(p.b3 + threadIdx.x) : threadIdx.x < 96 ? __ldg(p.b4 + threadIdx.x - 64) : __ldg(p.bo + threadIdx.x - 96);
   if (threadIdx.x == 0) {
     for (int s = 0; s < G; ++s) {
       ptx::mbar_init(bar(s, 0), 1);
@@ -148,7 +150,8 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
       const long long pix = tile * 128 + row;
       const bool valid = pix < p.total_px;
       // operands that do not depend on the tensor core: x_in row (gates), residual row, channel gates of this crop
-      uint4 xraw[4], rraw[4];
+      // (rows past the end of the batch compute on zeros; their stores are masked)
+      uint4 xraw[4] = {}, rraw[4] = {};
       if (valid) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -164,16 +167,15 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
       for (int c0 = 0; c0 < 64; c0 += 16) {
         float v[16];
         ptx::tc_ld16(taddr + c0, v);
-        uint4 lo, hi;
-        T* e0 = reinterpret_cast<T*>(&lo);
-        T* e1 = reinterpret_cast<T*>(&hi);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          e0[c] = from_f32<T>(fmaxf(v[c] + __ldg(p.b3 + c0 + c), 0.f));
-          e1[c] = from_f32<T>(fmaxf(v[8 + c] + __ldg(p.b3 + c0 + 8 + c), 0.f));
+        for (int c = 0; c < 16; c += 4) {
+          const float4 b = *reinterpret_cast<const float4*>(bias_s + c0 + c);
+          v[c] += b.x; v[c + 1] += b.y; v[c + 2] += b.z; v[c + 3] += b.w;
         }
-        *reinterpret_cast<uint4*>(a2 + ((size_t)(c0 / 8) * 128 + row) * 16) = lo;
-        *reinterpret_cast<uint4*>(a2 + ((size_t)(c0 / 8 + 1) * 128 + row) * 16) = hi;
+        *reinterpret_cast<uint4*>(a2 + ((size_t)(c0 / 8) * 128 + row) * 16) =
+            make_uint4(pack2<T, true>(v[0], v[1]), pack2<T, true>(v[2], v[3]), pack2<T, true>(v[4], v[5]), pack2<T, true>(v[6], v[7]));
+        *reinterpret_cast<uint4*>(a2 + ((size_t)(c0 / 8 + 1) * 128 + row) * 16) =
+            make_uint4(pack2<T, true>(v[8], v[9]), pack2<T, true>(v[10], v[11]), pack2<T, true>(v[12], v[13]), pack2<T, true>(v[14], v[15]));
       }
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
@@ -184,24 +186,39 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
       ptx::tc_fence_after();
 #pragma unroll
       for (int c0 = 0; c0 < 32; c0 += 16) {
-        float v[16];
+        float v[16], ga[16];
         ptx::tc_ld16(taddr + 64 + c0, v);
         const T* xe = reinterpret_cast<const T*>(xraw) + c0;
-        uint4 g1lo, g1hi, g2lo, g2hi;
-        T* q1 = reinterpret_cast<T*>(&g1lo); T* q2 = reinterpret_cast<T*>(&g1hi);
-        T* q3 = reinterpret_cast<T*>(&g2lo); T* q4 = reinterpret_cast<T*>(&g2hi);
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          const float x = valid ? to_f32<T>(xe[c]) : 0.f;
-          const float ss = __fdividef(1.f, 1.f + __expf(-(v[c] + __ldg(p.b4 + c0 + c))));
-          const float a = x * (x * __ldg(sc + c0 + c)), b = x * ss;
-          if (c < 8) { q1[c] = from_f32<T>(a); q3[c] = from_f32<T>(b); }
-          else       { q2[c - 8] = from_f32<T>(a); q4[c - 8] = from_f32<T>(b); }
+        for (int c = 0; c < 16; c += 4) {
+          const float4 b = *reinterpret_cast<const float4*>(bias_s + 64 + c0 + c);
+          const float4 s4 = __ldg(reinterpret_cast<const float4*>(sc + c0 + c));
+          const float bb[4] = {b.x, b.y, b.z, b.w}, ss4[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float x = to_f32<T>(xe[c + j]);
+            const float z = v[c + j] + bb[j];
+            float sg;
+            if constexpr (IsBf16<T>::value) {
+              // logistic through one MUFU: 0.5 + 0.5 * tanh(z / 2); tanh.approx's 2^-11 error is below the bf16 rounding of the product
+              float th;
+              asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * z));
+              sg = fmaf(0.5f, th, 0.5f);
+            } else {
+              sg = __fdividef(1.f, 1.f + __expf(-z));
+            }
+            ga[c + j] = x * (x * ss4[j]);                                    // channel branch x_in^2 * s_c (lpsr.py:133-135)
+            v[c + j] = x * sg;                                               // spatial branch x_in * s_s  (lpsr.py:150-153)
+          }
         }
-        *reinterpret_cast<uint4*>(a3 + ((size_t)(c0 / 8) * 128 + row) * 16) = g1lo;
-        *reinterpret_cast<uint4*>(a3 + ((size_t)(c0 / 8 + 1) * 128 + row) * 16) = g1hi;
-        *reinterpret_cast<uint4*>(a3 + ((size_t)(4 + c0 / 8) * 128 + row) * 16) = g2lo;
-        *reinterpret_cast<uint4*>(a3 + ((size_t)(4 + c0 / 8 + 1) * 128 + row) * 16) = g2hi;
+        *reinterpret_cast<uint4*>(a3 + ((size_t)(c0 / 8) * 128 + row) * 16) =
+            make_uint4(pack2<T, false>(ga[0], ga[1]), pack2<T, false>(ga[2], ga[3]), pack2<T, false>(ga[4], ga[5]), pack2<T, false>(ga[6], ga[7]));
+        *reinterpret_cast<uint4*>(a3 + ((size_t)(c0 / 8 + 1) * 128 + row) * 16) =
+            make_uint4(pack2<T, false>(ga[8], ga[9]), pack2<T, false>(ga[10], ga[11]), pack2<T, false>(ga[12], ga[13]), pack2<T, false>(ga[14], ga[15]));
+        *reinterpret_cast<uint4*>(a3 + ((size_t)(4 + c0 / 8) * 128 + row) * 16) =
+            make_uint4(pack2<T, false>(v[0], v[1]), pack2<T, false>(v[2], v[3]), pack2<T, false>(v[4], v[5]), pack2<T, false>(v[6], v[7]));
+        *reinterpret_cast<uint4*>(a3 + ((size_t)(4 + c0 / 8 + 1) * 128 + row) * 16) =
+            make_uint4(pack2<T, false>(v[8], v[9]), pack2<T, false>(v[10], v[11]), pack2<T, false>(v[12], v[13]), pack2<T, false>(v[14], v[15]));
       }
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
@@ -222,7 +239,13 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
         }
         const T* re = reinterpret_cast<const T*>(rraw) + c0;
 #pragma unroll
-        for (int c = 0; c < 16; ++c) v[c] += __ldg(p.bo + c0 + c) + (valid ? to_f32<T>(re[c]) : 0.f);
+        for (int c = 0; c < 16; c += 4) {
+          const float4 b = *reinterpret_cast<const float4*>(bias_s + 96 + c0 + c);
+          v[c] += b.x + to_f32<T>(re[c]);
+          v[c + 1] += b.y + to_f32<T>(re[c + 1]);
+          v[c + 2] += b.z + to_f32<T>(re[c + 2]);
+          v[c + 3] += b.w + to_f32<T>(re[c + 3]);
+        }
         store_chunk16_coalesced<T>(out, p.out_pitch, p.out_off + c0, pix32, v, stage, lane);
       }
     }
@@ -241,7 +264,7 @@ inline const char* csar_tail_umma_launch(const TailUmmaParams& pin, bool fp16, i
   TailTmap tm;
   if (const char* msg = umma_make_tmap(&tm.m, p.x_in, fp16, 32, 32, false, 0, 0, 0, 128, 0, p.total_px)) return msg;
   constexpr size_t kSlot = 128 * 64 + 2 * 128 * 128;
-  const size_t smem = 1024 + kTailGroups * kSlot + 32 * 64 * 2 + 2 * 64 * 32 * 2 + (7 * kTailGroups + 2) * 8 + 4 * kTailGroups * 1024 + 64;
+  const size_t smem = 1024 + kTailGroups * kSlot + 32 * 64 * 2 + 2 * 64 * 32 * 2 + (7 * kTailGroups + 2) * 8 + 4 * kTailGroups * 1024 + 128 * 4 + 64;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(csar_tail_umma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

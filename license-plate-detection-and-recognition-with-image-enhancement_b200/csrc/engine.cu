@@ -415,7 +415,9 @@ WsLayout ws_layout(const lpsr_handle* h, int B, int H, int W) {
   L.xin = take(BP * 32, es);
   L.g0 = take(BP * 32, es);
   L.g = take(BP * 32, es);
-  L.pool = take((size_t)B * S * 32, 4);
+  // 16-bit modes: one partial per (tile, epilogue warp) of conv_in.2; a crop has at most ~1.3 x P/126 tiles (halo rows of its strips)
+  L.pool_slots = half_mode(h) ? 4 * (2 * (L.P / 128) + 40) : 0;
+  L.pool = take((size_t)B * std::max(S, L.pool_slots) * 32, 4);
   L.sc = take((size_t)B * 32, 4);
   if (half_mode(h)) {   // tensor-core CSAR tail: 64-channel hidden map and the gated concat [x_in^2*s_c | x_in*s_s]
     L.hid = take(BP * 64, es);

@@ -100,6 +100,7 @@ inline size_t elem_size(const lpsr_handle* h) { return half_mode(h) ? 2 : 4; }
 struct WsLayout {
   size_t xu, c0, e0, e1, d0, s, ae, sfe1, x0, f[4], grow[2][4], t, xin, g0, g, pool, hid, gate, sc, total;
   int Hp, Wp, P, S;
+  int pool_slots;   // 16-bit modes: capacity (per crop) of the pooled partial sums written by conv_in.2's epilogue (0: not used)
 };
 
 WsLayout ws_layout(const lpsr_handle* h, int B, int H, int W);

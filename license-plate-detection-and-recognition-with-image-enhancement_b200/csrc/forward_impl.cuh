@@ -128,14 +128,36 @@ void csar_block(Ctx& c, const WsLayout& L, char* ws, int B, size_t in_t, size_t 
   c.tag = tag_conv;
   // x_in = conv_in.2(relu(conv_in.0(x)))                                               (lpsr.py:159-172,181)
   dense_conv<T>(c, h->csar_c1, conv_params(h->csar_c1, xres, 32, 0, 16, t, 32, 0, B, L.Hp, L.Wp, true));
-  dense_conv<T>(c, h->csar_c2, conv_params(h->csar_c2, t, 32, 0, 16, xin, 32, 0, B, L.Hp, L.Wp, false));
+  int pool_slots = L.S;                         // partial sums per crop feeding the channel gate
+  bool pooled = false;
+  if constexpr (sizeof(T) == 2) {
+    static int fuse_pool = -1;
+    if (fuse_pool < 0) { const char* e = getenv("LPSR_POOL_FUSED"); fuse_pool = (e && e[0] == '0') ? 0 : 1; }
+    if (fuse_pool && h->csar_c2.u.packed && L.pool_slots > 0) {
+      // conv_in.2 with AdaptiveAvgPool2d(1)'s partial sums (lpsr.py:124) taken from its own fp32 results: x_in is not read back
+      c.begin("umma_conv");
+      pooled = true;
+      if (!c.dry && c.rc == LPSR_OK) {
+        UmmaGate g{};
+        g.epi = kEpiPool;
+        g.pool = pool;
+        g.pool_slots_per_crop = L.pool_slots;
+        g.out_slots_per_crop = &pool_slots;
+        const char* msg = umma_conv_launch<T>(h->csar_c2.u, conv_params(h->csar_c2, t, 32, 0, 16, xin, 32, 0, B, L.Hp, L.Wp, false), h->num_sms, c.st, &g);
+        if (msg) c.rc = fail(h, LPSR_ERR_CUDA, "umma_conv conv_in.2 + pool launch: %s", msg);
+      }
+    }
+  }
+  if (!pooled) dense_conv<T>(c, h->csar_c2, conv_params(h->csar_c2, t, 32, 0, 16, xin, 32, 0, B, L.Hp, L.Wp, false));
   c.tag = tag_tail;
-  // AdaptiveAvgPool2d(1) partial sums                                                    (lpsr.py:124)
-  c.begin("gap_partial");
-  if (!c.dry && c.rc == LPSR_OK) {
-    gap_partial_kernel<T><<<dim3(L.S, B), kThreads, 0, c.st>>>(xin, 32, 0, L.P, L.S, pool);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) c.rc = fail(h, LPSR_ERR_CUDA, "gap_partial launch: %s", cudaGetErrorString(e));
+  if (!pooled) {
+    // AdaptiveAvgPool2d(1) partial sums                                                    (lpsr.py:124)
+    c.begin("gap_partial");
+    if (!c.dry && c.rc == LPSR_OK) {
+      gap_partial_kernel<T><<<dim3(L.S, B), kThreads, 0, c.st>>>(xin, 32, 0, L.P, L.S, pool);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) c.rc = fail(h, LPSR_ERR_CUDA, "gap_partial launch: %s", cudaGetErrorString(e));
+    }
   }
   // gates + conv_out + residual                                                          (lpsr.py:182-186)
   if constexpr (sizeof(T) == 2) {
@@ -146,7 +168,7 @@ void csar_block(Ctx& c, const WsLayout& L, char* ws, int B, size_t in_t, size_t 
       float* sc = reinterpret_cast<float*>(ws + L.sc);
       c.begin("channel_gate");
       if (!c.dry && c.rc == LPSR_OK) {
-        channel_gate_kernel<<<B, 32, 0, c.st>>>(pool, L.S, L.P, h->ca_w1, h->ca_b1, h->ca_w2, h->ca_b2, sc);
+        channel_gate_kernel<<<B, 32, 0, c.st>>>(pool, pool_slots, L.P, h->ca_w1, h->ca_b1, h->ca_w2, h->ca_b2, sc);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) c.rc = fail(h, LPSR_ERR_CUDA, "channel_gate launch: %s", cudaGetErrorString(e));
       }

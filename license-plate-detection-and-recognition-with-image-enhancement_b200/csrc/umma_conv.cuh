@@ -81,6 +81,7 @@ struct UmmaParams {
   const float* gate;                         // s_c [B][32]
   int out_off2;
   int px_per_crop;
+  float* pool;                      // kEpiPool: [n_items * k][4 warps][32] channel sums
   long long* trace;                 // LPSR_UMMA_TRACE (profiling experiments): clock64 stamps of CTA 0 [role][tile][stamp]
   int debug;                        // LPSR_UMMA_DEBUG bitmask (profiling experiments only): 1 skip MMAs, 2 skip stores, 4 skip TMA loads
 };
@@ -251,7 +252,33 @@ template <> struct IsBf16<__nv_bfloat16> { static constexpr bool value = true; }
 //   UnshuffleRelu: 12 real channels of pixel (y,x) -> ReLU -> channel c*4 + (y&1)*2 + (x&1) of pixel (y/2, x/2) of a half-size tensor
 //   ReluUp2Res   : N = 2 x 48: column block J is pixel (2y + I, 2x + J) of a double-size tensor (I = out_off2): ReLU, + residual
 //   Shuffle8     : N = 4 sub-pixels x 4 (3 real): sub-pixel (I,J) -> 8-channel (16-byte) pixel (2y + I, 2x + J)
-enum { kEpiPlain = 0, kEpiGate = 1, kEpiFinalSigmoid = 2, kEpiRelu = 3, kEpiResidual = 4, kEpiUnshuffleRelu = 5, kEpiReluUp2Res = 6, kEpiShuffle8 = 7 };
+//   Pool         : plain (+bias) store, and per (tile, warp) channel sums of the fp32 results -> pool[(tile*4 + warp)*32 + c]: the partial
+//                  sums of AdaptiveAvgPool2d(1) over CSAR's x_in (lpsr.py:124,181) without reading x_in back; fixed order, so deterministic
+enum { kEpiPlain = 0, kEpiGate = 1, kEpiFinalSigmoid = 2, kEpiRelu = 3, kEpiResidual = 4, kEpiUnshuffleRelu = 5, kEpiReluUp2Res = 6, kEpiShuffle8 = 7,
+       kEpiPool = 8 };
+
+// sum over the 32 lanes of 16 values per lane (a 32 x 16 transpose-reduce): 16 shuffles; lane l returns the total of value (l >> 1) & 15
+__device__ __forceinline__ float warp_column_sums16(const float (&r)[16], int lane) {
+  float a8[8], a4[4], a2[2];
+  {
+    const bool hi = (lane & 16) != 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a8[i] = (hi ? r[8 + i] : r[i]) + __shfl_xor_sync(0xffffffffu, hi ? r[i] : r[8 + i], 16);
+  }
+  {
+    const bool hi = (lane & 8) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a4[i] = (hi ? a8[4 + i] : a8[i]) + __shfl_xor_sync(0xffffffffu, hi ? a8[i] : a8[4 + i], 8);
+  }
+  {
+    const bool hi = (lane & 4) != 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) a2[i] = (hi ? a4[2 + i] : a4[i]) + __shfl_xor_sync(0xffffffffu, hi ? a4[i] : a4[2 + i], 4);
+  }
+  const bool hi = (lane & 2) != 0;
+  const float a1 = (hi ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, hi ? a2[0] : a2[1], 2);
+  return a1 + __shfl_xor_sync(0xffffffffu, a1, 1);
+}
 
 // ---------------------------------------------------------------------------------------------------
 // the kernel
@@ -797,6 +824,13 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
                 for (int c = 0; c < CH; ++c) v[c] += r[c];
               }
             }
+            if constexpr (EPI == kEpiPool) {
+              float r[CH];
+#pragma unroll
+              for (int c = 0; c < CH; ++c) r[c] = pix >= 0 ? v[c] : 0.f;
+              const float tot = warp_column_sums16(r, lane);
+              if (!(lane & 1)) p.pool[((size_t)(item * k_tiles + m) * 4 + wq) * NOUT + cc + ((lane >> 1) & 15)] = tot;
+            }
             // all 32 lanes take part in the staged, coalesced store (rows without a pixel are skipped inside)
             if (!LPSR_DBG(32)) store_chunk16_coalesced<T, EPI == kEpiRelu>(out, out_pitch, out_off + cc, pix32, v, stage, lane);
             else if (v[0] == 123.456f) out[0] = from_f32<T>(v[1] + v[5] + v[9] + v[13]);
@@ -866,7 +900,9 @@ inline const char* umma_make_tmap(CUtensorMap* out, const void* base, bool fp16,
 
 inline long long*& umma_trace_buffer() { static long long* b = nullptr; return b; }
 
-inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvParams& cp, int num_sms, bool fp16, bool fp32_out = false) {
+// batch_invariant: the tiling of a crop must not depend on the batch size (the pooled partial sums are added tile by tile)
+inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvParams& cp, int num_sms, bool fp16, bool fp32_out = false,
+                             bool batch_invariant = false) {
   UmmaParams& p = plan.p;
   p = UmmaParams{};
   memset(&plan.tm, 0, sizeof plan.tm);
@@ -973,7 +1009,7 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
         const double work = (double)items_strip * k * 128 / (double)(cp.H * TW);
         const double stage = (double)items_strip * (double)npx / (double)(cp.H * TW);
         const long long waves = (items + num_sms - 1) / num_sms;
-        const double fill = (double)(waves * num_sms) / (double)items;
+        const double fill = batch_invariant ? 1.0 : (double)(waves * num_sms) / (double)items;
         const double cost = fill * (0.75 * work + 0.25 * stage);
         if (cost < best_cost - 1e-9) { best_cost = cost; best_k = k; best_ns = ns; }
       }
@@ -1048,6 +1084,9 @@ inline const char* umma_launch_epi(const UmmaPlan& plan, cudaStream_t st) {
   if constexpr (N == 32 && MODE == kConv1x1) {
     if (p.mode == kEpiGate) return umma_launch_inst<T, N, MODE, kEpiGate>(plan, st);
   }
+  if constexpr (N == 32 && MODE == kConv3x3Taps) {
+    if (p.mode == kEpiPool) return umma_launch_inst<T, N, MODE, kEpiPool>(plan, st);
+  }
   if constexpr (N == 16 && MODE == kConv3x3Fold) {
     if (p.mode == kEpiFinalSigmoid) return umma_launch_inst<T, N, MODE, kEpiFinalSigmoid>(plan, st);
   }
@@ -1089,15 +1128,25 @@ struct UmmaGate {
   int final_sigmoid;       // 1: kEpiFinalSigmoid instead (ConvParams::out is a float [B*H*W] tensor)
   int epi = 0;             // kEpiUnshuffleRelu / kEpiReluUp2Res / kEpiShuffle8: the AutoEncoder's shuffling stores (else 0)
   int up_row = 0;          // kEpiReluUp2Res: row parity I produced by this launch
+  float* pool = nullptr;   // kEpiPool: partial-sum buffer, pool_slots_per_crop x 32 floats per crop
+  int pool_slots_per_crop = 0;          // capacity of `pool` per crop
+  int* out_slots_per_crop = nullptr;    // kEpiPool: receives the slots the launch wrote per crop (tiles per crop x 4)
 };
 
 template <typename T, typename TOUT = T>
 inline const char* umma_conv_launch(const UmmaWeights& w, const ConvParams& cp, int num_sms, cudaStream_t st, const UmmaGate* gate = nullptr) {
   UmmaPlan plan;
-  if (const char* msg = umma_plan(plan, w, cp, num_sms, !IsBf16<T>::value, gate && gate->final_sigmoid)) return msg;
+  if (const char* msg = umma_plan(plan, w, cp, num_sms, !IsBf16<T>::value, gate && gate->final_sigmoid, gate && gate->epi == kEpiPool)) return msg;
   if (gate && gate->epi) {
     plan.p.mode = gate->epi;
     plan.p.out_off2 = gate->up_row;
+    if (gate->epi == kEpiPool) {
+      const int slots = plan.p.n_strips * plan.p.items_per_strip * plan.p.k * 4;
+      if (w.ks != 3 || w.cout != 32 || !gate->pool || !gate->out_slots_per_crop) return "pool epilogue needs a 3x3 conv with Cout = 32 and a partial buffer";
+      if (slots > gate->pool_slots_per_crop) return "pool partial buffer too small";
+      plan.p.pool = gate->pool;
+      *gate->out_slots_per_crop = slots;
+    }
     if (gate->epi == kEpiReluUp2Res && (!cp.res || cp.res_pitch % 8 || cp.res_off % 8)) return "up2 epilogue needs an aligned residual";
   } else if (gate && gate->final_sigmoid) {
     if (w.ks != 3 || w.cout != 16) return "final epilogue needs the folded 3x3 conv with Cout padded to 16";
