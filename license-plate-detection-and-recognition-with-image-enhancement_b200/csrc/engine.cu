@@ -173,14 +173,14 @@ DenseConv compose_dconv(const lpsr_handle* h, const std::string& p, int cin, int
 
 // The same convolution evaluated on the 2x COARSER grid (space-to-depth): a coarse pixel carries its 2x2 fine pixels as channels,
 // fine output row 2h + I reads fine rows 2h + I + dy - R = 2(h + th) + i, th in {-1,0,1} for any ks <= 5, so the coarse kernel is
-// 3x3 with w'[n(co,I,J)][k(ci,i,j)][th][tw] = w[co][ci][2th + i - I + R][2tw + j - J + R] (zero where that tap does not exist).
-// in_index / out_index give the operand's channel order (out_index < 0: column not produced by this launch).
-// Returns [9][cin_cols][cout_cols] fp32 (the layout umma_pack_weights takes) and the per-column bias.
+// 3x3 (5x5 for a 7x7 fine kernel: th in {-2..2}) with w'[n(co,I,J)][k(ci,i,j)][th][tw] = w[co][ci][2th + i - I + R][2tw + j - J + R]
+// (zero where that tap does not exist).  in_index / out_index give the operand's channel order (out_index < 0: column not produced
+// by this launch).  Returns [KC*KC][cin_cols][cout_cols] fp32 (the layout umma_pack_weights takes) and the per-column bias.
 template <typename InIdx, typename OutIdx>
 void s2d_weights(const DenseConv& d, int cin_cols, int cout_cols, InIdx in_index, OutIdx out_index, std::vector<float>& pw,
                  std::vector<float>& pb) {
-  const int R = d.ks / 2;
-  pw.assign((size_t)9 * cin_cols * cout_cols, 0.f);
+  const int R = d.ks / 2, RC = d.ks <= 5 ? 1 : 2, KC = 2 * RC + 1;
+  pw.assign((size_t)KC * KC * cin_cols * cout_cols, 0.f);
   pb.assign(cout_cols, 0.f);
   for (int co = 0; co < d.cout; ++co)
     for (int I = 0; I < 2; ++I)
@@ -192,13 +192,13 @@ void s2d_weights(const DenseConv& d, int cin_cols, int cout_cols, InIdx in_index
           for (int i = 0; i < 2; ++i)
             for (int j = 0; j < 2; ++j) {
               const int k = in_index(ci, i, j);
-              for (int th = -1; th <= 1; ++th) {
+              for (int th = -RC; th <= RC; ++th) {
                 const int dy = 2 * th + i - I + R;
                 if (dy < 0 || dy >= d.ks) continue;
-                for (int tw = -1; tw <= 1; ++tw) {
+                for (int tw = -RC; tw <= RC; ++tw) {
                   const int dx = 2 * tw + j - J + R;
                   if (dx < 0 || dx >= d.ks) continue;
-                  pw[((size_t)((th + 1) * 3 + (tw + 1)) * cin_cols + k) * cout_cols + n] = d.w[((size_t)co * d.cin + ci) * d.ks * d.ks + dy * d.ks + dx];
+                  pw[((size_t)((th + RC) * KC + (tw + RC)) * cin_cols + k) * cout_cols + n] = d.w[((size_t)co * d.cin + ci) * d.ks * d.ks + dy * d.ks + dx];
                 }
               }
             }
@@ -248,11 +248,17 @@ bool pack_ae_tensor_core(lpsr_handle* h) {
     s2d_weights(d1, 48, 96, unshuffle_idx, [I0](int co, int I, int J) { return I == I0 ? J * 48 + co : -1; }, pw, pb);
     ok &= umma_pack_weights(h->aet_dec1[I0], pw.data(), pb.data(), 3, 48, 96, fp16, put16, put32);
   }
-  // conv_out 12 -> 3 (3x3, no bias) on the half grid: columns (I*2+J)*4 + co (3 real of 4) -> 8-channel full-resolution pixels
+  // conv_out 12 -> 3 (3x3, no bias) on the half grid: the output stays PixelUnshuffle(ae_out), 12 real of 16 columns
   DenseConv co;
   co.cin = 12; co.cout = 3; co.ks = 3; co.w = W(h, "auto_encoder.conv_out.weight");
-  s2d_weights(co, 48, 16, unshuffle_idx, [](int c, int I, int J) { return (I * 2 + J) * 4 + c; }, pw, pb);
+  s2d_weights(co, 48, 16, unshuffle_idx, unshuffle_idx, pw, pb);
   ok &= umma_pack_weights(h->aet_out, pw.data(), nullptr, 3, 48, 16, fp16, put16, put32);
+  // RDN shallowF1 (7x7, 3 -> 32, lpsr.py:195-197) on the half grid: 5x5 coarse taps over the 12 (of 16) unshuffled channels, four
+  // 32-channel full-resolution pixels per half-grid pixel (N = 128), written by the epilogue in the trunk's element type
+  DenseConv s1;
+  s1.cin = 3; s1.cout = 32; s1.ks = 7; s1.w = W(h, "rdn.shallowF1.weight"); s1.b = W(h, "rdn.shallowF1.bias");
+  s2d_weights(s1, 16, 128, unshuffle_idx, [](int c, int I, int J) { return (I * 2 + J) * 32 + c; }, pw, pb);
+  ok &= umma_pack_weights(h->aet_sfe1, pw.data(), pb.data(), 5, 16, 128, fp16, put16, put32);
   return ok;
 }
 
@@ -690,7 +696,7 @@ int lpsr_debug_read_tap(lpsr_handle* h, const char* name, float* dst, int64_t ds
   const Tap taps[] = {
       {"ae.c0", L.c0, tc ? 48 : 12, 0, 12, 1, tc, tc},  {"ae.enc0", L.e0, 48, 0, 48, 2, 0, tc},   {"ae.enc1", L.e1, 48, 0, 48, 4, 0, tc},
       {"ae.dec0", L.d0, tc ? 48 : 12, 0, 12, 2, tc, tc}, {"ae.sum", L.s, tc ? 48 : (h->sfe1_u.packed ? 16 : 12), 0, 12, 1, tc, tc},
-      {"ae.out", L.ae, tc ? 8 : (h->sfe1_u.packed ? 16 : 3), 0, 3, 1, 0, 0},
+      {"ae.out", L.ae, tc ? 16 : (h->sfe1_u.packed ? 16 : 3), 0, 3, 1, tc, tc},
       {"rdn.sfe1", L.sfe1, 32, 0, 32, 1, 0}, {"rdn.sfe2", L.x0, 32, 0, 32, 1, 0},
       {"rdn.block0", L.f[0], 32, 0, 32, 1, 0}, {"rdn.block1", L.f[1], 32, 0, 32, 1, 0},
       {"rdn.block2", L.f[2], 32, 0, 32, 1, 0}, {"rdn.block3", L.f[3], 32, 0, 32, 1, 0},

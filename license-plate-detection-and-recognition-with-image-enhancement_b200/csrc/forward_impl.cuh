@@ -261,7 +261,8 @@ void rdb_block(Ctx& c, const WsLayout& L, char* ws, int B, int r, size_t x_t, si
 //   d0q [H/4][W/4][48]  = relu(DConv(e1)), shuffle pending         5x5 taps on the quarter grid, N=48        (lpsr.py:83-89)
 //   s   [H/2][W/2][48]  = c0u + relu(unshuffle(shuffle(DConv(shuffle(d0q)))))   3x3 taps on the quarter grid, two launches of
 //                         N=96 (row parity I), each storing half-grid pixels (2h+I, 2w+{0,1})               (lpsr.py:90-96,115)
-//   ae  [H][W][8]       = conv_out(c0 + d)                         folded 3x3 on the half grid, N=4x4, shuffling store (102-104,116)
+//   aeu [H/2][W/2][16]  = unshuffle(conv_out(c0 + d))              folded 3x3 on the half grid, N=12 of 16   (lpsr.py:102-104,116)
+//   sfe1 [H][W][32]     = shallowF1(ae_out) (7x7)                  5x5 taps on the half grid, K=16, N=4x32, 2x up-store (195-197)
 // Operands and intermediate tensors of the AutoEncoder are fp16 in BOTH 16-bit modes (its activations are O(1), and the extra three
 // mantissa bits matter: the trunk amplifies AutoEncoder rounding ~20x); only the last stage converts to the trunk's type T.
 template <typename T>
@@ -274,12 +275,13 @@ void ae_forward_tc(Ctx& c, const WsLayout& L, char* ws, const float* x, int B, i
   TA* e1 = reinterpret_cast<TA*>(ws + L.e1);
   TA* d0q = reinterpret_cast<TA*>(ws + L.d0);
   TA* s = reinterpret_cast<TA*>(ws + L.s);
-  T* ae = reinterpret_cast<T*>(ws + L.ae);
+  TA* aeu = reinterpret_cast<TA*>(ws + L.ae);                  // PixelUnshuffle(AutoEncoder output): 12 real of 16 channels
+  TA* sfe1 = reinterpret_cast<TA*>(ws + L.sfe1);               // written as T by the Up2Store epilogue (same element size)
   const int H2 = L.Hp / 2, W2 = L.Wp / 2, H4 = L.Hp / 4, W4 = L.Wp / 4;
   auto run = [&](const char* what, const UmmaWeights& u, const ConvParams& p, const UmmaGate* g) {
     c.begin("umma_conv_ae");
     if (c.dry || c.rc != LPSR_OK) return;
-    const char* msg = (g && g->epi == kEpiShuffle8) ? umma_conv_launch<TA, T>(u, p, h->num_sms, c.st, g) : umma_conv_launch<TA>(u, p, h->num_sms, c.st, g);
+    const char* msg = (g && g->epi == kEpiUp2Store) ? umma_conv_launch<TA, T>(u, p, h->num_sms, c.st, g) : umma_conv_launch<TA>(u, p, h->num_sms, c.st, g);
     if (msg) c.rc = fail(h, LPSR_ERR_CUDA, "umma_conv %s launch: %s", what, msg);
   };
   auto shape = [](int ks, int cin, int cout) { ConvW w; w.ks = ks; w.cin = cin; w.cout = cout; return w; };
@@ -311,10 +313,13 @@ void ae_forward_tc(Ctx& c, const WsLayout& L, char* ws, const float* x, int B, i
     run("ae.dec1", h->aet_dec1[I], conv_params(shape(3, 48, 96), d0q, 48, 0, 16, s, 48, 0, B, H4, W4, true, c0u, 48, 0), &g);
   }
   c.tag = "ae.conv_out";
+  run("ae.conv_out", h->aet_out, conv_params(shape(3, 48, 16), s, 48, 0, 16, aeu, 16, 0, B, H2, W2, false), nullptr);
+  // RDN shallowF1: the 7x7 over the 3-channel AutoEncoder output, evaluated on the half grid (25 coarse taps, K = 16, N = 4 x 32)
+  c.tag = "rdn.shallowF1";
   {
     UmmaGate g{};
-    g.epi = kEpiShuffle8;
-    run("ae.conv_out", h->aet_out, conv_params(shape(3, 48, 16), s, 48, 0, 16, ae, 8, 0, B, H2, W2, false), &g);
+    g.epi = kEpiUp2Store;
+    run("rdn.shallowF1", h->aet_sfe1, conv_params(shape(5, 16, 128), aeu, 16, 0, 16, sfe1, 32, 0, B, H2, W2, false), &g);
   }
 }
 
@@ -340,7 +345,6 @@ int forward_impl(lpsr_handle* h, const float* x, float* y, int B, int H, int W, 
   bool ae_tc = false;
   if constexpr (sizeof(T) == 2) ae_tc = h->ae_tc;
   const bool sfe1_tc = (sizeof(T) == 2) && h->sfe1_u.packed && h->ae_out_u.packed;
-  const int ae_pitch = ae_tc ? 8 : 16;                         // 16-byte pixels (3 real channels) straight from the tensor-core conv_out
   if (ae_tc) {
     if constexpr (sizeof(T) == 2) ae_forward_tc<T>(c, L, ws, x, B, H, W);
   } else {
@@ -382,17 +386,17 @@ int forward_impl(lpsr_handle* h, const float* x, float* y, int B, int H, int W, 
   // ---- RDN (lpsr.py:214-225) ---------------------------------------------------------------------------
   c.tag = "rdn.shallowF1";
   if constexpr (sizeof(T) == 2) {
-    if (sfe1_tc) {
+    if (sfe1_tc && !ae_tc) {
       c.begin("umma_conv7x7");
       if (!c.dry && c.rc == LPSR_OK) {
         ConvW w7;
         w7.ks = 7; w7.cin = 448; w7.cout = 32;
-        const char* msg = umma_conv_launch<T>(h->sfe1_u, conv_params(w7, {Seg{ae, ae_pitch, 0, 8}}, 8, sfe1, 32, 0, B, Hp, Wp, false), h->num_sms, c.st);
+        const char* msg = umma_conv_launch<T>(h->sfe1_u, conv_params(w7, {Seg{ae, 16, 0, 8}}, 8, sfe1, 32, 0, B, Hp, Wp, false), h->num_sms, c.st);
         if (msg) c.rc = fail(h, LPSR_ERR_CUDA, "umma_conv 7x7 launch: %s", msg);
       }
     }
   }
-  if (!sfe1_tc) launch_direct<T, 7, 3, 32, false, false>(c, conv_params(h->sfe1, ae, 3, 0, 3, sfe1, 32, 0, B, Hp, Wp, false));
+  if (!sfe1_tc && !ae_tc) launch_direct<T, 7, 3, 32, false, false>(c, conv_params(h->sfe1, ae, 3, 0, 3, sfe1, 32, 0, B, Hp, Wp, false));
   c.tag = "rdn.shallowF2";
   dense_conv<T>(c, h->sfe2, conv_params(h->sfe2, sfe1, 32, 0, 16, x0, 32, 0, B, Hp, Wp, false));
   c.tag = "rdb0";

@@ -251,10 +251,11 @@ template <> struct IsBf16<__nv_bfloat16> { static constexpr bool value = true; }
 // PixelUnshuffle / PixelShuffle (lpsr.py:72,79,88,95) are folded into the convolutions around them:
 //   UnshuffleRelu: 12 real channels of pixel (y,x) -> ReLU -> channel c*4 + (y&1)*2 + (x&1) of pixel (y/2, x/2) of a half-size tensor
 //   ReluUp2Res   : N = 2 x 48: column block J is pixel (2y + I, 2x + J) of a double-size tensor (I = out_off2): ReLU, + residual
-//   Shuffle8     : N = 4 sub-pixels x 4 (3 real): sub-pixel (I,J) -> 8-channel (16-byte) pixel (2y + I, 2x + J)
+//   Up2Store     : N = 4 sub-pixels x 32: column block (I*2 + J) is pixel (2y + I, 2x + J) of a double-size 32-channel tensor of type TOUT
+//                  (shallowF1's 7x7 evaluated on the half grid, lpsr.py:195-197)
 //   Pool         : plain (+bias) store, and per (tile, warp) channel sums of the fp32 results -> pool[(tile*4 + warp)*32 + c]: the partial
 //                  sums of AdaptiveAvgPool2d(1) over CSAR's x_in (lpsr.py:124,181) without reading x_in back; fixed order, so deterministic
-enum { kEpiPlain = 0, kEpiGate = 1, kEpiFinalSigmoid = 2, kEpiRelu = 3, kEpiResidual = 4, kEpiUnshuffleRelu = 5, kEpiReluUp2Res = 6, kEpiShuffle8 = 7,
+enum { kEpiPlain = 0, kEpiGate = 1, kEpiFinalSigmoid = 2, kEpiRelu = 3, kEpiResidual = 4, kEpiUnshuffleRelu = 5, kEpiReluUp2Res = 6, kEpiUp2Store = 7,
        kEpiPool = 8 };
 
 // sum over the 32 lanes of 16 values per lane (a 32 x 16 transpose-reduce): 16 shuffles; lane l returns the total of value (l >> 1) & 15
@@ -335,8 +336,8 @@ struct UmmaTmaps { CUtensorMap m[kUmmaMaxKChunks]; };   // one tiled map per K-c
 
 // EPI (epilogue, compile time so the per-tile instruction stream carries no dead branches):
 //   kEpiPlain: +bias | kEpiRelu: +bias, ReLU | kEpiResidual: +bias, +residual | kEpiGate: CSAR gates | kEpiFinalSigmoid
-// TOUT: element type of the Shuffle8 output (the AutoEncoder runs fp16 operands in both 16-bit modes; its last stage writes the
-// trunk's type)
+// TOUT: element type of the Up2Store output (the AutoEncoder and shallowF1 run fp16 operands in both 16-bit modes; the stage that
+// feeds the trunk writes the trunk's type)
 template <typename T, int NOUT, int MODE, int EPI, typename TOUT = T>
 __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid_constant__ UmmaParams p, const __grid_constant__ UmmaTmaps tm) {
   static_assert(sizeof(T) == 2, "16-bit operands");
@@ -629,6 +630,21 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
             for (int i = 0; i < NRES; ++i) rsd_raw[i] = *reinterpret_cast<const uint4*>(res + (size_t)pix * res_pitch + res_off + i * 8);
           }
         }
+        // double-size residual (kEpiReluUp2Res): rolling prefetch two 16-channel chunks ahead, so the global-load latency hides
+        // behind the accumulator wait and the previous chunks' stores instead of stalling every chunk
+        [[maybe_unused]] uint4 up_nxt[2][2];
+        [[maybe_unused]] int up_base = -1;
+        if constexpr (EPI == kEpiReluUp2Res) {
+          if (pix >= 0) {
+            up_base = (nn * 2 * Himg + 2 * yy + p.out_off2) * 2 * Wimg + 2 * xx;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const T* src = res + (size_t)(up_base + (q * CH) / 48) * res_pitch + res_off + (q * CH) % 48;
+              up_nxt[q][0] = *reinterpret_cast<const uint4*>(src);
+              up_nxt[q][1] = *reinterpret_cast<const uint4*>(src + 8);
+            }
+          }
+        }
         LPSR_TRACE(wq == 0 && lane == 0, ii * k_tiles + m, 3, clock64());
         ptx::mbar_wait(tfull_bar(grp), my_par);
         ptx::tc_fence_after();
@@ -760,33 +776,23 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
           } else if constexpr (EPI == kEpiReluUp2Res) {
             // this launch produces row 2y + I of the double-size tensor; column block J = cc / 48 is pixel 2x + J
             static_assert(EPI != kEpiReluUp2Res || NOUT == 96, "two 48-channel pixels per row");
-            const int up = valid ? ((nn * 2 * Himg + 2 * yy + p.out_off2) * 2 * Wimg + 2 * xx + cc / 48) : -1;
-            if (valid) {
-              float r[CH];
-              load_vec<T, CH>(res + (size_t)up * res_pitch + res_off + cc % 48, r);
+            const int up = valid ? up_base + cc / 48 : -1;
+            {
+              const uint4 cur[2] = {up_nxt[(cc / CH) & 1][0], up_nxt[(cc / CH) & 1][1]};
+              if (cc + 2 * CH < NOUT && pix >= 0) {
+                const T* src = res + (size_t)(up_base + (cc + 2 * CH) / 48) * res_pitch + res_off + (cc + 2 * CH) % 48;
+                up_nxt[(cc / CH) & 1][0] = *reinterpret_cast<const uint4*>(src);
+                up_nxt[(cc / CH) & 1][1] = *reinterpret_cast<const uint4*>(src + 8);
+              }
+              const T* re = reinterpret_cast<const T*>(cur);
 #pragma unroll
-              for (int c = 0; c < CH; ++c) v[c] = fmaxf(v[c], 0.f) + r[c];
+              for (int c = 0; c < CH; ++c) v[c] = fmaxf(v[c], 0.f) + to_f32<T>(re[c]);
             }
             store_chunk16_coalesced<T>(out, out_pitch, out_off + cc % 48, up, v, stage, lane);
-          } else if constexpr (EPI == kEpiShuffle8) {
-            // PixelShuffle-like store of 4 sub-pixels x 3 channels into 8-channel (16-byte) pixels; J = 0,1 are adjacent: 32-byte runs
-            static_assert(EPI != kEpiShuffle8 || NOUT == 16, "4 sub-pixels x 4 columns");
-            if (valid) {
-#pragma unroll
-              for (int I = 0; I < 2; ++I) {
-                uint4 q[2];
-#pragma unroll
-                for (int J = 0; J < 2; ++J) {
-                  TOUT* e = reinterpret_cast<TOUT*>(&q[J]);
-#pragma unroll
-                  for (int c = 0; c < 8; ++c) e[c] = from_f32<TOUT>(c < 3 ? v[(I * 2 + J) * 4 + c] : 0.f);
-                }
-                static_assert(sizeof(TOUT) == sizeof(T), "same element size");
-                uint4* o = reinterpret_cast<uint4*>(out + (size_t)((nn * 2 * Himg + 2 * yy + I) * 2 * Wimg + 2 * xx) * out_pitch + out_off);
-                o[0] = q[0];
-                *reinterpret_cast<uint4*>(reinterpret_cast<T*>(o) + out_pitch) = q[1];
-              }
-            }
+          } else if constexpr (EPI == kEpiUp2Store) {
+            static_assert(EPI != kEpiUp2Store || NOUT == 128, "four 32-channel pixels per row");
+            const int up = valid ? ((nn * 2 * Himg + 2 * yy + cc / 64) * 2 * Wimg + 2 * xx + (cc / 32) % 2) : -1;
+            store_chunk16_coalesced<TOUT>(reinterpret_cast<TOUT*>(out), out_pitch, out_off + cc % 32, up, v, stage, lane);
           } else if constexpr (EPI == kEpiGate) {
             // CSAR gates (1x1, NOUT = 32): spatial branch x_in * sigmoid(.), channel branch x_in^2 * s_c
             float g1[CH];
@@ -1101,12 +1107,12 @@ inline const char* umma_plan_launch(const UmmaPlan& plan, const UmmaWeights& w, 
   if (w.ks == 5) {   // AutoEncoder stages (composed depthwise + pointwise)
     if (w.cout == 16 && mode == kEpiUnshuffleRelu) return umma_launch_inst<T, 16, kConv5x5Taps, kEpiUnshuffleRelu>(plan, st);
     if (w.cout == 48 && plain && plan.p.relu) return umma_launch_inst<T, 48, kConv5x5Taps, kEpiRelu>(plan, st);
+    if (w.cout == 128 && mode == kEpiUp2Store) return umma_launch_inst<T, 128, kConv5x5Taps, kEpiUp2Store, TOUT>(plan, st);
     return "5x5 conv: shape/epilogue not instantiated";
   }
   if (w.ks == 3) {
     if (w.fused_lff) return (mode == kEpiPlain && plan.p.res) ? umma_launch_inst<T, 16, kConv3x3FoldLff, kEpiResidual>(plan, st)
                                                                : "fused dense layer + lff needs the residual";
-    if (w.cout == 16 && mode == kEpiShuffle8) return umma_launch_inst<T, 16, kConv3x3Fold, kEpiShuffle8, TOUT>(plan, st);
     if (w.cout == 16) return umma_launch_epi<T, 16, kConv3x3Fold>(plan, st);
     if (w.cout == 32) return umma_launch_epi<T, 32, kConv3x3Taps>(plan, st);
     if (w.cout == 48 && plain) return plan.p.relu ? umma_launch_inst<T, 48, kConv3x3Taps, kEpiRelu>(plan, st)
@@ -1126,7 +1132,7 @@ struct UmmaGate {
   const float* s_c;        // [B][32] channel gates
   int out_off_spatial;     // channel offset of x_in * sigmoid(.) in the output buffer (x_in^2 * s_c goes to ConvParams::out_off)
   int final_sigmoid;       // 1: kEpiFinalSigmoid instead (ConvParams::out is a float [B*H*W] tensor)
-  int epi = 0;             // kEpiUnshuffleRelu / kEpiReluUp2Res / kEpiShuffle8: the AutoEncoder's shuffling stores (else 0)
+  int epi = 0;             // kEpiUnshuffleRelu / kEpiReluUp2Res / kEpiUp2Store / kEpiPool (else 0)
   int up_row = 0;          // kEpiReluUp2Res: row parity I produced by this launch
   float* pool = nullptr;   // kEpiPool: partial-sum buffer, pool_slots_per_crop x 32 floats per crop
   int pool_slots_per_crop = 0;          // capacity of `pool` per crop
