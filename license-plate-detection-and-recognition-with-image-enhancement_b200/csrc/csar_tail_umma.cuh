@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::griddep_wait();
   const int n_my = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
 
   if (warp == 4 * G + 1) {
@@ -271,8 +272,8 @@ inline const char* csar_tail_umma_launch(const TailUmmaParams& pin, bool fp16, i
     if (e != cudaSuccess) return cudaGetErrorString(e);
     configured = true;
   }
-  csar_tail_umma_kernel<T><<<std::min(p.n_tiles, num_sms), kTailThreads, smem, st>>>(p, tm);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(csar_tail_umma_kernel<T>, dim3(std::min(p.n_tiles, num_sms)), dim3(kTailThreads), smem, st, p, tm);
+  if (e == cudaSuccess) e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 

@@ -428,6 +428,7 @@ static __global__ void __launch_bounds__(32) channel_gate_kernel(const float* __
                                                           const float* __restrict__ b1, const float* __restrict__ w2,
                                                           const float* __restrict__ b2, float* __restrict__ s_c) {
   __shared__ float s_mean[32], s_hid[8];
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // programmatic dependent launch (see umma_conv.cuh)
   const int b = blockIdx.x, c = threadIdx.x;
   float t = 0.f;
   for (int s = 0; s < S; ++s) t += partial[((size_t)b * S + s) * 32 + c];

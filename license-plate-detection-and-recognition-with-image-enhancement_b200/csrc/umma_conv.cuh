@@ -35,6 +35,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -177,6 +178,10 @@ __device__ __forceinline__ void tc_mma_f16_lohi(uint32_t d_tmem, uint32_t a_lo, 
       ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Programmatic dependent launch (launch attribute programmaticStreamSerialization): the kernel may be scheduled before the previous
+// grid of the stream has drained, so it waits for that grid (completion + memory flush) before touching any activation.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void bar_sync_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -425,6 +430,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // No explicit griddepcontrol.launch_dependents: measured on B200 (B = 1024), triggering at kernel start costs 4% (10.54 vs 10.12 ms
+  // per forward) and triggering before the teardown 8%; the implicit trigger at grid completion still shortens the launch gap.
+  ptx::griddep_wait();                                          // everything above touched only weights and on-chip state
 
   const int n_my_items = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int rows_per_item = p.k * p.tstride;
@@ -1066,6 +1074,24 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
   return nullptr;
 }
 
+// stream-ordered launch that may overlap the previous kernel's tail (the kernels call griddepcontrol.wait before reading activations)
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("LPSR_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 template <typename T, int N, int MODE, int EPI, typename TOUT = T>
 inline const char* umma_launch_inst(const UmmaPlan& plan, cudaStream_t st) {
   static bool configured = false;
@@ -1074,8 +1100,8 @@ inline const char* umma_launch_inst(const UmmaPlan& plan, cudaStream_t st) {
     if (e != cudaSuccess) return cudaGetErrorString(e);
     configured = true;
   }
-  umma_conv_kernel<T, N, MODE, EPI, TOUT><<<plan.grid, kUmmaThreads, plan.smem_bytes, st>>>(plan.p, plan.tm);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(umma_conv_kernel<T, N, MODE, EPI, TOUT>, dim3(plan.grid), dim3(kUmmaThreads), plan.smem_bytes, st, plan.p, plan.tm);
+  if (e == cudaSuccess) e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
