@@ -33,34 +33,71 @@ struct TailUmmaParams {
   int n_tiles;
 };
 
-struct TailTmap { CUtensorMap m; };
+struct TailTmap { CUtensorMap m; CUtensorMap r; };   // x_in tiles, residual (CSAR input) tiles
 
 template <typename T>
 __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const __grid_constant__ TailUmmaParams p, const __grid_constant__ TailTmap tm) {
   constexpr int G = kTailGroups;
-  constexpr uint32_t kA1 = 128 * 64, kA2 = 128 * 128, kSlot = kA1 + 2 * kA2;     // bytes: x_in tile, hidden tile, gated tile
+  constexpr uint32_t kA1 = 128 * 64, kA2 = 128 * 128, kSlot = 2 * kA1 + 2 * kA2;     // bytes: x_in tile, residual tile, hidden tile, gated tile
   constexpr uint32_t kW3 = 32 * 64 * 2, kW4 = 64 * 32 * 2;
+  // The additions of the three epilogues run on the tensor core as well (its pipe is mostly idle here, the epilogue warps are the
+  // bottleneck): a constant "ones" operand times a K=16 bias operand {hi(b), lo(b), 0...} starts every accumulator at its bias
+  // (hi + lo keeps the fp32 bias to 2^-17), and the residual tile times a 32x32 identity adds x exactly (1.0 * 16-bit value).
+  constexpr uint32_t kOnes = 2 * 128 * 16, kB3 = 2 * 64 * 16, kB4 = 2 * 32 * 16, kIdent = 4 * 32 * 16;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* slots = smem;                                       // G slots, each 1024-aligned (40 KB)
   uint8_t* w3_s = smem + (size_t)G * kSlot;
   uint8_t* w4_s = w3_s + kW3;
   uint8_t* wo_s = w4_s + kW4;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(wo_s + kW4);
+  uint8_t* ones_s = wo_s + kW4;                                // [2 planes][128 rows][8]: channels 0 and 1 are 1.0
+  uint8_t* b3_s = ones_s + kOnes;                              // [2][64][8]: k = 0 -> hi(b3[n]), k = 1 -> lo(b3[n])
+  uint8_t* b4_s = b3_s + kB3;
+  uint8_t* bo_s = b4_s + kB4;
+  uint8_t* id_s = bo_s + kB4;                                  // [4][32][8]: identity
+  uint64_t* bars = reinterpret_cast<uint64_t*>(id_s + kIdent);
   // per slot: 0 a1_full, 1 h_full, 2 a2_ready, 3 s_full, 4 a3_ready, 5 o_full, 6 slot_free
   const uint32_t bar0 = ptx::smem_u32(bars);
   auto bar = [&](int slot, int which) { return bar0 + 8u * (uint32_t)(slot * 7 + which); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7 * G);
   uint8_t* stage_all = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(bars + 7 * G + 2) + 15) & ~(uintptr_t)15);   // 1 KB per epilogue warp
-  float* bias_s = reinterpret_cast<float*>(stage_all + (size_t)4 * G * 1024);   // b3[64] | b4[32] | bo[32]: read as broadcast float4
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (uint32_t i = threadIdx.x; i < kW3 / 16; i += kTailThreads) reinterpret_cast<uint4*>(w3_s)[i] = __ldg(reinterpret_cast<const uint4*>(p.w3) + i);
   for (uint32_t i = threadIdx.x; i < kW4 / 16; i += kTailThreads) {
-    reinterpret_cast<uint4*>(w4_s)[i] = __ldg(reinterpret_cast<const uint4*>(p.w4) + i);
+    // W4 and b4 are halved (exact in a binary float format): the logistic is evaluated as 0.5 + 0.5 * tanh(z / 2)
+    uint4 w = __ldg(reinterpret_cast<const uint4*>(p.w4) + i);
+    T* we = reinterpret_cast<T*>(&w);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) we[j] = from_f32<T>(0.5f * to_f32<T>(we[j]));
+    reinterpret_cast<uint4*>(w4_s)[i] = w;
     reinterpret_cast<uint4*>(wo_s)[i] = __ldg(reinterpret_cast<const uint4*>(p.wo) + i);
   }
-  if (threadIdx.x < 128) bias_s[threadIdx.x] = threadIdx.x < 64 ? __ldg(p.b3 + threadIdx.x) : threadIdx.x < 96 ? __ldg(p.b4 + threadIdx.x - 64) : __ldg(p.bo + threadIdx.x - 96);
+  {
+    T* ones = reinterpret_cast<T*>(ones_s);
+    for (uint32_t i = threadIdx.x; i < 2 * 128 * 8; i += kTailThreads) ones[i] = from_f32<T>((i < 128 * 8 && (i & 7) < 2) ? 1.f : 0.f);
+    auto put_bias = [&](uint8_t* dst, const float* b, int n, float scale) {
+      T* d = reinterpret_cast<T*>(dst);
+      for (uint32_t i = threadIdx.x; i < (uint32_t)(2 * n * 8); i += kTailThreads) {
+        const uint32_t k = i & 7, col = (i >> 3) % (uint32_t)n, plane = (i >> 3) / (uint32_t)n;
+        float v = 0.f;
+        if (plane == 0 && k < 2) {
+          const float bv = scale * __ldg(b + col);
+          const float hi = to_f32<T>(from_f32<T>(bv));
+          v = k == 0 ? hi : bv - hi;
+        }
+        d[i] = from_f32<T>(v);
+      }
+    };
+    put_bias(b3_s, p.b3, 64, 1.f);
+    put_bias(b4_s, p.b4, 32, 0.5f);
+    put_bias(bo_s, p.bo, 32, 1.f);
+    T* idm = reinterpret_cast<T*>(id_s);
+    for (uint32_t i = threadIdx.x; i < 4 * 32 * 8; i += kTailThreads) {
+      const uint32_t k = (i >> 8) * 8 + (i & 7), col = (i >> 3) & 31;   // [cg][col][8]: K index = cg*8 + j
+      idm[i] = from_f32<T>(k == col ? 1.f : 0.f);
+    }
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < G; ++s) {
       ptx::mbar_init(bar(s, 0), 1);
@@ -89,12 +126,14 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
     // =================================== TMA producer ==============================================
     if (ptx::elect_one()) {
       ptx::prefetch_tmap(&tm.m);
+      ptx::prefetch_tmap(&tm.r);
       for (int t = 0; t < n_my; ++t) {
         const int s = t % G;
         ptx::mbar_wait(bar(s, 6), (((uint32_t)(t / G)) & 1u) ^ 1u);        // slot free
-        ptx::mbar_arrive_expect_tx(bar(s, 0), kA1);
+        ptx::mbar_arrive_expect_tx(bar(s, 0), 2 * kA1);
         const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
         ptx::tma_load_2d(ptx::smem_u32(slots + (size_t)s * kSlot), &tm.m, bar(s, 0), 0, (int)(tile * 128));
+        ptx::tma_load_2d(ptx::smem_u32(slots + (size_t)s * kSlot + kA1), &tm.r, bar(s, 0), p.res_off, (int)(tile * 128));
       }
     }
   } else if (warp == 4 * G) {
@@ -104,6 +143,9 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
     const uint32_t w3_lo = umma_desc_lo(ptx::smem_u32(w3_s), 64 * 16), w4_lo = umma_desc_lo(ptx::smem_u32(w4_s), 32 * 16),
                    wo_lo = umma_desc_lo(ptx::smem_u32(wo_s), 32 * 16);
     const uint32_t a1_hi = umma_desc_hi_swizzled(64);
+    const uint32_t ones_lo = umma_desc_lo(ptx::smem_u32(ones_s), 128 * 16);
+    const uint32_t b3_lo = umma_desc_lo(ptx::smem_u32(b3_s), 64 * 16), b4_lo = umma_desc_lo(ptx::smem_u32(b4_s), 32 * 16),
+                   bo_lo = umma_desc_lo(ptx::smem_u32(bo_s), 32 * 16), id_lo = umma_desc_lo(ptx::smem_u32(id_s), 32 * 16);
     for (int base = 0; base < n_my; base += G) {
       const uint32_t par = ((uint32_t)(base / G)) & 1u;
 #pragma unroll 1
@@ -115,18 +157,24 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
           if (leader) {
             const uint32_t slot16 = ptx::smem_u32(slots + (size_t)s * kSlot) >> 4;
             const uint32_t d = tmem_base + (uint32_t)(s * 128);
-            if (phase == 0) {          // hid = x_in (128x32, swizzle-64B rows) * W3^T -> 64 columns
+            if (phase == 0) {          // hid = b3 + x_in (128x32, swizzle-64B rows) * W3^T -> 64 columns
+              ptx::tc_mma_f16_lohi(d, ones_lo, kUmmaDescHi, b3_lo, kUmmaDescHi, idesc64, 0u);
 #pragma unroll
               for (int ks = 0; ks < 2; ++ks)
-                ptx::tc_mma_f16_lohi(d, (slot16 + 2u * ks) | (1u << 16), a1_hi, w3_lo + (uint32_t)(ks * 2 * 64), kUmmaDescHi, idesc64, (uint32_t)ks);
-            } else {                   // 128x64 planar operand ([8 cg][128 rows][16 B]) * W^T -> 32 columns
-              const uint32_t a16 = slot16 + ((phase == 1 ? kA1 : kA1 + kA2) >> 4);
+                ptx::tc_mma_f16_lohi(d, (slot16 + 2u * ks) | (1u << 16), a1_hi, w3_lo + (uint32_t)(ks * 2 * 64), kUmmaDescHi, idesc64, 1u);
+            } else {                   // bias (+ residual * I) + 128x64 planar operand ([8 cg][128 rows][16 B]) * W^T -> 32 columns
+              const uint32_t a16 = slot16 + ((phase == 1 ? 2 * kA1 : 2 * kA1 + kA2) >> 4);
               const uint32_t w_lo = phase == 1 ? w4_lo : wo_lo;
               const uint32_t dd = d + (phase == 1 ? 64u : 96u);
+              ptx::tc_mma_f16_lohi(dd, ones_lo, kUmmaDescHi, phase == 1 ? b4_lo : bo_lo, kUmmaDescHi, idesc32, 0u);
+              if (phase == 2) {
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks)                             // + x: the residual tile (swizzle-64B rows) times the identity
+                  ptx::tc_mma_f16_lohi(dd, (slot16 + (kA1 >> 4) + 2u * ks) | (1u << 16), a1_hi, id_lo + (uint32_t)(ks * 2 * 32), kUmmaDescHi, idesc32, 1u);
+              }
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                ptx::tc_mma_f16_lohi(dd, (a16 + (uint32_t)(ks * 2 * 128)) | (128u << 16), kUmmaDescHi, w_lo + (uint32_t)(ks * 2 * 32), kUmmaDescHi, idesc32,
-                                     (uint32_t)ks);
+                ptx::tc_mma_f16_lohi(dd, (a16 + (uint32_t)(ks * 2 * 128)) | (128u << 16), kUmmaDescHi, w_lo + (uint32_t)(ks * 2 * 32), kUmmaDescHi, idesc32, 1u);
             }
             ptx::tc_commit(bar(s, phase * 2 + 1));                         // h_full / s_full / o_full
           }
@@ -138,12 +186,11 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
     // =================================== epilogue groups ==========================================
     const int g = warp >> 2, wq = warp & 3, row = wq * 32 + lane;
     uint8_t* slot = slots + (size_t)g * kSlot;
-    uint8_t* a2 = slot + kA1;
+    uint8_t* a2 = slot + 2 * kA1;
     uint8_t* a3 = a2 + kA2;
     uint8_t* stage = stage_all + (size_t)warp * 1024;
     const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(g * 128);
     const T* xin = static_cast<const T*>(p.x_in);
-    const T* res = static_cast<const T*>(p.res);
     T* out = static_cast<T*>(p.out);
     uint32_t par = 0;
     for (int t = g; t < n_my; t += G, par ^= 1u) {
@@ -152,13 +199,10 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
       const bool valid = pix < p.total_px;
       // operands that do not depend on the tensor core: x_in row (gates), residual row, channel gates of this crop
       // (rows past the end of the batch compute on zeros; their stores are masked)
-      uint4 xraw[4] = {}, rraw[4] = {};
+      uint4 xraw[4] = {};
       if (valid) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          xraw[i] = *reinterpret_cast<const uint4*>(xin + (size_t)pix * 32 + i * 8);
-          rraw[i] = *reinterpret_cast<const uint4*>(res + (size_t)pix * p.res_pitch + p.res_off + i * 8);
-        }
+        for (int i = 0; i < 4; ++i) xraw[i] = *reinterpret_cast<const uint4*>(xin + (size_t)pix * 32 + i * 8);
       }
       const float* sc = p.s_c + (size_t)(valid ? pix / p.px_per_crop : 0) * 32;
       // ---- phase 1: hidden = relu(acc + b3) -> A2
@@ -168,11 +212,6 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
       for (int c0 = 0; c0 < 64; c0 += 16) {
         float v[16];
         ptx::tc_ld16(taddr + c0, v);
-#pragma unroll
-        for (int c = 0; c < 16; c += 4) {
-          const float4 b = *reinterpret_cast<const float4*>(bias_s + c0 + c);
-          v[c] += b.x; v[c + 1] += b.y; v[c + 2] += b.z; v[c + 3] += b.w;
-        }
         *reinterpret_cast<uint4*>(a2 + ((size_t)(c0 / 8) * 128 + row) * 16) =
             make_uint4(pack2<T, true>(v[0], v[1]), pack2<T, true>(v[2], v[3]), pack2<T, true>(v[4], v[5]), pack2<T, true>(v[6], v[7]));
         *reinterpret_cast<uint4*>(a2 + ((size_t)(c0 / 8 + 1) * 128 + row) * 16) =
@@ -192,21 +231,20 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
         const T* xe = reinterpret_cast<const T*>(xraw) + c0;
 #pragma unroll
         for (int c = 0; c < 16; c += 4) {
-          const float4 b = *reinterpret_cast<const float4*>(bias_s + 64 + c0 + c);
           const float4 s4 = __ldg(reinterpret_cast<const float4*>(sc + c0 + c));
-          const float bb[4] = {b.x, b.y, b.z, b.w}, ss4[4] = {s4.x, s4.y, s4.z, s4.w};
+          const float ss4[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float x = to_f32<T>(xe[c + j]);
-            const float z = v[c + j] + bb[j];
+            const float zh = v[c + j];                                       // (W4 hid + b4) / 2, bias and halving done by the MMA
             float sg;
             if constexpr (IsBf16<T>::value) {
               // logistic through one MUFU: 0.5 + 0.5 * tanh(z / 2); tanh.approx's 2^-11 error is below the bf16 rounding of the product
               float th;
-              asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * z));
+              asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(zh));
               sg = fmaf(0.5f, th, 0.5f);
             } else {
-              sg = __fdividef(1.f, 1.f + __expf(-z));
+              sg = __fdividef(1.f, 1.f + __expf(-2.f * zh));
             }
             ga[c + j] = x * (x * ss4[j]);                                    // channel branch x_in^2 * s_c (lpsr.py:133-135)
             v[c + j] = x * sg;                                               // spatial branch x_in * s_s  (lpsr.py:150-153)
@@ -225,7 +263,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar(g, 4));
-      // ---- phase 3: out = x + acc + bo
+      // ---- phase 3: out = acc (bias and residual already accumulated by the tensor core)
       ptx::mbar_wait(bar(g, 5), par);
       ptx::tc_fence_after();
       const int pix32 = valid ? (int)pix : -1;
@@ -237,15 +275,6 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(bar(g, 6));
-        }
-        const T* re = reinterpret_cast<const T*>(rraw) + c0;
-#pragma unroll
-        for (int c = 0; c < 16; c += 4) {
-          const float4 b = *reinterpret_cast<const float4*>(bias_s + 96 + c0 + c);
-          v[c] += b.x + to_f32<T>(re[c]);
-          v[c + 1] += b.y + to_f32<T>(re[c + 1]);
-          v[c + 2] += b.z + to_f32<T>(re[c + 2]);
-          v[c + 3] += b.w + to_f32<T>(re[c + 3]);
         }
         store_chunk16_coalesced<T>(out, p.out_pitch, p.out_off + c0, pix32, v, stage, lane);
       }
@@ -264,8 +293,10 @@ inline const char* csar_tail_umma_launch(const TailUmmaParams& pin, bool fp16, i
   p.n_tiles = (int)((p.total_px + 127) / 128);
   TailTmap tm;
   if (const char* msg = umma_make_tmap(&tm.m, p.x_in, fp16, 32, 32, false, 0, 0, 0, 128, 0, p.total_px)) return msg;
-  constexpr size_t kSlot = 128 * 64 + 2 * 128 * 128;
-  const size_t smem = 1024 + kTailGroups * kSlot + 32 * 64 * 2 + 2 * 64 * 32 * 2 + (7 * kTailGroups + 2) * 8 + 4 * kTailGroups * 1024 + 128 * 4 + 64;
+  if (const char* msg = umma_make_tmap(&tm.r, p.res, fp16, p.res_pitch, 32, false, 0, 0, 0, 128, 0, p.total_px)) return msg;
+  constexpr size_t kSlot = 2 * 128 * 64 + 2 * 128 * 128;
+  const size_t smem = 1024 + kTailGroups * kSlot + 32 * 64 * 2 + 2 * 64 * 32 * 2 + (2 * 128 + 2 * 64 + 2 * 32 + 2 * 32 + 4 * 32) * 16 +
+                      (7 * kTailGroups + 2) * 8 + 4 * kTailGroups * 1024 + 64;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(csar_tail_umma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
