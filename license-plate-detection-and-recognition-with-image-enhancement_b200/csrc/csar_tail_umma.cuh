@@ -17,7 +17,7 @@
 
 namespace lpsr {
 
-constexpr int kTailGroups = 3;
+constexpr int kTailGroups = 4;   // tile slots in flight (4 x 128 TMEM columns); one tile's three-phase chain is latency bound
 constexpr int kTailThreads = (4 * kTailGroups + 2) * 32;
 
 struct TailUmmaParams {
@@ -38,7 +38,8 @@ struct TailTmap { CUtensorMap m; CUtensorMap r; };   // x_in tiles, residual (CS
 template <typename T>
 __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const __grid_constant__ TailUmmaParams p, const __grid_constant__ TailTmap tm) {
   constexpr int G = kTailGroups;
-  constexpr uint32_t kA1 = 128 * 64, kA2 = 128 * 128, kSlot = 2 * kA1 + 2 * kA2;     // bytes: x_in tile, residual tile, hidden tile, gated tile
+  // bytes: x_in tile, residual tile, and ONE 64-channel planar operand: the hidden map, then (once MMA2 has consumed it) the gated map
+  constexpr uint32_t kA1 = 128 * 64, kA2 = 128 * 128, kSlot = 2 * kA1 + kA2;
   constexpr uint32_t kW3 = 32 * 64 * 2, kW4 = 64 * 32 * 2;
   // The additions of the three epilogues run on the tensor core as well (its pipe is mostly idle here, the epilogue warps are the
   // bottleneck): a constant "ones" operand times a K=16 bias operand {hi(b), lo(b), 0...} starts every accumulator at its bias
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
               for (int ks = 0; ks < 2; ++ks)
                 ptx::tc_mma_f16_lohi(d, (slot16 + 2u * ks) | (1u << 16), a1_hi, w3_lo + (uint32_t)(ks * 2 * 64), kUmmaDescHi, idesc64, 1u);
             } else {                   // bias (+ residual * I) + 128x64 planar operand ([8 cg][128 rows][16 B]) * W^T -> 32 columns
-              const uint32_t a16 = slot16 + ((phase == 1 ? 2 * kA1 : 2 * kA1 + kA2) >> 4);
+              const uint32_t a16 = slot16 + ((2 * kA1) >> 4);
               const uint32_t w_lo = phase == 1 ? w4_lo : wo_lo;
               const uint32_t dd = d + (phase == 1 ? 64u : 96u);
               ptx::tc_mma_f16_lohi(dd, ones_lo, kUmmaDescHi, phase == 1 ? b4_lo : bo_lo, kUmmaDescHi, idesc32, 0u);
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
     const int g = warp >> 2, wq = warp & 3, row = wq * 32 + lane;
     uint8_t* slot = slots + (size_t)g * kSlot;
     uint8_t* a2 = slot + 2 * kA1;
-    uint8_t* a3 = a2 + kA2;
+    uint8_t* a3 = a2;                                            // s_full (MMA2 complete) precedes the first write of the gated map
     uint8_t* stage = stage_all + (size_t)warp * 1024;
     const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(g * 128);
     const T* xin = static_cast<const T*>(p.x_in);
@@ -199,11 +200,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
       const bool valid = pix < p.total_px;
       // operands that do not depend on the tensor core: x_in row (gates), residual row, channel gates of this crop
       // (rows past the end of the batch compute on zeros; their stores are masked)
-      uint4 xraw[4] = {};
-      if (valid) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) xraw[i] = *reinterpret_cast<const uint4*>(xin + (size_t)pix * 32 + i * 8);
-      }
+
       const float* sc = p.s_c + (size_t)(valid ? pix / p.px_per_crop : 0) * 32;
       // ---- phase 1: hidden = relu(acc + b3) -> A2
       ptx::mbar_wait(bar(g, 1), par);
@@ -224,6 +221,10 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
       // ---- phase 2: s_s = sigmoid(acc + b4); gated concat [x_in^2 * s_c | x_in * s_s] -> A3
       ptx::mbar_wait(bar(g, 3), par);
       ptx::tc_fence_after();
+      // x_in row of this pixel from the TMA-written tile (64-byte rows, SWIZZLE_64B: 16-byte chunk j sits at j ^ ((row >> 1) & 3))
+      uint4 xraw[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) xraw[j] = *reinterpret_cast<const uint4*>(slot + row * 64 + ((j ^ ((row >> 1) & 3)) << 4));
 #pragma unroll
       for (int c0 = 0; c0 < 32; c0 += 16) {
         float v[16], ga[16];
@@ -294,7 +295,7 @@ inline const char* csar_tail_umma_launch(const TailUmmaParams& pin, bool fp16, i
   TailTmap tm;
   if (const char* msg = umma_make_tmap(&tm.m, p.x_in, fp16, 32, 32, false, 0, 0, 0, 128, 0, p.total_px)) return msg;
   if (const char* msg = umma_make_tmap(&tm.r, p.res, fp16, p.res_pitch, 32, false, 0, 0, 0, 128, 0, p.total_px)) return msg;
-  constexpr size_t kSlot = 2 * 128 * 64 + 2 * 128 * 128;
+  constexpr size_t kSlot = 2 * 128 * 64 + 128 * 128;
   const size_t smem = 1024 + kTailGroups * kSlot + 32 * 64 * 2 + 2 * 64 * 32 * 2 + (2 * 128 + 2 * 64 + 2 * 32 + 2 * 32 + 4 * 32) * 16 +
                       (7 * kTailGroups + 2) * 8 + 4 * kTailGroups * 1024 + 64;
   static bool configured = false;
