@@ -43,6 +43,12 @@ UMMA_MAC_PER_PIXEL = {
     "csar1.tail": 32 * 64 + 64 * 32 + 64 * 32, "csar3.tail": 32 * 64 + 64 * 32 + 64 * 32,   # only when the tail runs on tensor cores
 }
 CSAR_TAIL_ELEMS_PER_PIXEL = 96          # read x_in + read x + write out, 32 ch each
+# Layer-by-layer activation traffic of the reference graph (elements per full-resolution pixel: channels read + written by every layer,
+# dense concatenation in place, residual reads included; SURVEY 8d quotes ~3.66 kB/px in bf16).  AutoEncoder 102 (conv_in 3+12, enc0
+# 12+12, enc1 (48+12)/4, dec0 (48+48)/16, dec1 (12+48)/4+12, conv_out 12+3), shallowF1 3+32, shallowF2 32+32, each RDB 48+64+80+96+160,
+# each CSAR 64+64+32(pool)+96, gff 128+32 and 32+32+32, final conv 32+2.  This is the HBM roofline of an implementation that runs the
+# graph one layer at a time; fused layers (RDB tail, CSAR tail, pooled conv_in.2) move less than this.
+LAYERWISE_ELEMS_PER_PIXEL = 102 + 35 + 64 + 2 * 448 + 2 * 256 + 160 + 96 + 34
 
 
 def peaks():
@@ -288,6 +294,12 @@ def run_ours(args):
                      "peak_kind": f"copy bandwidth, of {pk['src']}", "traffic": (tr["tail_dram_bytes_per_forward"] * scale) if tr else None,
                      "algorithmic_bytes_per_forward": tail_bytes, "kernel_ms_per_forward": tail_ms}
     conv_frac_whole = value / world * P * DENSE_FLOP_PER_PIXEL / 1e12 / pk["tf_sustained"]
+    lw_bytes = float(B) * P * LAYERWISE_ELEMS_PER_PIXEL * esz
+    roofline_layerwise = {"bound": "hbm", "kernel": "whole forward, layer-by-layer activation traffic of the reference graph",
+                          "achieved": lw_bytes / (ms_step * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                          "frac": lw_bytes / (ms_step * 1e-3) / 1e9 / pk["hbm_gbs"], "peak_kind": f"copy bandwidth, of {pk['src']}",
+                          "algorithmic_bytes_per_forward": lw_bytes,
+                          "note": "fused kernels move fewer bytes than this; > 1.0 would mean the layer-by-layer HBM bound is beaten"}
 
     # ---------------- end to end through the C-ABI host-buffer call --------------------------------------------------
     y_host = torch.empty((B, 1, (H + 3) // 4 * 4, (Wd + 3) // 4 * 4), dtype=torch.float32).pin_memory()
@@ -315,7 +327,7 @@ def run_ours(args):
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[args.precision], "data": "synthetic",
                 "config": workload_config(args, B, args.precision), "clocks": clocks, "e2e": e2e, "gpu_launches": launches * args.steps,
-                "launches_per_step": launches, "roofline": roofline, "roofline_csar": roofline_csar,
+                "launches_per_step": launches, "roofline": roofline, "roofline_csar": roofline_csar, "roofline_layerwise_hbm": roofline_layerwise,
                 "conv_roofline_frac_whole_forward": conv_frac_whole,
                 "kernel_ms_per_forward": {k: round(v[0], 4) for k, v in per_kernel.items()},
                 "layer_ms_per_forward": {k: round(v, 4) for k, v in fam_ms.items()},

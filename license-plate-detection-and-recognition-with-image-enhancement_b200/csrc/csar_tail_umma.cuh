@@ -17,7 +17,7 @@
 
 namespace lpsr {
 
-constexpr int kTailGroups = 4;   // tile slots in flight (4 x 128 TMEM columns); one tile's three-phase chain is latency bound
+constexpr int kTailGroups = 5;   // tile slots in flight (4 x 128 TMEM columns); one tile's three-phase chain is latency bound
 constexpr int kTailThreads = (4 * kTailGroups + 2) * 32;
 
 struct TailUmmaParams {
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
           ptx::tc_fence_after();
           if (leader) {
             const uint32_t slot16 = ptx::smem_u32(slots + (size_t)s * kSlot) >> 4;
-            const uint32_t d = tmem_base + (uint32_t)(s * 128);
+            const uint32_t d = tmem_base + (uint32_t)(s * 64);     // 64 columns per slot: H, then S in [0,32) and O in [32,64)
             if (phase == 0) {          // hid = b3 + x_in (128x32, swizzle-64B rows) * W3^T -> 64 columns
               ptx::tc_mma_f16_lohi(d, ones_lo, kUmmaDescHi, b3_lo, kUmmaDescHi, idesc64, 0u);
 #pragma unroll
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
             } else {                   // bias (+ residual * I) + 128x64 planar operand ([8 cg][128 rows][16 B]) * W^T -> 32 columns
               const uint32_t a16 = slot16 + ((2 * kA1) >> 4);
               const uint32_t w_lo = phase == 1 ? w4_lo : wo_lo;
-              const uint32_t dd = d + (phase == 1 ? 64u : 96u);
+              const uint32_t dd = d + (phase == 1 ? 0u : 32u);
               ptx::tc_mma_f16_lohi(dd, ones_lo, kUmmaDescHi, phase == 1 ? b4_lo : bo_lo, kUmmaDescHi, idesc32, 0u);
               if (phase == 2) {
 #pragma unroll
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
     uint8_t* a2 = slot + 2 * kA1;
     uint8_t* a3 = a2;                                            // s_full (MMA2 complete) precedes the first write of the gated map
     uint8_t* stage = stage_all + (size_t)warp * 1024;
-    const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(g * 128);
+    const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(g * 64);
     const T* xin = static_cast<const T*>(p.x_in);
     T* out = static_cast<T*>(p.out);
     uint32_t par = 0;
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
 #pragma unroll
       for (int c0 = 0; c0 < 32; c0 += 16) {
         float v[16], ga[16];
-        ptx::tc_ld16(taddr + 64 + c0, v);
+        ptx::tc_ld16(taddr + c0, v);
         const T* xe = reinterpret_cast<const T*>(xraw) + c0;
 #pragma unroll
         for (int c = 0; c < 16; c += 4) {
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
 #pragma unroll
       for (int c0 = 0; c0 < 32; c0 += 16) {
         float v[16];
-        ptx::tc_ld16(taddr + 96 + c0, v);
+        ptx::tc_ld16(taddr + 32 + c0, v);
         if (c0 == 16) {                                                   // accumulators are in registers: free the slot
           ptx::tc_fence_before();
           __syncwarp();

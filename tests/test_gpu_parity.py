@@ -83,6 +83,28 @@ def test_fp32_intermediates_match_reference_hooks(models):
     assert np.abs(got - (t["ae.c0"] + t["ae.dec1"])).max() <= FP32_TOL
 
 
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_half_mode_intermediates_match_reference_hooks(prec, models):
+    """16-bit modes: the AutoEncoder runs as dense tensor-core convolutions on the half / quarter grid and keeps its full-resolution
+    tensors in PixelUnshuffle layout; the taps undo that layout, so every stage must still match the reference's forward hooks.
+    AutoEncoder stages use fp16 operands in both modes (tight bound); the trunk is bounded relative to each tensor's scale."""
+    t = np.load(os.path.join(GOLDEN, "taps_u_b1_16x32.npz"))
+    m = models[prec]
+    x = torch.from_numpy(t["x"]).to(DEV)
+    m(x)
+    trunk_tol = 2.5e-2 if prec == "bf16" else 6e-3
+    for name, ch, div, tol in (("ae.c0", 12, 1, 2e-3), ("ae.enc0", 48, 2, 2e-3), ("ae.enc1", 48, 4, 2e-3), ("ae.dec0", 12, 2, 2e-3),
+                               ("ae.out", 3, 1, 3e-3), ("rdn.sfe1", 32, 1, 8e-3), ("rdn.sfe2", 32, 1, trunk_tol),
+                               ("rdn.block0", 32, 1, trunk_tol), ("rdn.block1", 32, 1, trunk_tol), ("rdn.block2", 32, 1, trunk_tol),
+                               ("rdn.block3", 32, 1, trunk_tol), ("csar3.x_in", 32, 1, trunk_tol), ("rdn.out", 32, 1, trunk_tol)):
+        got = m.read_tap(name, x.shape, ch, div).cpu().numpy()
+        ref = t[name]
+        assert got.shape == ref.shape, name
+        assert np.abs(got - ref).max() <= tol * max(1.0, float(np.abs(ref).max())), (name, float(np.abs(got - ref).max()))
+    got = m.read_tap("ae.sum", x.shape, 12, 1).cpu().numpy()
+    assert np.abs(got - (t["ae.c0"] + t["ae.dec1"])).max() <= 3e-3
+
+
 @pytest.mark.parametrize("shape", [(2, 3, 8, 12), (1, 12, 64, 192), (3, 48, 32, 96), (1, 1, 2, 2)])
 def test_pixel_unshuffle_bit_exact(shape):
     x = torch.randn(*shape, generator=torch.Generator().manual_seed(1)).to(DEV)
