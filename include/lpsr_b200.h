@@ -124,6 +124,9 @@ int lpsr_forward_launch_count(const lpsr_handle* h, int32_t B, int32_t H, int32_
  * names follow tests/golden/taps_*.npz ("ae.c0", "ae.out", "rdn.sfe1", "rdn.block0", ...). */
 int lpsr_debug_read_tap(lpsr_handle* h, const char* name, float* dst_nchw_dev, int64_t dst_numel,
                         int32_t B, int32_t H, int32_t W, void* workspace, void* cuda_stream);
+/* profiling builds only (-DLPSR_UMMA_TRACE_BUILD, env LPSR_UMMA_TRACE=1): copies the 512 x 8 clock64 stamps the last traced
+ * tensor-core launch recorded for CTA 0 to host memory; LPSR_ERR_INVALID_ARG when tracing is not compiled in / enabled. */
+int lpsr_debug_umma_trace(long long* dst_host);
 const char* lpsr_last_error(const lpsr_handle* h);   /* h may be NULL: last global (create-time) error */
 int lpsr_abi_version(void);
 /* compute capability major*10+minor of the handle's device, 0 on error */

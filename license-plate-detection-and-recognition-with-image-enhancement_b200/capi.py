@@ -17,7 +17,7 @@ PREC = {"fp32": 0, "bf16": 1, "fp16": 2}
 EXPORTS = [
     "lpsr_create", "lpsr_destroy", "lpsr_load_weights", "lpsr_num_live_tensors", "lpsr_live_tensor_name",
     "lpsr_live_tensor_numel", "lpsr_output_shape", "lpsr_workspace_bytes", "lpsr_forward", "lpsr_forward_profiled", "lpsr_forward_host",
-    "lpsr_forward_launch_count", "lpsr_debug_read_tap", "lpsr_last_error", "lpsr_abi_version", "lpsr_device_sm",
+    "lpsr_forward_launch_count", "lpsr_debug_read_tap", "lpsr_debug_umma_trace", "lpsr_last_error", "lpsr_abi_version", "lpsr_device_sm",
     "lpsr_op_pixel_unshuffle2", "lpsr_op_pixel_shuffle2", "lpsr_op_conv2d",
 ]
 
