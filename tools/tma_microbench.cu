@@ -69,6 +69,12 @@ int main() {
       {"4D halo box 64B rows  [10][98][32ch] pitch288", 288, 32, 4, 98, 10, 1},
       {"4D halo box 128B rows [10][98][64ch] pitch288", 288, 64, 4, 98, 10, 1},
       {"4D halo box 32B rows  [10][98][16ch] pitch288", 288, 16, 4, 98, 10, 1},
+      {"4D halo box 32B rows  [10][98][16ch] pitch16 (dense)", 16, 16, 4, 98, 10, 1},
+      {"4D halo box 32B rows  [10][98][16ch] pitch32", 32, 16, 4, 98, 10, 1},
+      {"4D halo box 32B rows  [10][98][16ch] pitch48", 48, 16, 4, 98, 10, 1},
+      {"4D halo box 64B rows  [10][98][32ch] pitch48", 48, 32, 4, 98, 10, 1},
+      {"4D halo box 128B rows [10][98][64ch] pitch64 (dense)", 64, 64, 4, 98, 10, 1},
+      {"4D halo box 64B rows  [10][98][32ch] pitch64", 64, 32, 4, 98, 10, 1},
       {"4D halo 64B rows split in 5 boxes of 2+2 rows", 32, 32, 4, 98, 4, 5},
       {"2D box 64B rows  [128px][32ch] pitch32 (contig)", 32, 32, 2, 128, 1, 1},
       {"2D box 64B rows  [128px][32ch] pitch32  x4", 32, 32, 2, 128, 1, 4},
