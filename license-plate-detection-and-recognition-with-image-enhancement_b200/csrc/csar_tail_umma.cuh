@@ -17,7 +17,7 @@
 
 namespace lpsr {
 
-constexpr int kTailGroups = 5;   // tile slots in flight (4 x 128 TMEM columns); one tile's three-phase chain is latency bound
+constexpr int kTailGroups = 6;   // tile slots in flight (4 x 128 TMEM columns); one tile's three-phase chain is latency bound
 constexpr int kTailThreads = (4 * kTailGroups + 2) * 32;
 
 struct TailUmmaParams {
@@ -61,7 +61,6 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
   const uint32_t bar0 = ptx::smem_u32(bars);
   auto bar = [&](int slot, int which) { return bar0 + 8u * (uint32_t)(slot * 7 + which); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7 * G);
-  uint8_t* stage_all = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(bars + 7 * G + 2) + 15) & ~(uintptr_t)15);   // 1 KB per epilogue warp
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (uint32_t i = threadIdx.x; i < kW3 / 16; i += kTailThreads) reinterpret_cast<uint4*>(w3_s)[i] = __ldg(reinterpret_cast<const uint4*>(p.w3) + i);
@@ -189,7 +188,6 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
     uint8_t* slot = slots + (size_t)g * kSlot;
     uint8_t* a2 = slot + 2 * kA1;
     uint8_t* a3 = a2;                                            // s_full (MMA2 complete) precedes the first write of the gated map
-    uint8_t* stage = stage_all + (size_t)warp * 1024;
     const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(g * 64);
     const T* xin = static_cast<const T*>(p.x_in);
     T* out = static_cast<T*>(p.out);
@@ -277,7 +275,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(bar(g, 6));
         }
-        store_chunk16_coalesced<T>(out, p.out_pitch, p.out_off + c0, pix32, v, stage, lane);
+        store_chunk16<T>(out, p.out_pitch, p.out_off + c0, pix32, v);
       }
     }
   }
@@ -290,14 +288,14 @@ template <typename T>
 inline const char* csar_tail_umma_launch(const TailUmmaParams& pin, bool fp16, int num_sms, cudaStream_t st) {
   TailUmmaParams p = pin;
   if (p.total_px >= (1LL << 31)) return "batch too large for 32-bit pixel indices";
-  if (p.res_pitch % 8 || p.res_off % 8 || p.out_pitch % 8 || p.out_off % 8) return "pitch/offset not 16-byte aligned";
+  if (p.res_pitch % 8 || p.res_off % 8 || p.out_pitch % 16 || p.out_off % 16 || reinterpret_cast<uintptr_t>(p.out) % 32) return "pitch/offset not aligned";
   p.n_tiles = (int)((p.total_px + 127) / 128);
   TailTmap tm;
   if (const char* msg = umma_make_tmap(&tm.m, p.x_in, fp16, 32, 32, false, 0, 0, 0, 128, 0, p.total_px)) return msg;
   if (const char* msg = umma_make_tmap(&tm.r, p.res, fp16, p.res_pitch, 32, false, 0, 0, 0, 128, 0, p.total_px)) return msg;
   constexpr size_t kSlot = 2 * 128 * 64 + 128 * 128;
   const size_t smem = 1024 + kTailGroups * kSlot + 32 * 64 * 2 + 2 * 64 * 32 * 2 + (2 * 128 + 2 * 64 + 2 * 32 + 2 * 32 + 4 * 32) * 16 +
-                      (7 * kTailGroups + 2) * 8 + 4 * kTailGroups * 1024 + 64;
+                      (7 * kTailGroups + 2) * 8 + 64;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(csar_tail_umma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -307,22 +307,18 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   }
 }
 
+// Store of one 16-channel chunk (32 bytes) per accumulator row: ONE 256-bit store per thread (STG.E.ENL2.256, sm_100).  Thread = row
+// and consecutive rows are consecutive pixels, so a warp writes 32 full 32-byte sectors (1 KB contiguous for a 16-channel tensor)
+// without the shared-memory staging round trip (two warp syncs, 4 smem ops, 2 shuffles) the 128-bit version needed.
+// pix < 0: the row has no pixel.  Requires pitch % 16 == 0, off % 16 == 0 and a 32-byte aligned tensor.
 template <typename T, bool RELU = false>
-__device__ __forceinline__ void store_chunk16_coalesced(T* __restrict__ out, int pitch, int off, int pix, const float (&v)[16],
-                                                        uint8_t* __restrict__ stage /*1 KB per warp*/, int lane) {
-  const uint4 lo = make_uint4(pack2<T, RELU>(v[0], v[1]), pack2<T, RELU>(v[2], v[3]), pack2<T, RELU>(v[4], v[5]), pack2<T, RELU>(v[6], v[7]));
-  const uint4 hi = make_uint4(pack2<T, RELU>(v[8], v[9]), pack2<T, RELU>(v[10], v[11]), pack2<T, RELU>(v[12], v[13]), pack2<T, RELU>(v[14], v[15]));
-  __syncwarp();                                                  // previous use of the staging rows is finished
-  *reinterpret_cast<uint4*>(stage + lane * 32) = lo;
-  *reinterpret_cast<uint4*>(stage + lane * 32 + 16) = hi;
-  __syncwarp();
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const int r = 16 * j + (lane >> 1);
-    const int rp = __shfl_sync(0xffffffffu, pix, r);
-    const uint4 d = *reinterpret_cast<const uint4*>(stage + j * 512 + lane * 16);
-    if (rp >= 0) *reinterpret_cast<uint4*>(out + (size_t)rp * pitch + off + (lane & 1) * 8) = d;
-  }
+__device__ __forceinline__ void store_chunk16(T* __restrict__ out, int pitch, int off, int pix, const float (&v)[16]) {
+  if (pix < 0) return;
+  T* dst = out + (size_t)pix * pitch + off;
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(pack2<T, RELU>(v[0], v[1])), "r"(pack2<T, RELU>(v[2], v[3])),
+               "r"(pack2<T, RELU>(v[4], v[5])), "r"(pack2<T, RELU>(v[6], v[7])), "r"(pack2<T, RELU>(v[8], v[9])),
+               "r"(pack2<T, RELU>(v[10], v[11])), "r"(pack2<T, RELU>(v[12], v[13])), "r"(pack2<T, RELU>(v[14], v[15]))
+               : "memory");
 }
 
 // MODE: kConv1x1 | kConv3x3Taps (one MMA per tap, N = Cout: used for Cout >= 32 where the MMA is already efficient)
@@ -384,9 +380,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
   // per-K-slice MMA operand table {A offset in 16-B units inside the item buffer, row bytes/16, descriptor hi word, dy shift/16}
   uint4* steps = reinterpret_cast<uint4*>(xchg + XCH);
   int* slot_base_s = reinterpret_cast<int*>(steps + kUmmaMaxSteps);   // [R] written by the producer, read by the MMA warp
-  uint8_t* stage_all = reinterpret_cast<uint8_t*>(slot_base_s + 8);  // 1 KB of store staging per epilogue warp
   // fused layer: per group a 4 KB K=16 operand, two planes of [128 rows][8 ch] (no-swizzle K-major: row stride 16 B, LBO = 2048 B)
-  uint8_t* a2_all = stage_all + (size_t)4 * G * 1024;
+  uint8_t* a2_all = reinterpret_cast<uint8_t*>(slot_base_s + 8);
 
   // ---- one-time setup ------------------------------------------------------------------------------
   {
@@ -566,7 +561,6 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
     T* out = static_cast<T*>(p.out);
     const T* res = static_cast<const T*>(p.res);
     float* xg = xchg + (size_t)grp * (2 * 4 * 2 * NOUT);
-    uint8_t* stage = stage_all + (size_t)warp * 1024;
     const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(grp * NMMA);
     // everything the per-tile path needs lives in registers
     const int pitch = p.pitch, tstride = p.tstride, k_tiles = p.k, Himg = p.H, Wimg = p.W, halo = p.halo, TWs = p.TW;
@@ -768,7 +762,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
                   o[c + 2] += b4.z + to_f32<T>(re[c + 2]); o[c + 3] += b4.w + to_f32<T>(re[c + 3]);
                 }
               }
-              store_chunk16_coalesced<T>(out, out_pitch, out_off + hh * CH, pix32, o, stage, lane);
+              store_chunk16<T>(out, out_pitch, out_off + hh * CH, pix32, o);
             }
           } else if constexpr (EPI == kEpiFinalSigmoid) {
             // final conv (Cout = 1, padded to 16): channel 0 only, fp32; lanes are consecutive pixels -> coalesced 4-byte stores
@@ -796,11 +790,11 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
 #pragma unroll
               for (int c = 0; c < CH; ++c) v[c] = fmaxf(v[c], 0.f) + to_f32<T>(re[c]);
             }
-            store_chunk16_coalesced<T>(out, out_pitch, out_off + cc % 48, up, v, stage, lane);
+            store_chunk16<T>(out, out_pitch, out_off + cc % 48, up, v);
           } else if constexpr (EPI == kEpiUp2Store) {
             static_assert(EPI != kEpiUp2Store || NOUT == 128, "four 32-channel pixels per row");
             const int up = valid ? ((nn * 2 * Himg + 2 * yy + cc / 64) * 2 * Wimg + 2 * xx + (cc / 32) % 2) : -1;
-            store_chunk16_coalesced<TOUT>(reinterpret_cast<TOUT*>(out), out_pitch, out_off + cc % 32, up, v, stage, lane);
+            store_chunk16<TOUT>(reinterpret_cast<TOUT*>(out), out_pitch, out_off + cc % 32, up, v);
           } else if constexpr (EPI == kEpiGate) {
             // CSAR gates (1x1, NOUT = 32): spatial branch x_in * sigmoid(.), channel branch x_in^2 * s_c
             float g1[CH];
@@ -820,8 +814,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
                 }
               }
             }
-            store_chunk16_coalesced<T>(out, out_pitch, out_off + cc, pix32, g1, stage, lane);
-            store_chunk16_coalesced<T>(out, out_pitch, p.out_off2 + cc, pix32, v, stage, lane);
+            store_chunk16<T>(out, out_pitch, out_off + cc, pix32, g1);
+            store_chunk16<T>(out, out_pitch, p.out_off2 + cc, pix32, v);
           } else {
 
             if constexpr (EPI == kEpiResidual) {
@@ -846,7 +840,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
               if (!(lane & 1)) p.pool[((size_t)(item * k_tiles + m) * 4 + wq) * NOUT + cc + ((lane >> 1) & 15)] = tot;
             }
             // all 32 lanes take part in the staged, coalesced store (rows without a pixel are skipped inside)
-            if (!LPSR_DBG(32)) store_chunk16_coalesced<T, EPI == kEpiRelu>(out, out_pitch, out_off + cc, pix32, v, stage, lane);
+            if (!LPSR_DBG(32)) store_chunk16<T, EPI == kEpiRelu>(out, out_pitch, out_off + cc, pix32, v);
             else if (v[0] == 123.456f) out[0] = from_f32<T>(v[1] + v[5] + v[9] + v[13]);
           }
         }
@@ -930,7 +924,8 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
   p.n_ks = w.cin / 16;                                       // 7x7: 28 pixel-pair steps (UmmaWeights::cin = 448 pseudo channels)
   if (p.n_ks > kUmmaMaxSteps) return "too many K-steps";
   if (!c7 && cp.n_chunks != p.n_ks) return "chunk table does not match Cin/16";
-  if (!fp32_out && (cp.out_pitch % 8 || cp.out_off % 8 || (cp.res && (cp.res_pitch % 8 || cp.res_off % 8)))) return "pitch/offset not 16-byte aligned";
+  if (!fp32_out && (cp.out_pitch % 16 || cp.out_off % 16 || reinterpret_cast<uintptr_t>(cp.out) % 32)) return "output pitch/offset not 32-byte aligned (256-bit stores)";
+  if (cp.res && (cp.res_pitch % 8 || cp.res_off % 8)) return "residual pitch/offset not 16-byte aligned";
   if (kEpiGroups * NMMA > 512) return "N too large for the TMEM accumulators";
   // ---- K-chunks: merge runs of 16-channel slices that are contiguous in the SAME tensor into TMA boxes of 64 / 32 / 16 ch
   const void* chunk_base[kUmmaMaxKChunks];
@@ -989,7 +984,7 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
   }
   const size_t w_bytes = ((size_t)ntap * w.cin * NMMA * 2 + (lff ? 2 * kLffN * 16 : 0) + 127) & ~(size_t)127;
   const size_t a2_bytes = lff ? (size_t)kEpiGroups * 4096 : 0;
-  const size_t fixed = w_bytes + (2 * kUmmaMaxBufs + 4 * kEpiGroups + 2) * 8 + xch_bytes + a2_bytes + 640 /*steps, slot_base*/ + 4 * kEpiGroups * 1024 /*store staging*/ + 1024 /*alignment slack*/ + 256;
+  const size_t fixed = w_bytes + (2 * kUmmaMaxBufs + 4 * kEpiGroups + 2) * 8 + xch_bytes + a2_bytes + 640 /*steps, slot_base*/ + 1024 /*alignment slack*/ + 256;
   const size_t smem_cap = 227 * 1024 - fixed;
   auto item_buf_bytes = [&](size_t npx) {                      // every chunk is 1024-aligned inside the buffer
     size_t b = 0;
@@ -1064,7 +1059,7 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
   if (bufs < 2) return "tile does not fit in shared memory";
   if (bufs > kUmmaMaxBufs) bufs = kUmmaMaxBufs;
   p.n_bufs = bufs;
-  plan.smem_bytes = (size_t)bufs * off + w_bytes + (2 * bufs + 4 * kEpiGroups + 2) * 8 + xch_bytes + a2_bytes + 640 + 4 * kEpiGroups * 1024 + 1024 + 64;
+  plan.smem_bytes = (size_t)bufs * off + w_bytes + (2 * bufs + 4 * kEpiGroups + 2) * 8 + xch_bytes + a2_bytes + 640 + 1024 + 64;
   plan.grid = std::min(p.n_items, num_sms);
   // ---- tensor maps, one per K-chunk
   for (int c = 0; c < p.n_chunks; ++c)
