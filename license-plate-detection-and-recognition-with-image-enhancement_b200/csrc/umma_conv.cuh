@@ -656,6 +656,18 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
         my_par ^= 1u;
         const bool valid = pix >= 0 && !skip_store;
         const int pix32 = valid ? pix : -1;
+        // narrow accumulators: all TMEM loads in flight at once, one wait, and the accumulator goes back to the MMA warp before any math
+        constexpr bool PRELOAD = !FOLD && NOUT <= 64;
+        [[maybe_unused]] float vall[PRELOAD ? NOUT : 1];
+        if constexpr (PRELOAD) {
+#pragma unroll
+          for (int cc = 0; cc < NOUT; cc += CH) ptx::tc_ld16_nowait(taddr + cc, vall + cc);
+          ptx::tc_wait_ld();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(tempty_bar(grp));
+          LPSR_TRACE(wq == 0 && lane == 0, ii * k_tiles + m, 5, clock64());
+        }
 #pragma unroll
         for (int cc = 0; cc < NOUT; cc += CH) {
           float v[CH];
@@ -705,6 +717,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
             }
 #pragma unroll
             for (int c = 0; c < CH; ++c) v[c] += lf[c] + rg[c];
+          } else if constexpr (PRELOAD) {
+#pragma unroll
+            for (int c = 0; c < CH; ++c) v[c] = vall[cc + c];
           } else {
             ptx::tc_ld16_nowait(taddr + cc, v);
             ptx::tc_wait_ld();
