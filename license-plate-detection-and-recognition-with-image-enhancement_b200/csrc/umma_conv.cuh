@@ -382,12 +382,35 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
   int* slot_base_s = reinterpret_cast<int*>(steps + kUmmaMaxSteps);   // [R] written by the producer, read by the MMA warp
   // fused layer: per group a 4 KB K=16 operand, two planes of [128 rows][8 ch] (no-swizzle K-major: row stride 16 B, LBO = 2048 B)
   uint8_t* a2_all = reinterpret_cast<uint8_t*>(slot_base_s + 8);
+  // fused layer: the additions of its two epilogue passes run on the tensor core (its pipe has slack, the epilogue warps do not): a
+  // "ones" operand times {hi(bias), lo(bias)} starts the accumulator at the biases (b3 in the dx = 1 block, lff's in columns 48..79),
+  // and x (chunk 0 of the staged block, centre tap) times a 32x32 identity adds the residual exactly.
+  uint8_t* ones_s = a2_all + (size_t)G * 4096;                 // [2 planes][128 rows][8]: k = 0, 1 are 1.0
+  uint8_t* lffb_s = ones_s + 2 * 128 * 16;                     // [2][80][8]
+  uint8_t* lffid_s = lffb_s + 2 * kLffCols * 16;               // [4][32][8]
 
   // ---- one-time setup ------------------------------------------------------------------------------
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.w);
     uint4* dst = reinterpret_cast<uint4*>(w_smem);
     for (uint32_t i = threadIdx.x; i < w_bytes / 16; i += kUmmaThreads) dst[i] = __ldg(src + i);
+  }
+  if constexpr (LFF) {
+    T* ones = reinterpret_cast<T*>(ones_s);
+    for (uint32_t i = threadIdx.x; i < 2 * 128 * 8; i += kUmmaThreads) ones[i] = from_f32<T>((i < 128 * 8 && (i & 7) < 2) ? 1.f : 0.f);
+    T* bb = reinterpret_cast<T*>(lffb_s);
+    for (uint32_t i = threadIdx.x; i < 2 * kLffCols * 8; i += kUmmaThreads) {
+      const uint32_t k = i & 7, col = (i >> 3) % kLffCols, plane = (i >> 3) / kLffCols;
+      float v = 0.f;
+      if (plane == 0 && k < 2 && ((col >= 16 && col < 32) || col >= 48)) {
+        const float bv = __ldg(p.bias + (col < 32 ? col - 16 : col - 32));   // bias = [b3 (16) | lff bias (32)]
+        const float hi = to_f32<T>(from_f32<T>(bv));
+        v = k == 0 ? hi : bv - hi;
+      }
+      bb[i] = from_f32<T>(v);
+    }
+    T* idm = reinterpret_cast<T*>(lffid_s);
+    for (uint32_t i = threadIdx.x; i < 4 * 32 * 8; i += kUmmaThreads) idm[i] = from_f32<T>(((i >> 8) * 8 + (i & 7)) == ((i >> 3) & 31) ? 1.f : 0.f);
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < R; ++s) {
@@ -478,6 +501,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
     constexpr uint32_t idesc48 = umma_idesc_f16(IsBf16<T>::value, 48), idesc32 = umma_idesc_f16(IsBf16<T>::value, kLffN);
     const uint32_t w2_lo = umma_desc_lo(ptx::smem_u32(w_smem) + w_main_bytes, (uint32_t)kLffN * 16);
     const uint32_t a2_lo = umma_desc_lo(ptx::smem_u32(a2_all) + (uint32_t)mg * 4096u, 2048u);
+    const uint32_t ones_lo = umma_desc_lo(ptx::smem_u32(ones_s), 2048u), lffb_lo = umma_desc_lo(ptx::smem_u32(lffb_s), (uint32_t)kLffCols * 16),
+                   lffid_lo = umma_desc_lo(ptx::smem_u32(lffid_s), 32u * 16);
     uint32_t a2_par = 0;
     const uint32_t w_lo = umma_desc_lo(ptx::smem_u32(w_smem), (uint32_t)NMMA * 16);
     const uint32_t cgn = (uint32_t)(CG * NMMA);               // weights: 16-byte units between taps
@@ -511,17 +536,22 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
           const uint32_t d = tmem_base + acc * NMMA;
           uint32_t b_lo = w_lo;
           if (!no_mma) {
+            if constexpr (LFF) ptx::tc_mma_f16_lohi(d, ones_lo, kUmmaDescHi, lffb_lo, kUmmaDescHi, idesc, 0u);   // accumulator := biases
 #pragma unroll 1
             for (int ks = 0; ks < n_ks; ++ks) {
               const uint4 e = steps[ks];
               const uint32_t a0 = (buf16 + e.x + slot * e.y) | (1u << 16);
+              if constexpr (LFF) {
+                if (ks < 2)   // + x: channels 16 ks .. 16 ks + 15 of the block input (centre tap) times the identity -> lff columns
+                  ptx::tc_mma_f16_lohi(d + 48, a0 + e.w, e.z, lffid_lo + (uint32_t)(ks * 2 * 32), kUmmaDescHi, idesc32, 1u);
+              }
 #pragma unroll
               for (int t = 0; t < NTAP; ++t) {
                 // tap -> start shift in 16-byte units: folded: dy rows (dx lives in N); per-tap: dy rows + dx pixels
                 if constexpr (LFF) {
                   // dy = 1 goes first: its 80-column MMA (48 folded + 32 lff) initialises the whole accumulator
                   const uint32_t dyv = t == 0 ? 1u : (t == 1 ? 0u : 2u);
-                  ptx::tc_mma_f16_lohi(d, a0 + dyv * e.w, e.z, b_lo + dyv * cgn, kUmmaDescHi, t == 0 ? idesc : idesc48, (uint32_t)(ks | t));
+                  ptx::tc_mma_f16_lohi(d, a0 + dyv * e.w, e.z, b_lo + dyv * cgn, kUmmaDescHi, t == 0 ? idesc : idesc48, 1u);
                 } else {
                   const uint32_t shift = FOLD ? (uint32_t)t * e.w : (uint32_t)(t / KSZ) * e.w + (uint32_t)(t % KSZ) * e.y;
                   ptx::tc_mma_f16_lohi(d, a0 + shift, e.z, b_lo + (uint32_t)t * cgn, kUmmaDescHi, idesc, (uint32_t)(ks | t));
@@ -626,7 +656,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
         }
         // operands that do not depend on the accumulator are requested before waiting for it
         uint4 rsd_raw[NRES];                                    // raw 16-bit residual: converted only after the accumulator arrived
-        if constexpr (EPI == kEpiResidual && NOUT <= 32) {
+        if constexpr (EPI == kEpiResidual && NOUT <= 32 && !LFF) {
           if (pix >= 0) {
 #pragma unroll
             for (int i = 0; i < NRES; ++i) rsd_raw[i] = *reinterpret_cast<const uint4*>(res + (size_t)pix * res_pitch + res_off + i * 8);
@@ -730,7 +760,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
               LPSR_TRACE(wq == 0 && lane == 0, ii * k_tiles + m, 5, clock64());
             }
           }
-          if constexpr (NOUT <= 32) {
+          if constexpr (LFF) {
+            // biases and the residual were accumulated by the tensor core
+          } else if constexpr (NOUT <= 32) {
 #pragma unroll
             for (int c = 0; c < CH; ++c) v[c] += bias_r[cc + c];
           } else {
@@ -743,41 +775,31 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
           if constexpr (LFF) {
             // ---- stage 1: g3 = relu(conv + bias) becomes the K = 16 operand of lff's last slice (planes of 8 channels, row = 16 B)
             {
-              uint4 lo, hi;
-              T* e0 = reinterpret_cast<T*>(&lo);
-              T* e1 = reinterpret_cast<T*>(&hi);
-#pragma unroll
-              for (int c = 0; c < 8; ++c) { e0[c] = from_f32<T>(fmaxf(v[c], 0.f)); e1[c] = from_f32<T>(fmaxf(v[8 + c], 0.f)); }
               uint8_t* a2 = a2_all + (size_t)grp * 4096;
-              *reinterpret_cast<uint4*>(a2 + row * 16) = lo;
-              *reinterpret_cast<uint4*>(a2 + 2048 + row * 16) = hi;
+              *reinterpret_cast<uint4*>(a2 + row * 16) =
+                  make_uint4(pack2<T, true>(v[0], v[1]), pack2<T, true>(v[2], v[3]), pack2<T, true>(v[4], v[5]), pack2<T, true>(v[6], v[7]));
+              *reinterpret_cast<uint4*>(a2 + 2048 + row * 16) =
+                  make_uint4(pack2<T, true>(v[8], v[9]), pack2<T, true>(v[10], v[11]), pack2<T, true>(v[12], v[13]), pack2<T, true>(v[14], v[15]));
             }
             ptx::fence_proxy_async();                           // generic-proxy stores -> visible to the tensor core
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(a2full_bar(grp));
-            // ---- stage 2: columns 48..79 = lff(cat[x, g0..g3]); + bias + x -> block output
+            // ---- stage 2: columns 48..79 = x + lff(cat[x, g0..g3]) + bias -> block output
             ptx::mbar_wait(tfull2_bar(grp), tile_par);
             ptx::tc_fence_after();
+            float o[kLffN];
+#pragma unroll
+            for (int hh = 0; hh < kLffN / CH; ++hh) ptx::tc_ld16_nowait(taddr + 48 + hh * CH, o + hh * CH);
+            ptx::tc_wait_ld();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty_bar(grp));
 #pragma unroll
             for (int hh = 0; hh < kLffN / CH; ++hh) {
-              float o[CH];
-              ptx::tc_ld16_nowait(taddr + 48 + hh * CH, o);
-              ptx::tc_wait_ld();
-              if (hh == kLffN / CH - 1) {
-                ptx::tc_fence_before();
-                __syncwarp();
-              if (lane == 0) ptx::mbar_arrive(tempty_bar(grp));
-              }
-              if (valid) {
-                const T* re = reinterpret_cast<const T*>(rsd_raw) + hh * CH;
+              float oc[CH];
 #pragma unroll
-                for (int c = 0; c < CH; c += 4) {
-                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + NOUT + hh * CH + c));
-                  o[c] += b4.x + to_f32<T>(re[c]); o[c + 1] += b4.y + to_f32<T>(re[c + 1]);
-                  o[c + 2] += b4.z + to_f32<T>(re[c + 2]); o[c + 3] += b4.w + to_f32<T>(re[c + 3]);
-                }
-              }
-              store_chunk16<T>(out, out_pitch, out_off + hh * CH, pix32, o);
+              for (int c = 0; c < CH; ++c) oc[c] = o[hh * CH + c];
+              store_chunk16<T>(out, out_pitch, out_off + hh * CH, pix32, oc);
             }
           } else if constexpr (EPI == kEpiFinalSigmoid) {
             // final conv (Cout = 1, padded to 16): channel 0 only, fp32; lanes are consecutive pixels -> coalesced 4-byte stores
@@ -998,7 +1020,7 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
 #endif
   }
   const size_t w_bytes = ((size_t)ntap * w.cin * NMMA * 2 + (lff ? 2 * kLffN * 16 : 0) + 127) & ~(size_t)127;
-  const size_t a2_bytes = lff ? (size_t)kEpiGroups * 4096 : 0;
+  const size_t a2_bytes = lff ? (size_t)kEpiGroups * 4096 + 2 * 128 * 16 + 2 * kLffCols * 16 + 4 * 32 * 16 : 0;   // g3 operands, ones, biases, identity
   const size_t fixed = w_bytes + (2 * kUmmaMaxBufs + 4 * kEpiGroups + 2) * 8 + xch_bytes + a2_bytes + 640 /*steps, slot_base*/ + 1024 /*alignment slack*/ + 256;
   const size_t smem_cap = 227 * 1024 - fixed;
   auto item_buf_bytes = [&](size_t npx) {                      // every chunk is 1024-aligned inside the buffer
