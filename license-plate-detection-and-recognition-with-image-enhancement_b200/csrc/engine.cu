@@ -205,14 +205,16 @@ void s2d_weights(const DenseConv& d, int cin_cols, int cout_cols, InIdx in_index
       }
 }
 
-// dense conv at its own grid: [ks*ks][cin][cout_cols] (columns >= cout are zero)
-void plain_weights(const DenseConv& d, int cout_cols, std::vector<float>& pw, std::vector<float>& pb) {
-  pw.assign((size_t)d.ks * d.ks * d.cin * cout_cols, 0.f);
+// dense conv at its own grid: [ks*ks][cin_rows][cout_cols]; output channel co goes to column col_of(co), unused rows / columns are zero
+template <typename ColOf>
+void plain_weights(const DenseConv& d, int cin_rows, int cout_cols, ColOf col_of, std::vector<float>& pw, std::vector<float>& pb) {
+  pw.assign((size_t)d.ks * d.ks * cin_rows * cout_cols, 0.f);
   pb.assign(cout_cols, 0.f);
   for (int co = 0; co < d.cout; ++co) {
-    pb[co] = d.b.empty() ? 0.f : d.b[co];
+    const int n = col_of(co);
+    pb[n] = d.b.empty() ? 0.f : d.b[co];
     for (int ci = 0; ci < d.cin; ++ci)
-      for (int t = 0; t < d.ks * d.ks; ++t) pw[((size_t)t * d.cin + ci) * cout_cols + co] = d.w[((size_t)co * d.cin + ci) * d.ks * d.ks + t];
+      for (int t = 0; t < d.ks * d.ks; ++t) pw[((size_t)t * cin_rows + ci) * cout_cols + n] = d.w[((size_t)co * d.cin + ci) * d.ks * d.ks + t];
   }
 }
 
@@ -235,19 +237,18 @@ bool pack_ae_tensor_core(lpsr_handle* h) {
   ok &= umma_pack_weights(h->aet_enc0, pw.data(), pb.data(), 3, 48, 48, fp16, put16, put32);
   // encoder.3: DConv 48 -> 12 on the half grid (5x5 taps); PixelUnshuffle + ReLU in the store (lpsr.py:74-80)
   const DenseConv e1 = compose_dconv(h, "auto_encoder.encoder.3.dConv.", 48, 12, 5);
-  plain_weights(e1, 16, pw, pb);
+  plain_weights(e1, 48, 16, [](int co) { return co; }, pw, pb);
   ok &= umma_pack_weights(h->aet_enc1, pw.data(), pb.data(), 5, 48, 16, fp16, put16, put32);
-  // decoder.0: DConv 48 -> 48 on the quarter grid; its PixelShuffle is only a relabeling for the next stage (lpsr.py:83-89)
+  // decoder.0: DConv 48 -> 48 on the quarter grid + PixelShuffle + ReLU (lpsr.py:83-89): output channel c*4 + i*2 + j goes to column
+  // (i*2 + j)*16 + c, so the epilogue stores four 16-channel (12 real) half-grid pixels per quarter-grid pixel
   const DenseConv d0 = compose_dconv(h, "auto_encoder.decoder.0.dConv.", 48, 48, 5);
-  plain_weights(d0, 48, pw, pb);
-  ok &= umma_pack_weights(h->aet_dec0, pw.data(), pb.data(), 5, 48, 48, fp16, put16, put32);
-  // decoder.3: DConv 12 -> 48 on the half grid == 48 -> 4 x 48 on the quarter grid; one launch per output row parity I, columns
-  // J*48 + co are half-grid pixel (2h + I, 2w + J) whose 48 channels are PixelUnshuffle(full-resolution 12 channels) (lpsr.py:90-96)
+  plain_weights(d0, 48, 64, [](int co) { return (co & 3) * 16 + (co >> 2); }, pw, pb);
+  ok &= umma_pack_weights(h->aet_dec0, pw.data(), pb.data(), 5, 48, 64, fp16, put16, put32);
+  // decoder.3: DConv 12 -> 48 on the half grid (lpsr.py:90-96); its 48 outputs per half-grid pixel ARE PixelUnshuffle of the
+  // full-resolution 12 channels, the layout of c0 (residual, lpsr.py:115) and of conv_out's operand: plain ReLU + residual store
   const DenseConv d1 = compose_dconv(h, "auto_encoder.decoder.3.dConv.", 12, 48, 5);
-  for (int I0 = 0; I0 < 2; ++I0) {
-    s2d_weights(d1, 48, 96, unshuffle_idx, [I0](int co, int I, int J) { return I == I0 ? J * 48 + co : -1; }, pw, pb);
-    ok &= umma_pack_weights(h->aet_dec1[I0], pw.data(), pb.data(), 3, 48, 96, fp16, put16, put32);
-  }
+  plain_weights(d1, 16, 48, [](int co) { return co; }, pw, pb);
+  ok &= umma_pack_weights(h->aet_dec1, pw.data(), pb.data(), 5, 16, 48, fp16, put16, put32);
   // conv_out 12 -> 3 (3x3, no bias) on the half grid: the output stays PixelUnshuffle(ae_out), 12 real of 16 columns
   DenseConv co;
   co.cin = 12; co.cout = 3; co.ks = 3; co.w = W(h, "auto_encoder.conv_out.weight");
@@ -409,7 +410,7 @@ WsLayout ws_layout(const lpsr_handle* h, int B, int H, int W) {
   L.c0 = take(BP * 12, es);
   L.e0 = take(BP / 4 * 48, es);
   L.e1 = take(BP / 16 * 48, es);
-  L.d0 = take(BP / 4 * 12, es);
+  L.d0 = take(BP / 4 * 16, es);   // 12 channels on the half grid; the tensor-core path pads the pitch to 16
   L.s = take(BP * 16, es);   // c0 + decoder output: 12 channels, pitch 16 (zero padded) on the tensor-core path
   L.ae = take(BP * 16, es);  // AutoEncoder output: 3 channels (pitch 3), or padded to 16 channels on the tensor-core path
   L.sfe1 = take(BP * 32, es);
@@ -721,7 +722,7 @@ int lpsr_debug_read_tap(lpsr_handle* h, const char* name, float* dst, int64_t ds
   const bool tc = h->ae_tc;    // tensor-core AutoEncoder: full-resolution tensors are stored as their PixelUnshuffle on the half grid
   const Tap taps[] = {
       {"ae.c0", L.c0, tc ? 48 : 12, 0, 12, 1, tc, tc},  {"ae.enc0", L.e0, 48, 0, 48, 2, 0, tc},   {"ae.enc1", L.e1, 48, 0, 48, 4, 0, tc},
-      {"ae.dec0", L.d0, tc ? 48 : 12, 0, 12, 2, tc, tc}, {"ae.sum", L.s, tc ? 48 : (h->sfe1_u.packed ? 16 : 12), 0, 12, 1, tc, tc},
+      {"ae.dec0", L.d0, tc ? 16 : 12, 0, 12, 2, 0, tc}, {"ae.sum", L.s, tc ? 48 : (h->sfe1_u.packed ? 16 : 12), 0, 12, 1, tc, tc},
       {"ae.out", L.ae, tc ? 16 : (h->sfe1_u.packed ? 16 : 3), 0, 3, 1, tc, tc},
       {"rdn.sfe1", L.sfe1, 32, 0, 32, 1, 0}, {"rdn.sfe2", L.x0, 32, 0, 32, 1, 0},
       {"rdn.block0", L.f[0], 32, 0, 32, 1, 0}, {"rdn.block1", L.f[1], 32, 0, 32, 1, 0},

@@ -58,7 +58,7 @@ struct lpsr_handle {
   // (un)shuffles are channel relabelings of space-to-depth operands (DESIGN.md "AutoEncoder on tensor cores")
   lpsr::UmmaWeights rdb_fused[2];   // last dense layer + lff + residual of each RDB as one tensor-core launch (16-bit modes)
   bool ae_tc = false;
-  lpsr::UmmaWeights aet_in, aet_enc0, aet_enc1, aet_dec0, aet_dec1[2], aet_out, aet_sfe1;
+  lpsr::UmmaWeights aet_in, aet_enc0, aet_enc1, aet_dec0, aet_dec1, aet_out, aet_sfe1;
   lpsr::DConvW dc[4];
   float *ca_w1 = nullptr, *ca_b1 = nullptr, *ca_w2 = nullptr, *ca_b2 = nullptr;
   float *sa_w1 = nullptr, *sa_b1 = nullptr, *sa_w2 = nullptr, *sa_b2 = nullptr, *co_w = nullptr, *co_b = nullptr;

@@ -259,9 +259,9 @@ void rdb_block(Ctx& c, const WsLayout& L, char* ws, int B, int r, size_t x_t, si
 //   c0u [H/2][W/2][48]  = unshuffle(conv_in(x))                    3x3 taps on the half grid, K=16, N=48     (lpsr.py:67-69)
 //   e0  [H/2][W/2][48]  = relu(unshuffle(DConv(c0)))               3x3 taps on the half grid, K=48, N=48     (lpsr.py:71-73)
 //   e1  [H/4][W/4][48]  = relu(unshuffle(DConv(e0)))               5x5 taps on the half grid, N=12, unshuffling store (74-80)
-//   d0q [H/4][W/4][48]  = relu(DConv(e1)), shuffle pending         5x5 taps on the quarter grid, N=48        (lpsr.py:83-89)
-//   s   [H/2][W/2][48]  = c0u + relu(unshuffle(shuffle(DConv(shuffle(d0q)))))   3x3 taps on the quarter grid, two launches of
-//                         N=96 (row parity I), each storing half-grid pixels (2h+I, 2w+{0,1})               (lpsr.py:90-96,115)
+//   d0  [H/2][W/2][16]  = relu(shuffle(DConv(e1))) (12 real ch)    5x5 taps on the quarter grid, N=4x16, 2x up-store (83-89)
+//   s   [H/2][W/2][48]  = c0u + relu(unshuffle(shuffle(DConv(d0))))  5x5 taps on the half grid, K=16, N=48: the 48 outputs per
+//                         half-grid pixel are already PixelUnshuffle(full-resolution 12 ch)                  (lpsr.py:90-96,115)
 //   aeu [H/2][W/2][16]  = unshuffle(conv_out(c0 + d))              folded 3x3 on the half grid, N=12 of 16   (lpsr.py:102-104,116)
 //   sfe1 [H][W][32]     = shallowF1(ae_out) (7x7)                  5x5 taps on the half grid, K=16, N=4x32, 2x up-store (195-197)
 // Operands and intermediate tensors of the AutoEncoder are fp16 in BOTH 16-bit modes (its activations are O(1), and the extra three
@@ -274,15 +274,16 @@ void ae_forward_tc(Ctx& c, const WsLayout& L, char* ws, const float* x, int B, i
   TA* c0u = reinterpret_cast<TA*>(ws + L.c0);
   TA* e0 = reinterpret_cast<TA*>(ws + L.e0);
   TA* e1 = reinterpret_cast<TA*>(ws + L.e1);
-  TA* d0q = reinterpret_cast<TA*>(ws + L.d0);
+  TA* d0 = reinterpret_cast<TA*>(ws + L.d0);
   TA* s = reinterpret_cast<TA*>(ws + L.s);
   TA* aeu = reinterpret_cast<TA*>(ws + L.ae);                  // PixelUnshuffle(AutoEncoder output): 12 real of 16 channels
   TA* sfe1 = reinterpret_cast<TA*>(ws + L.sfe1);               // written as T by the Up2Store epilogue (same element size)
   const int H2 = L.Hp / 2, W2 = L.Wp / 2, H4 = L.Hp / 4, W4 = L.Wp / 4;
-  auto run = [&](const char* what, const UmmaWeights& u, const ConvParams& p, const UmmaGate* g) {
+  auto run = [&](const char* what, const UmmaWeights& u, const ConvParams& p, const UmmaGate* g, bool trunk_out = false) {
     c.begin("umma_conv_ae");
     if (c.dry || c.rc != LPSR_OK) return;
-    const char* msg = (g && g->epi == kEpiUp2Store) ? umma_conv_launch<TA, T>(u, p, h->num_sms, c.st, g) : umma_conv_launch<TA>(u, p, h->num_sms, c.st, g);
+    // trunk_out: the stage that feeds the trunk converts to the trunk's element type in its (Up2Store) epilogue
+    const char* msg = trunk_out ? umma_conv_launch<TA, T>(u, p, h->num_sms, c.st, g) : umma_conv_launch<TA>(u, p, h->num_sms, c.st, g);
     if (msg) c.rc = fail(h, LPSR_ERR_CUDA, "umma_conv %s launch: %s", what, msg);
   };
   auto shape = [](int ks, int cin, int cout) { ConvW w; w.ks = ks; w.cin = cin; w.cout = cout; return w; };
@@ -305,14 +306,13 @@ void ae_forward_tc(Ctx& c, const WsLayout& L, char* ws, const float* x, int B, i
     run("ae.enc1", h->aet_enc1, conv_params(shape(5, 48, 16), e0, 48, 0, 16, e1, 48, 0, B, H2, W2, true), &g);
   }
   c.tag = "ae.dec0";
-  run("ae.dec0", h->aet_dec0, conv_params(shape(5, 48, 48), e1, 48, 0, 16, d0q, 48, 0, B, H4, W4, true), nullptr);
-  c.tag = "ae.dec1";
-  for (int I = 0; I < 2; ++I) {
+  {
     UmmaGate g{};
-    g.epi = kEpiReluUp2Res;
-    g.up_row = I;
-    run("ae.dec1", h->aet_dec1[I], conv_params(shape(3, 48, 96), d0q, 48, 0, 16, s, 48, 0, B, H4, W4, true, c0u, 48, 0), &g);
+    g.epi = kEpiUp2Store;                                      // PixelShuffle + ReLU in the store: four half-grid pixels per row
+    run("ae.dec0", h->aet_dec0, conv_params(shape(5, 48, 64), e1, 48, 0, 16, d0, 16, 0, B, H4, W4, true), &g);
   }
+  c.tag = "ae.dec1";
+  run("ae.dec1", h->aet_dec1, conv_params(shape(5, 16, 48), d0, 16, 0, 16, s, 48, 0, B, H2, W2, true, c0u, 48, 0), nullptr);
   c.tag = "ae.conv_out";
   run("ae.conv_out", h->aet_out, conv_params(shape(3, 48, 16), s, 48, 0, 16, aeu, 16, 0, B, H2, W2, false), nullptr);
   // RDN shallowF1: the 7x7 over the 3-channel AutoEncoder output, evaluated on the half grid (25 coarse taps, K = 16, N = 4 x 32)
@@ -320,7 +320,7 @@ void ae_forward_tc(Ctx& c, const WsLayout& L, char* ws, const float* x, int B, i
   {
     UmmaGate g{};
     g.epi = kEpiUp2Store;
-    run("rdn.shallowF1", h->aet_sfe1, conv_params(shape(5, 16, 128), aeu, 16, 0, 16, sfe1, 32, 0, B, H2, W2, false), &g);
+    run("rdn.shallowF1", h->aet_sfe1, conv_params(shape(5, 16, 128), aeu, 16, 0, 16, sfe1, 32, 0, B, H2, W2, false), &g, true);
   }
 }
 

@@ -255,12 +255,12 @@ template <> struct IsBf16<__nv_bfloat16> { static constexpr bool value = true; }
 // Epilogues.  FinalSigmoid: channel 0 -> sigmoid -> fp32 [pixel] (lpsr.py:273-274).  The last three serve the AutoEncoder, whose
 // PixelUnshuffle / PixelShuffle (lpsr.py:72,79,88,95) are folded into the convolutions around them:
 //   UnshuffleRelu: 12 real channels of pixel (y,x) -> ReLU -> channel c*4 + (y&1)*2 + (x&1) of pixel (y/2, x/2) of a half-size tensor
-//   ReluUp2Res   : N = 2 x 48: column block J is pixel (2y + I, 2x + J) of a double-size tensor (I = out_off2): ReLU, + residual
-//   Up2Store     : N = 4 sub-pixels x 32: column block (I*2 + J) is pixel (2y + I, 2x + J) of a double-size 32-channel tensor of type TOUT
-//                  (shallowF1's 7x7 evaluated on the half grid, lpsr.py:195-197)
+//   ReluResidual : ReLU, then + residual (the decoder's last stage: c0 + relu(...), lpsr.py:115)
+//   Up2Store     : N = 4 sub-pixels x N/4: column block (I*2 + J) is pixel (2y + I, 2x + J) of a double-size tensor of type TOUT, optional
+//                  ReLU (shallowF1's 7x7 evaluated on the half grid, lpsr.py:195-197; decoder.0 + PixelShuffle, lpsr.py:83-89)
 //   Pool         : plain (+bias) store, and per (tile, warp) channel sums of the fp32 results -> pool[(tile*4 + warp)*32 + c]: the partial
 //                  sums of AdaptiveAvgPool2d(1) over CSAR's x_in (lpsr.py:124,181) without reading x_in back; fixed order, so deterministic
-enum { kEpiPlain = 0, kEpiGate = 1, kEpiFinalSigmoid = 2, kEpiRelu = 3, kEpiResidual = 4, kEpiUnshuffleRelu = 5, kEpiReluUp2Res = 6, kEpiUp2Store = 7,
+enum { kEpiPlain = 0, kEpiGate = 1, kEpiFinalSigmoid = 2, kEpiRelu = 3, kEpiResidual = 4, kEpiUnshuffleRelu = 5, kEpiReluResidual = 6, kEpiUp2Store = 7,
        kEpiPool = 8 };
 
 // sum over the 32 lanes of 16 values per lane (a 32 x 16 transpose-reduce): 16 shuffles; lane l returns the total of value (l >> 1) & 15
@@ -662,21 +662,6 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
             for (int i = 0; i < NRES; ++i) rsd_raw[i] = *reinterpret_cast<const uint4*>(res + (size_t)pix * res_pitch + res_off + i * 8);
           }
         }
-        // double-size residual (kEpiReluUp2Res): rolling prefetch two 16-channel chunks ahead, so the global-load latency hides
-        // behind the accumulator wait and the previous chunks' stores instead of stalling every chunk
-        [[maybe_unused]] uint4 up_nxt[2][2];
-        [[maybe_unused]] int up_base = -1;
-        if constexpr (EPI == kEpiReluUp2Res) {
-          if (pix >= 0) {
-            up_base = (nn * 2 * Himg + 2 * yy + p.out_off2) * 2 * Wimg + 2 * xx;
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              const T* src = res + (size_t)(up_base + (q * CH) / 48) * res_pitch + res_off + (q * CH) % 48;
-              up_nxt[q][0] = *reinterpret_cast<const uint4*>(src);
-              up_nxt[q][1] = *reinterpret_cast<const uint4*>(src + 8);
-            }
-          }
-        }
         LPSR_TRACE(wq == 0 && lane == 0, ii * k_tiles + m, 3, clock64());
         ptx::mbar_wait(tfull_bar(grp), my_par);
         ptx::tc_fence_after();
@@ -812,26 +797,12 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
 #pragma unroll
               for (int c = 0; c < 12; ++c) o[c * 4] = from_f32<T>(fmaxf(v[c], 0.f));
             }
-          } else if constexpr (EPI == kEpiReluUp2Res) {
-            // this launch produces row 2y + I of the double-size tensor; column block J = cc / 48 is pixel 2x + J
-            static_assert(EPI != kEpiReluUp2Res || NOUT == 96, "two 48-channel pixels per row");
-            const int up = valid ? up_base + cc / 48 : -1;
-            {
-              const uint4 cur[2] = {up_nxt[(cc / CH) & 1][0], up_nxt[(cc / CH) & 1][1]};
-              if (cc + 2 * CH < NOUT && pix >= 0) {
-                const T* src = res + (size_t)(up_base + (cc + 2 * CH) / 48) * res_pitch + res_off + (cc + 2 * CH) % 48;
-                up_nxt[(cc / CH) & 1][0] = *reinterpret_cast<const uint4*>(src);
-                up_nxt[(cc / CH) & 1][1] = *reinterpret_cast<const uint4*>(src + 8);
-              }
-              const T* re = reinterpret_cast<const T*>(cur);
-#pragma unroll
-              for (int c = 0; c < CH; ++c) v[c] = fmaxf(v[c], 0.f) + to_f32<T>(re[c]);
-            }
-            store_chunk16<T>(out, out_pitch, out_off + cc % 48, up, v);
           } else if constexpr (EPI == kEpiUp2Store) {
-            static_assert(EPI != kEpiUp2Store || NOUT == 128, "four 32-channel pixels per row");
-            const int up = valid ? ((nn * 2 * Himg + 2 * yy + cc / 64) * 2 * Wimg + 2 * xx + (cc / 32) % 2) : -1;
-            store_chunk16<TOUT>(reinterpret_cast<TOUT*>(out), out_pitch, out_off + cc % 32, up, v);
+            static_assert(EPI != kEpiUp2Store || NOUT == 128 || NOUT == 64, "four pixels of 32 or 16 channels per row");
+            constexpr int CS = NOUT / 4;                          // channels per sub-pixel
+            const int up = valid ? ((nn * 2 * Himg + 2 * yy + cc / (2 * CS)) * 2 * Wimg + 2 * xx + (cc / CS) % 2) : -1;
+            if (p.relu) store_chunk16<TOUT, true>(reinterpret_cast<TOUT*>(out), out_pitch, out_off + cc % CS, up, v);
+            else store_chunk16<TOUT>(reinterpret_cast<TOUT*>(out), out_pitch, out_off + cc % CS, up, v);
           } else if constexpr (EPI == kEpiGate) {
             // CSAR gates (1x1, NOUT = 32): spatial branch x_in * sigmoid(.), channel branch x_in^2 * s_c
             float g1[CH];
@@ -855,6 +826,14 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
             store_chunk16<T>(out, out_pitch, p.out_off2 + cc, pix32, v);
           } else {
 
+            if constexpr (EPI == kEpiReluResidual) {
+              if (valid) {
+                float r[CH];
+                load_vec<T, CH>(res + (size_t)pix * res_pitch + res_off + cc, r);
+#pragma unroll
+                for (int c = 0; c < CH; ++c) v[c] = fmaxf(v[c], 0.f) + r[c];
+              }
+            }
             if constexpr (EPI == kEpiResidual) {
               if (valid) {
                 float r[CH];
@@ -1164,7 +1143,8 @@ inline const char* umma_plan_launch(const UmmaPlan& plan, const UmmaWeights& w, 
   if (w.ks == 7) return w.cout == 32 ? umma_launch_epi<T, 32, kConv7x7>(plan, st) : "unsupported Cout";
   if (w.ks == 5) {   // AutoEncoder stages (composed depthwise + pointwise)
     if (w.cout == 16 && mode == kEpiUnshuffleRelu) return umma_launch_inst<T, 16, kConv5x5Taps, kEpiUnshuffleRelu>(plan, st);
-    if (w.cout == 48 && plain && plan.p.relu) return umma_launch_inst<T, 48, kConv5x5Taps, kEpiRelu>(plan, st);
+    if (w.cout == 48 && mode == kEpiPlain && plan.p.relu && plan.p.res) return umma_launch_inst<T, 48, kConv5x5Taps, kEpiReluResidual>(plan, st);
+    if (w.cout == 64 && mode == kEpiUp2Store) return umma_launch_inst<T, 64, kConv5x5Taps, kEpiUp2Store, T>(plan, st);
     if (w.cout == 128 && mode == kEpiUp2Store) return umma_launch_inst<T, 128, kConv5x5Taps, kEpiUp2Store, TOUT>(plan, st);
     return "5x5 conv: shape/epilogue not instantiated";
   }
@@ -1175,7 +1155,6 @@ inline const char* umma_plan_launch(const UmmaPlan& plan, const UmmaWeights& w, 
     if (w.cout == 32) return umma_launch_epi<T, 32, kConv3x3Taps>(plan, st);
     if (w.cout == 48 && plain) return plan.p.relu ? umma_launch_inst<T, 48, kConv3x3Taps, kEpiRelu>(plan, st)
                                                   : umma_launch_inst<T, 48, kConv3x3Taps, kEpiPlain>(plan, st);
-    if (w.cout == 96 && mode == kEpiReluUp2Res) return umma_launch_inst<T, 96, kConv3x3Taps, kEpiReluUp2Res>(plan, st);
   } else {
     if (w.cout == 16) return umma_launch_epi<T, 16, kConv1x1>(plan, st);
     if (w.cout == 32) return umma_launch_epi<T, 32, kConv1x1>(plan, st);
@@ -1190,8 +1169,7 @@ struct UmmaGate {
   const float* s_c;        // [B][32] channel gates
   int out_off_spatial;     // channel offset of x_in * sigmoid(.) in the output buffer (x_in^2 * s_c goes to ConvParams::out_off)
   int final_sigmoid;       // 1: kEpiFinalSigmoid instead (ConvParams::out is a float [B*H*W] tensor)
-  int epi = 0;             // kEpiUnshuffleRelu / kEpiReluUp2Res / kEpiUp2Store / kEpiPool (else 0)
-  int up_row = 0;          // kEpiReluUp2Res: row parity I produced by this launch
+  int epi = 0;             // kEpiUnshuffleRelu / kEpiUp2Store / kEpiPool (else 0)
   float* pool = nullptr;   // kEpiPool: partial-sum buffer, pool_slots_per_crop x 32 floats per crop
   int pool_slots_per_crop = 0;          // capacity of `pool` per crop
   int* out_slots_per_crop = nullptr;    // kEpiPool: receives the slots the launch wrote per crop (tiles per crop x 4)
@@ -1203,7 +1181,6 @@ inline const char* umma_conv_launch(const UmmaWeights& w, const ConvParams& cp, 
   if (const char* msg = umma_plan(plan, w, cp, num_sms, !IsBf16<T>::value, gate && gate->final_sigmoid, gate && gate->epi == kEpiPool)) return msg;
   if (gate && gate->epi) {
     plan.p.mode = gate->epi;
-    plan.p.out_off2 = gate->up_row;
     if (gate->epi == kEpiPool) {
       const int slots = plan.p.n_strips * plan.p.items_per_strip * plan.p.k * 4;
       if (w.ks != 3 || w.cout != 32 || !gate->pool || !gate->out_slots_per_crop) return "pool epilogue needs a 3x3 conv with Cout = 32 and a partial buffer";
@@ -1211,7 +1188,6 @@ inline const char* umma_conv_launch(const UmmaWeights& w, const ConvParams& cp, 
       plan.p.pool = gate->pool;
       *gate->out_slots_per_crop = slots;
     }
-    if (gate->epi == kEpiReluUp2Res && (!cp.res || cp.res_pitch % 8 || cp.res_off % 8)) return "up2 epilogue needs an aligned residual";
   } else if (gate && gate->final_sigmoid) {
     if (w.ks != 3 || w.cout != 16) return "final epilogue needs the folded 3x3 conv with Cout padded to 16";
     plan.p.mode = kEpiFinalSigmoid;

@@ -1,5 +1,5 @@
 """Write profiles/r1_ncu_traffic.json from the raw-page CSV of an `ncu --set full` capture covering every tensor-core launch of
-ONE 16-bit forward in launch order (tools/ncu_forward.py, `-k regex:"umma|csar_tail" --launch-skip 26 --launch-count 26`).
+ONE 16-bit forward in launch order (tools/ncu_forward.py, `-k regex:"umma|csar_tail" --launch-skip 25 --launch-count 25`).
 Usage: python tools/ncu_traffic.py raw.csv B H W"""
 import csv, json, os, sys
 raw, B, H, W = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
@@ -14,9 +14,9 @@ def us(r):
     return v * {"us": 1.0, "ms": 1e3, "ns": 1e-3}[u]
 launches = [{"kernel": r[idx["Kernel Name"]][:80], "us": us(r), "dram": gb(r, "dram__bytes_read.sum") + gb(r, "dram__bytes_write.sum")}
             for r in rows[2:]]
-# launch order of one 16-bit forward (forward_impl.cuh): AutoEncoder (conv_in, enc0, enc1, dec0, dec1 x2, conv_out), shallowF1, shallowF2,
+# launch order of one 16-bit forward (forward_impl.cuh): AutoEncoder (conv_in, enc0, enc1, dec0, dec1, conv_out), shallowF1, shallowF2,
 # RDB (3 dense layers + fused last layer/lff), CSAR (conv_in.0, conv_in.2 + pool, fused tail), RDB, CSAR, gff.0, gff.1, final conv
-names = (["ae.conv_in", "ae.enc0", "ae.enc1", "ae.dec0", "ae.dec1", "ae.dec1", "ae.conv_out", "sfe1", "sfe2"] + ["rdb0"] * 4 +
+names = (["ae.conv_in", "ae.enc0", "ae.enc1", "ae.dec0", "ae.dec1", "ae.conv_out", "sfe1", "sfe2"] + ["rdb0"] * 4 +
          ["csar1.conv_in"] * 2 + ["csar1.tail"] + ["rdb2"] * 4 + ["csar3.conv_in"] * 2 + ["csar3.tail"] + ["gff0", "gff1", "final"])
 assert len(launches) == len(names), (len(launches), len(names))
 out = {"batch": B, "pixels_per_crop": H * W, "source": os.path.basename(raw),
