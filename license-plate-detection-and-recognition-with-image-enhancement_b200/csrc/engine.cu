@@ -530,6 +530,8 @@ int lpsr_destroy(lpsr_handle* h) {
   if (h->host_x) cudaFree(h->host_x);
   if (h->host_y) cudaFree(h->host_y);
   if (h->host_ws) cudaFree(h->host_ws);
+  if (h->host_ws2) cudaFree(h->host_ws2);
+  if (h->host_stream2) cudaStreamDestroy(h->host_stream2);
   if (h->host_stream) {
     cudaStreamDestroy(h->host_stream);
     cudaStreamDestroy(h->copy_in_stream);
@@ -641,6 +643,7 @@ int lpsr_forward_host(lpsr_handle* h, const float* x_host, float* y_host, int32_
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   if (!h->host_stream) {
     CUDA_TRY(h, cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking));
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->host_stream2, cudaStreamNonBlocking));
     CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_in_stream, cudaStreamNonBlocking));
     CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_out_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2 * kHostChunksMax; ++i) CUDA_TRY(h, cudaEventCreateWithFlags(&h->host_ev[i], cudaEventDisableTiming));
@@ -692,6 +695,12 @@ int lpsr_forward_host(lpsr_handle* h, const float* x_host, float* y_host, int32_
   CUDA_TRY(h, grow(&h->host_x, &h->host_x_cap, x_crop * B));
   CUDA_TRY(h, grow(&h->host_y, &h->host_y_cap, y_crop * B));
   CUDA_TRY(h, grow(&h->host_ws, &h->host_ws_cap, L.total));
+  // Chunks alternate between two compute streams (each with its own workspace): the persistent kernels of chunk i+1 start on SMs the
+  // kernels of chunk i have already left, so the per-launch ramp-down / ramp-up of ~28 launches per chunk overlaps instead of adding up.
+  static int two_streams = -1;
+  if (two_streams < 0) { const char* e2 = getenv("LPSR_HOST_STREAMS"); two_streams = (e2 && e2[0] == '1') ? 0 : 1; }
+  const bool dual = two_streams && nchunk > 1;
+  if (dual) CUDA_TRY(h, grow(&h->host_ws2, &h->host_ws2_cap, L.total));
   char* dx = static_cast<char*>(h->host_x);
   char* dy = static_cast<char*>(h->host_y);
   const char* hx = reinterpret_cast<const char*>(x_host);
@@ -701,16 +710,18 @@ int lpsr_forward_host(lpsr_handle* h, const float* x_host, float* y_host, int32_
     if (n <= 0) continue;
     CUDA_TRY(h, cudaMemcpyAsync(dx + x_crop * lo, hx + x_crop * lo, x_crop * n, cudaMemcpyHostToDevice, h->copy_in_stream));
     CUDA_TRY(h, cudaEventRecord(h->host_ev[2 * i], h->copy_in_stream));
-    CUDA_TRY(h, cudaStreamWaitEvent(h->host_stream, h->host_ev[2 * i], 0));
-    rc = lpsr_forward(h, reinterpret_cast<const float*>(dx + x_crop * lo), reinterpret_cast<float*>(dy + y_crop * lo), n, H, W, h->host_ws,
-                      h->host_ws_cap, h->host_stream);
+    cudaStream_t cs = (dual && (i & 1)) ? h->host_stream2 : h->host_stream;
+    CUDA_TRY(h, cudaStreamWaitEvent(cs, h->host_ev[2 * i], 0));
+    rc = lpsr_forward(h, reinterpret_cast<const float*>(dx + x_crop * lo), reinterpret_cast<float*>(dy + y_crop * lo), n, H, W,
+                      (dual && (i & 1)) ? h->host_ws2 : h->host_ws, (dual && (i & 1)) ? h->host_ws2_cap : h->host_ws_cap, cs);
     if (rc) return rc;
-    CUDA_TRY(h, cudaEventRecord(h->host_ev[2 * i + 1], h->host_stream));
+    CUDA_TRY(h, cudaEventRecord(h->host_ev[2 * i + 1], cs));
     CUDA_TRY(h, cudaStreamWaitEvent(h->copy_out_stream, h->host_ev[2 * i + 1], 0));
     CUDA_TRY(h, cudaMemcpyAsync(hy + y_crop * lo, dy + y_crop * lo, y_crop * n, cudaMemcpyDeviceToHost, h->copy_out_stream));
   }
   CUDA_TRY(h, cudaStreamSynchronize(h->copy_out_stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->host_stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->host_stream2));
   return LPSR_OK;
 }
 

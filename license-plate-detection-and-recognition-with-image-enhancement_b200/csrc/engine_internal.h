@@ -63,10 +63,10 @@ struct lpsr_handle {
   float *ca_w1 = nullptr, *ca_b1 = nullptr, *ca_w2 = nullptr, *ca_b2 = nullptr;
   float *sa_w1 = nullptr, *sa_b1 = nullptr, *sa_w2 = nullptr, *sa_b2 = nullptr, *co_w = nullptr, *co_b = nullptr;
   // host-call path (lpsr_forward_host)
-  cudaStream_t host_stream = nullptr, copy_in_stream = nullptr, copy_out_stream = nullptr;
+  cudaStream_t host_stream = nullptr, host_stream2 = nullptr, copy_in_stream = nullptr, copy_out_stream = nullptr;
   cudaEvent_t host_ev[16] = {};
-  void* host_x = nullptr; void* host_y = nullptr; void* host_ws = nullptr;
-  size_t host_x_cap = 0, host_y_cap = 0, host_ws_cap = 0;
+  void* host_x = nullptr; void* host_y = nullptr; void* host_ws = nullptr; void* host_ws2 = nullptr;
+  size_t host_x_cap = 0, host_y_cap = 0, host_ws_cap = 0, host_ws2_cap = 0;
   char err[512] = "";
 };
 
