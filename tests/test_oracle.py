@@ -89,3 +89,54 @@ def test_survey_sanity_vector(shipped_weights):
     assert abs(float(y.sum()) - 15583.47) < 0.05
     assert np.allclose(y[0, 0, 0, :4], [0.54689, 0.60430, 0.63589, 0.61160], atol=2e-5)
     assert np.allclose(y[1, 0, 63, 188:], [0.64432, 0.54506, 0.48248, 0.49594], atol=2e-5)
+
+
+def _s2d_weights(w, b):
+    """The weight transformation the tensor-core AutoEncoder uses (engine.cu: s2d_weights), restated in numpy: a ks x ks conv on the
+    fine grid equals a 3x3 (5x5 for ks = 7) conv on the 2x coarser grid whose pixels carry their 2x2 fine pixels as channels in
+    PixelUnshuffle order c*4 + i*2 + j:  w'[(co,I,J)][(ci,i,j)][th][tw] = w[co][ci][2th + i - I + R][2tw + j - J + R]."""
+    cout, cin, ks, _ = w.shape
+    R, RC = ks // 2, (1 if ks <= 5 else 2)
+    KC = 2 * RC + 1
+    ws = np.zeros((cout * 4, cin * 4, KC, KC), dtype=w.dtype)
+    for I in range(2):
+        for J in range(2):
+            for i in range(2):
+                for j in range(2):
+                    for th in range(-RC, RC + 1):
+                        dy = 2 * th + i - I + R
+                        if not 0 <= dy < ks:
+                            continue
+                        for tw in range(-RC, RC + 1):
+                            dx = 2 * tw + j - J + R
+                            if 0 <= dx < ks:
+                                ws[I * 2 + J::4, i * 2 + j::4, th + RC, tw + RC] = w[:, :, dy, dx]
+    return ws, (None if b is None else np.repeat(b, 4))
+
+
+@pytest.mark.parametrize("ks", [3, 5, 7])
+def test_space_to_depth_conv_identity(ks):
+    """unshuffle(conv(x, w)) == conv(unshuffle(x), s2d(w)) with 'same' zero padding: the identity that lets the 16-bit path run the
+    AutoEncoder (lpsr.py:64-117) and shallowF1 (lpsr.py:195-197) on the half / quarter grid with the pixel (un)shuffles folded away."""
+    rng = np.random.default_rng(ks)
+    x = rng.standard_normal((2, 3, 12, 20)).astype(np.float32)
+    w = rng.standard_normal((5, 3, ks, ks)).astype(np.float32)
+    b = rng.standard_normal(5).astype(np.float32)
+    ws, bs = _s2d_weights(w, b)
+    fine = orc.pixel_unshuffle(orc.conv2d(x, w, b))
+    coarse = orc.conv2d(orc.pixel_unshuffle(x), ws, bs)
+    assert fine.shape == coarse.shape
+    assert np.abs(fine - coarse).max() <= 2e-5
+
+
+def test_dconv_is_one_dense_conv(shipped_weights):
+    """DConv (depthwise k x k + bias, pointwise 1x1 + bias, no activation in between, lpsr.py:8-28) == one dense k x k conv with
+    w[co][ci] = pw[co][ci] * dw[ci] and bias pw_b + pw @ dw_b: what the tensor-core path packs (engine.cu: compose_dconv)."""
+    W = shipped_weights
+    p = "auto_encoder.encoder.3.dConv."
+    dw, dwb, pw, pwb = W[p + "0.weight"], W[p + "0.bias"], W[p + "1.weight"], W[p + "1.bias"]
+    x = np.random.default_rng(0).standard_normal((1, dw.shape[0], 9, 11)).astype(np.float32)
+    ref = orc.conv2d(orc.conv2d(x, dw, dwb, groups=dw.shape[0]), pw, pwb)
+    dense_w = pw[:, :, 0, 0][:, :, None, None] * dw[:, 0][None]
+    dense_b = pwb + pw[:, :, 0, 0] @ dwb
+    assert np.abs(orc.conv2d(x, dense_w, dense_b) - ref).max() <= 1e-5
