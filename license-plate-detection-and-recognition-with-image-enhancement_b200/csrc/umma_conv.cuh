@@ -330,7 +330,9 @@ __device__ __forceinline__ void store_chunk16(T* __restrict__ out, int pitch, in
 //         the dy = 1 MMAs carry 32 extra columns = lff over the layer's own 80 input channels (same A rows, no extra traffic); the
 //         epilogue turns the folded 48 columns into g3 = relu(conv + bias), writes it to shared memory as a K = 16 operand, one more
 //         MMA adds lff's g3 slice, and a second epilogue pass adds bias + x and stores the block output.  g3 never goes to HBM.)
-enum { kConv1x1 = 0, kConv3x3Taps = 1, kConv3x3Fold = 2, kConv7x7 = 3, kConv5x5Taps = 4, kConv3x3FoldLff = 5 };
+//       | kConv5x5Fold (Cout = 16: the five dx taps folded into N = 80, 5 MMAs per K-slice instead of 25; the epilogue forms
+//         out[q] = sum_dx D[q + dx - 2, dx] with shuffles by 1 and 2 rows; tiles overlap by 4 rows (stride 124))
+enum { kConv1x1 = 0, kConv3x3Taps = 1, kConv3x3Fold = 2, kConv7x7 = 3, kConv5x5Taps = 4, kConv3x3FoldLff = 5, kConv5x5Fold = 6 };
 constexpr int kLffN = 32, kLffCols = 48 + kLffN;   // fused layer: TMEM columns per accumulator = 3*16 folded + 32 lff
 
 struct UmmaTmaps { CUtensorMap m[kUmmaMaxKChunks]; };   // one tiled map per K-chunk (its tensor, its box width)
@@ -344,12 +346,16 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
   static_assert(sizeof(T) == 2, "16-bit operands");
   constexpr bool LFF = (MODE == kConv3x3FoldLff);
   constexpr bool FOLD = (MODE == kConv3x3Fold) || LFF;
+  constexpr bool FOLD5 = (MODE == kConv5x5Fold);
+  constexpr int HF = FOLD5 ? 2 : (FOLD ? 1 : 0);               // rows of a tile lost on each side to the dx fold
   static_assert(!LFF || NOUT == 16, "fused layer: growth rate 16");
   constexpr bool K3 = (MODE != kConv1x1);
-  constexpr int NMMA = LFF ? kLffCols : (FOLD ? 3 * NOUT : NOUT);   // TMEM columns per tile (and weight rows per K core-matrix)
+  constexpr int NMMA = LFF ? kLffCols : (FOLD5 ? 5 * NOUT : (FOLD ? 3 * NOUT : NOUT));   // TMEM columns per tile (and weight rows per K core-matrix)
   constexpr int KSZ = (MODE == kConv5x5Taps) ? 5 : 3;          // taps per kernel row (per-tap / folded modes)
-  constexpr int NTAP = (MODE == kConv1x1 || MODE == kConv7x7) ? 1 : (FOLD ? 3 : KSZ * KSZ);   // MMAs per K-step
-  constexpr int XCH = FOLD ? kEpiGroups * 2 * 4 * 2 * NOUT : 0;                 // floats of warp-boundary exchange (folded epilogue only)
+  constexpr int NTAP = (MODE == kConv1x1 || MODE == kConv7x7) ? 1 : (FOLD5 ? 5 : (FOLD ? 3 : KSZ * KSZ));   // MMAs per K-step
+  // floats of warp-boundary exchange (folded epilogues): [group][parity][warp][side][rows x NOUT]; 5-wide fold: 3 rows per side
+  constexpr int XROW = FOLD5 ? 3 : 1;
+  constexpr int XCH = (FOLD || FOLD5) ? kEpiGroups * 2 * 4 * 2 * XROW * NOUT : 0;
   constexpr int G = kEpiGroups;
   static_assert(G * NMMA <= 512, "accumulators exceed TMEM");
   constexpr uint32_t kTmemCols = (G * NMMA <= 32) ? 32 : (G * NMMA <= 64) ? 64 : (G * NMMA <= 128) ? 128 : (G * NMMA <= 256) ? 256 : 512;
@@ -553,7 +559,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
                   const uint32_t dyv = t == 0 ? 1u : (t == 1 ? 0u : 2u);
                   ptx::tc_mma_f16_lohi(d, a0 + dyv * e.w, e.z, b_lo + dyv * cgn, kUmmaDescHi, t == 0 ? idesc : idesc48, 1u);
                 } else {
-                  const uint32_t shift = FOLD ? (uint32_t)t * e.w : (uint32_t)(t / KSZ) * e.w + (uint32_t)(t % KSZ) * e.y;
+                  const uint32_t shift = (FOLD || FOLD5) ? (uint32_t)t * e.w : (uint32_t)(t / KSZ) * e.w + (uint32_t)(t % KSZ) * e.y;
                   ptx::tc_mma_f16_lohi(d, a0 + shift, e.z, b_lo + (uint32_t)t * cgn, kUmmaDescHi, idesc, (uint32_t)(ks | t));
                 }
               }
@@ -590,7 +596,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
     constexpr int NB = NOUT <= 32 ? NOUT : 1;
     T* out = static_cast<T*>(p.out);
     const T* res = static_cast<const T*>(p.res);
-    float* xg = xchg + (size_t)grp * (2 * 4 * 2 * NOUT);
+    float* xg = xchg + (size_t)grp * (2 * 4 * 2 * XROW * NOUT);
     const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(grp * NMMA);
     // everything the per-tile path needs lives in registers
     const int pitch = p.pitch, tstride = p.tstride, k_tiles = p.k, Himg = p.H, Wimg = p.W, halo = p.halo, TWs = p.TW;
@@ -620,8 +626,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
         const int strip = rem / ips, j = rem - strip * ips;
         xbase = strip * TWs - halo;                             // image x of strip column xs is xbase + xs
         tw = min(TWs, Wimg - strip * TWs) + halo;               // valid strip columns are [halo, tw)
-        const int q = j * rows_per_item - (FOLD ? 1 : 0) + row; // linear strip position of this thread's row in tile 0 (>= -1)
-        y = (q + pitch) / pitch - 1;
+        const int q = j * rows_per_item - HF + row;             // linear strip position of this thread's row in tile 0 (>= -HF)
+        y = (q + 2 * pitch) / pitch - 2;
         xs = q - y * pitch;
         px = n * crop_px + xbase;
       } else {
@@ -645,7 +651,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
         [[maybe_unused]] int yy = 0, xx = 0;                    // image coordinates of this row's pixel (shuffling epilogues)
         if constexpr (K3) {
           // folded: rows 0 and 127 are the shuffle halo of the tile
-          if ((!FOLD || (row >= 1 && row <= 126)) && (unsigned)y < (unsigned)Himg && xs >= halo && xs < tw) pix = px + y * Wimg + xs;
+          if (row >= HF && row <= 127 - HF && (unsigned)y < (unsigned)Himg && xs >= halo && xs < tw) pix = px + y * Wimg + xs;
           yy = y; xx = xbase + xs;
           xs += advg_x;                                         // advance to the group's next tile
           y += advg_y;
@@ -666,13 +672,13 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
         ptx::mbar_wait(tfull_bar(grp), my_par);
         ptx::tc_fence_after();
         LPSR_TRACE(wq == 0 && lane == 0, ii * k_tiles + m, 4, clock64());
-        float* xb = xg + (size_t)my_par * (4 * 2 * NOUT);
+        float* xb = xg + (size_t)my_par * (4 * 2 * XROW * NOUT);
         [[maybe_unused]] const uint32_t tile_par = my_par;
         my_par ^= 1u;
         const bool valid = pix >= 0 && !skip_store;
         const int pix32 = valid ? pix : -1;
         // narrow accumulators: all TMEM loads in flight at once, one wait, and the accumulator goes back to the MMA warp before any math
-        constexpr bool PRELOAD = !FOLD && NOUT <= 64;
+        constexpr bool PRELOAD = !FOLD && !FOLD5 && NOUT <= 64;
         [[maybe_unused]] float vall[PRELOAD ? NOUT : 1];
         if constexpr (PRELOAD) {
 #pragma unroll
@@ -686,7 +692,67 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
 #pragma unroll
         for (int cc = 0; cc < NOUT; cc += CH) {
           float v[CH];
-          if constexpr (FOLD) {
+          if constexpr (FOLD5) {
+            // out[q] = D[q-2, dx=0] + D[q-1, dx=1] + D[q, dx=2] + D[q+1, dx=3] + D[q+2, dx=4]
+            static_assert(!FOLD5 || NOUT == 16, "5-wide fold: Cout = 16");
+            float d0[CH], d1[CH], d3[CH], d4[CH];
+            ptx::tc_ld16_nowait(taddr, d0);
+            ptx::tc_ld16_nowait(taddr + NOUT, d1);
+            ptx::tc_ld16_nowait(taddr + 2 * NOUT, v);
+            ptx::tc_ld16_nowait(taddr + 3 * NOUT, d3);
+            ptx::tc_ld16_nowait(taddr + 4 * NOUT, d4);
+            ptx::tc_wait_ld();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty_bar(grp));
+            // rows that cross a warp boundary travel through shared memory: up side {D0@30, D0@31, D1@31}, down side {D4@0, D4@1, D3@0}
+            float* up = xb + (size_t)(wq * 2 + 0) * (XROW * NOUT);
+            float* dn = xb + (size_t)(wq * 2 + 1) * (XROW * NOUT);
+            if (lane >= 30) {
+#pragma unroll
+              for (int c = 0; c < CH; c += 4) *reinterpret_cast<float4*>(&up[(lane - 30) * NOUT + c]) = make_float4(d0[c], d0[c + 1], d0[c + 2], d0[c + 3]);
+            }
+            if (lane == 31) {
+#pragma unroll
+              for (int c = 0; c < CH; c += 4) *reinterpret_cast<float4*>(&up[2 * NOUT + c]) = make_float4(d1[c], d1[c + 1], d1[c + 2], d1[c + 3]);
+            }
+            if (lane <= 1) {
+#pragma unroll
+              for (int c = 0; c < CH; c += 4) *reinterpret_cast<float4*>(&dn[lane * NOUT + c]) = make_float4(d4[c], d4[c + 1], d4[c + 2], d4[c + 3]);
+            }
+            if (lane == 0) {
+#pragma unroll
+              for (int c = 0; c < CH; c += 4) *reinterpret_cast<float4*>(&dn[2 * NOUT + c]) = make_float4(d3[c], d3[c + 1], d3[c + 2], d3[c + 3]);
+            }
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+              d0[c] = __shfl_up_sync(0xffffffffu, d0[c], 2);
+              d1[c] = __shfl_up_sync(0xffffffffu, d1[c], 1);
+              d3[c] = __shfl_down_sync(0xffffffffu, d3[c], 1);
+              d4[c] = __shfl_down_sync(0xffffffffu, d4[c], 2);
+            }
+            ptx::bar_sync_named(1 + grp, 128);
+            if (wq > 0 && lane <= 1) {                           // from the previous warp's rows 30, 31
+              const float* pu = xb + (size_t)((wq - 1) * 2 + 0) * (XROW * NOUT);
+#pragma unroll
+              for (int c = 0; c < CH; ++c) d0[c] = pu[lane * NOUT + c];
+              if (lane == 0) {
+#pragma unroll
+                for (int c = 0; c < CH; ++c) d1[c] = pu[2 * NOUT + c];
+              }
+            }
+            if (wq < 3 && lane >= 30) {                          // from the next warp's rows 0, 1
+              const float* pd = xb + (size_t)((wq + 1) * 2 + 1) * (XROW * NOUT);
+#pragma unroll
+              for (int c = 0; c < CH; ++c) d4[c] = pd[(lane - 30) * NOUT + c];
+              if (lane == 31) {
+#pragma unroll
+                for (int c = 0; c < CH; ++c) d3[c] = pd[2 * NOUT + c];
+              }
+            }
+#pragma unroll
+            for (int c = 0; c < CH; ++c) v[c] += (d0[c] + d1[c]) + (d3[c] + d4[c]);
+          } else if constexpr (FOLD) {
             float lf[CH], rg[CH];
             if (!LPSR_DBG(64)) ptx::tc_ld16_nowait(taddr + cc, lf);
             ptx::tc_ld16_nowait(taddr + NOUT + cc, v);
@@ -933,9 +999,10 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
   const bool c7 = (w.ks == 7);
   const bool k3 = (w.ks == 3) || (w.ks == 5) || c7, fold = umma_fold(w.ks, w.cout);
   const bool lff = w.fused_lff;
-  const int N = w.cout, NMMA = lff ? kLffCols : (fold ? 3 * N : N), ntap = fold ? 3 : ((w.ks == 3 || w.ks == 5) ? w.ks * w.ks : 1);
+  const bool fold5 = fold && w.ks == 5;
+  const int N = w.cout, NMMA = lff ? kLffCols : (fold ? w.ks * N : N), ntap = fold ? w.ks : ((w.ks == 3 || w.ks == 5) ? w.ks * w.ks : 1);
   const int halo = w.ks / 2;
-  const size_t xch_bytes = fold ? (size_t)kEpiGroups * 2 * 4 * 2 * N * 4 : 0;
+  const size_t xch_bytes = fold ? (size_t)kEpiGroups * 2 * 4 * 2 * (fold5 ? 3 : 1) * N * 4 : 0;
   p.halo = halo;
   p.n_ks = w.cin / 16;                                       // 7x7: 28 pixel-pair steps (UmmaWeights::cin = 448 pseudo channels)
   if (p.n_ks > kUmmaMaxSteps) return "too many K-steps";
@@ -1008,7 +1075,7 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
     return b;
   };
   if (k3) {
-    const int ts = fold ? 126 : 128;
+    const int ts = fold5 ? 124 : (fold ? 126 : 128);
     p.tstride = ts;
     // choose strip width TW (equalised over W) and tiles per item k by a cost model:
     //   MMA/epilogue work ~ computed rows per output pixel; staging traffic ~ staged slots per output pixel
@@ -1142,7 +1209,7 @@ inline const char* umma_plan_launch(const UmmaPlan& plan, const UmmaWeights& w, 
   const bool plain = (mode == kEpiPlain && !plan.p.res);
   if (w.ks == 7) return w.cout == 32 ? umma_launch_epi<T, 32, kConv7x7>(plan, st) : "unsupported Cout";
   if (w.ks == 5) {   // AutoEncoder stages (composed depthwise + pointwise)
-    if (w.cout == 16 && mode == kEpiUnshuffleRelu) return umma_launch_inst<T, 16, kConv5x5Taps, kEpiUnshuffleRelu>(plan, st);
+    if (w.cout == 16 && mode == kEpiUnshuffleRelu) return umma_launch_inst<T, 16, kConv5x5Fold, kEpiUnshuffleRelu>(plan, st);
     if (w.cout == 48 && mode == kEpiPlain && plan.p.relu && plan.p.res) return umma_launch_inst<T, 48, kConv5x5Taps, kEpiReluResidual>(plan, st);
     if (w.cout == 64 && mode == kEpiUp2Store) return umma_launch_inst<T, 64, kConv5x5Taps, kEpiUp2Store, T>(plan, st);
     if (w.cout == 128 && mode == kEpiUp2Store) return umma_launch_inst<T, 128, kConv5x5Taps, kEpiUp2Store, TOUT>(plan, st);

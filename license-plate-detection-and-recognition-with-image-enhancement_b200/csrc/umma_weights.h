@@ -41,7 +41,7 @@ inline bool umma_fold(int ks, int cout) {
   static int fold32 = -1;
   if (fold32 < 0) { const char* e = getenv("LPSR_FOLD32"); fold32 = (e && e[0] == '1') ? 1 : 0; }
   (void)fold32;
-  return ks == 3 && cout == 16;
+  return (ks == 3 || ks == 5) && cout == 16;   // 5x5 (AutoEncoder encoder.3): five dx taps -> N = 80
 }
 
 inline uint16_t f32_to_bf16_bits(float f) {
@@ -75,13 +75,13 @@ bool umma_pack_weights(UmmaWeights& u, const float* pw, const float* bias, int k
         for (int n = 0; n < cout; ++n)
           for (int j = 0; j < 8; ++j) v[(((size_t)t * cg + g) * cout + n) * 8 + j] = cvt(pw[((size_t)t * cin + g * 8 + j) * cout + n]);
   } else {
-    const int nf = 3 * cout;
-    for (int dy = 0; dy < 3; ++dy)
+    const int nf = ks * cout;
+    for (int dy = 0; dy < ks; ++dy)
       for (int g = 0; g < cg; ++g)
-        for (int dx = 0; dx < 3; ++dx)
+        for (int dx = 0; dx < ks; ++dx)
           for (int n = 0; n < cout; ++n)
             for (int j = 0; j < 8; ++j)
-              v[(((size_t)dy * cg + g) * nf + dx * cout + n) * 8 + j] = cvt(pw[((size_t)(dy * 3 + dx) * cin + g * 8 + j) * cout + n]);
+              v[(((size_t)dy * cg + g) * nf + dx * cout + n) * 8 + j] = cvt(pw[((size_t)(dy * ks + dx) * cin + g * 8 + j) * cout + n]);
   }
   std::vector<float> b(cout, 0.f);
   if (bias) b.assign(bias, bias + cout);
