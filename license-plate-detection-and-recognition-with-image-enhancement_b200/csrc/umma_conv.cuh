@@ -677,21 +677,28 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
         my_par ^= 1u;
         const bool valid = pix >= 0 && !skip_store;
         const int pix32 = valid ? pix : -1;
-        // narrow accumulators: all TMEM loads in flight at once, one wait, and the accumulator goes back to the MMA warp before any math
-        constexpr bool PRELOAD = !FOLD && !FOLD5 && NOUT <= 64;
-        [[maybe_unused]] float vall[PRELOAD ? NOUT : 1];
-        if constexpr (PRELOAD) {
-#pragma unroll
-          for (int cc = 0; cc < NOUT; cc += CH) ptx::tc_ld16_nowait(taddr + cc, vall + cc);
-          ptx::tc_wait_ld();
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(tempty_bar(grp));
-          LPSR_TRACE(wq == 0 && lane == 0, ii * k_tiles + m, 5, clock64());
-        }
+        // plain accumulators are read in blocks of up to 64 columns: all TMEM loads of a block in flight at once, one wait, and after
+        // the last block the accumulator goes back to the MMA warp before any math
+        constexpr bool PRELOAD = !FOLD && !FOLD5;
+        constexpr int PB = NOUT <= 64 ? NOUT : 64;
+        static_assert(NOUT % PB == 0, "block size");
+        [[maybe_unused]] float vall[PRELOAD ? PB : 1];
 #pragma unroll
         for (int cc = 0; cc < NOUT; cc += CH) {
           float v[CH];
+          if constexpr (PRELOAD) {
+            if (cc % PB == 0) {
+#pragma unroll
+              for (int c2 = 0; c2 < PB; c2 += CH) ptx::tc_ld16_nowait(taddr + cc + c2, vall + c2);
+              ptx::tc_wait_ld();
+              if (cc + PB >= NOUT) {
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(tempty_bar(grp));
+                LPSR_TRACE(wq == 0 && lane == 0, ii * k_tiles + m, 5, clock64());
+              }
+            }
+          }
           if constexpr (FOLD5) {
             // out[q] = D[q-2, dx=0] + D[q-1, dx=1] + D[q, dx=2] + D[q+1, dx=3] + D[q+2, dx=4]
             static_assert(!FOLD5 || NOUT == 16, "5-wide fold: Cout = 16");
@@ -798,18 +805,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
             }
 #pragma unroll
             for (int c = 0; c < CH; ++c) v[c] += lf[c] + rg[c];
-          } else if constexpr (PRELOAD) {
-#pragma unroll
-            for (int c = 0; c < CH; ++c) v[c] = vall[cc + c];
           } else {
-            ptx::tc_ld16_nowait(taddr + cc, v);
-            ptx::tc_wait_ld();
-            if (cc + CH >= NOUT) {
-              ptx::tc_fence_before();
-              __syncwarp();
-              if (lane == 0) ptx::mbar_arrive(tempty_bar(grp));
-              LPSR_TRACE(wq == 0 && lane == 0, ii * k_tiles + m, 5, clock64());
-            }
+#pragma unroll
+            for (int c = 0; c < CH; ++c) v[c] = vall[cc % PB + c];
           }
           if constexpr (LFF) {
             // biases and the residual were accumulated by the tensor core
