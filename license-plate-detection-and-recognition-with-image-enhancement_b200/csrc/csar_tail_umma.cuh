@@ -203,10 +203,17 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
       // ---- phase 1: hidden = relu(acc + b3) -> A2
       ptx::mbar_wait(bar(g, 1), par);
       ptx::tc_fence_after();
+      float blk[32];
 #pragma unroll
       for (int c0 = 0; c0 < 64; c0 += 16) {
         float v[16];
-        ptx::tc_ld16(taddr + c0, v);
+        if (c0 % 32 == 0) {                                               // two TMEM loads in flight per wait
+          ptx::tc_ld16_nowait(taddr + c0, blk);
+          ptx::tc_ld16_nowait(taddr + c0 + 16, blk + 16);
+          ptx::tc_wait_ld();
+        }
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] = blk[c0 % 32 + c];
         *reinterpret_cast<uint4*>(a2 + ((size_t)(c0 / 8) * 128 + row) * 16) =
             make_uint4(pack2<T, true>(v[0], v[1]), pack2<T, true>(v[2], v[3]), pack2<T, true>(v[4], v[5]), pack2<T, true>(v[6], v[7]));
         *reinterpret_cast<uint4*>(a2 + ((size_t)(c0 / 8 + 1) * 128 + row) * 16) =
@@ -266,15 +273,17 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
       ptx::mbar_wait(bar(g, 5), par);
       ptx::tc_fence_after();
       const int pix32 = valid ? (int)pix : -1;
+      ptx::tc_ld16_nowait(taddr + 32, blk);
+      ptx::tc_ld16_nowait(taddr + 48, blk + 16);
+      ptx::tc_wait_ld();
+      ptx::tc_fence_before();                                             // accumulators are in registers: free the slot
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar(g, 6));
 #pragma unroll
       for (int c0 = 0; c0 < 32; c0 += 16) {
         float v[16];
-        ptx::tc_ld16(taddr + 32 + c0, v);
-        if (c0 == 16) {                                                   // accumulators are in registers: free the slot
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(bar(g, 6));
-        }
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] = blk[c0 + c];
         store_chunk16<T>(out, p.out_pitch, p.out_off + c0, pix32, v);
       }
     }

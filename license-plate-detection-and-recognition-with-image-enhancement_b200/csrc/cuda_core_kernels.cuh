@@ -422,16 +422,26 @@ __global__ void __launch_bounds__(kThreads) gap_partial_kernel(const T* __restri
 
 // ---------------------------------------------------------------------------------------------------
 // channel gate: s_c[b][c] = sigmoid(W2 relu(W1 mean_hw(x_in[b]) + b1) + b2)   (ChannelAttention, lpsr.py:120-135)
-// one CTA of 32 threads per crop; the mean comes from gap_partial_kernel's slice sums
+// one CTA of 256 threads per crop; the mean comes from the partial sums of gap_partial_kernel or of conv_in.2's epilogue
 // ---------------------------------------------------------------------------------------------------
-static __global__ void __launch_bounds__(32) channel_gate_kernel(const float* __restrict__ partial, int S, int P, const float* __restrict__ w1,
-                                                          const float* __restrict__ b1, const float* __restrict__ w2,
-                                                          const float* __restrict__ b2, float* __restrict__ s_c) {
-  __shared__ float s_mean[32], s_hid[8];
+static __global__ void __launch_bounds__(256) channel_gate_kernel(const float* __restrict__ partial, int S, int P, const float* __restrict__ w1,
+                                                           const float* __restrict__ b1, const float* __restrict__ w2,
+                                                           const float* __restrict__ b2, float* __restrict__ s_c) {
+  __shared__ float s_part[8][32], s_mean[32], s_hid[8];
   asm volatile("griddepcontrol.wait;" ::: "memory");   // programmatic dependent launch (see umma_conv.cuh)
-  const int b = blockIdx.x, c = threadIdx.x;
+  const int b = blockIdx.x, c = threadIdx.x & 31, wv = threadIdx.x >> 5;
+  // eight warps sum eight contiguous ranges of the partial sums, then one warp adds the eight results: a fixed order, so the pooled
+  // mean of a crop does not depend on the batch it is in
+  const int s0 = (int)(((long long)wv * S) / 8), s1 = (int)(((long long)(wv + 1) * S) / 8);
   float t = 0.f;
-  for (int s = 0; s < S; ++s) t += partial[((size_t)b * S + s) * 32 + c];
+#pragma unroll 4
+  for (int s = s0; s < s1; ++s) t += partial[((size_t)b * S + s) * 32 + c];
+  s_part[wv][c] = t;
+  __syncthreads();
+  if (wv != 0) return;
+  t = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) t += s_part[k][c];
   s_mean[c] = t / (float)P;
   __syncwarp();
   if (c < 8) {

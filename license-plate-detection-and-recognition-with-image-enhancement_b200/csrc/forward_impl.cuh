@@ -168,7 +168,7 @@ void csar_block(Ctx& c, const WsLayout& L, char* ws, int B, size_t in_t, size_t 
       float* sc = reinterpret_cast<float*>(ws + L.sc);
       c.begin("channel_gate");
       if (!c.dry && c.rc == LPSR_OK) {
-        cudaError_t e = launch_pdl(channel_gate_kernel, dim3(B), dim3(32), 0, c.st, (const float*)pool, pool_slots, L.P, (const float*)h->ca_w1,
+        cudaError_t e = launch_pdl(channel_gate_kernel, dim3(B), dim3(256), 0, c.st, (const float*)pool, pool_slots, L.P, (const float*)h->ca_w1,
                                    (const float*)h->ca_b1, (const float*)h->ca_w2, (const float*)h->ca_b2, sc);
         if (e == cudaSuccess) e = cudaGetLastError();
         if (e != cudaSuccess) c.rc = fail(h, LPSR_ERR_CUDA, "channel_gate launch: %s", cudaGetErrorString(e));
