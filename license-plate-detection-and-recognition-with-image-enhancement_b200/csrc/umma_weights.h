@@ -36,13 +36,9 @@ inline bool umma_supported(int ks, int cin, int cout) {
   return false;
 }
 
-// 3x3 with Cout = 16: fold the three dx taps into GEMM-N (N = 48); wider Cout: one MMA per tap
-inline bool umma_fold(int ks, int cout) {
-  static int fold32 = -1;
-  if (fold32 < 0) { const char* e = getenv("LPSR_FOLD32"); fold32 = (e && e[0] == '1') ? 1 : 0; }
-  (void)fold32;
-  return (ks == 3 || ks == 5) && cout == 16;   // 5x5 (AutoEncoder encoder.3): five dx taps -> N = 80
-}
+// Cout = 16: fold the dx taps of a 3x3 / 5x5 kernel into GEMM-N (N = 48 / 80); wider Cout: one MMA per tap
+// (folding Cout = 32 into N = 96 was measured slower: the shuffle epilogue outweighs the MMA saving)
+inline bool umma_fold(int ks, int cout) { return (ks == 3 || ks == 5) && cout == 16; }
 
 inline uint16_t f32_to_bf16_bits(float f) {
   uint32_t u;
