@@ -181,6 +181,19 @@ def test_half_modes_delta_psnr_below_0p05_db(prec, shipped_weights, models):
     assert abs(_psnr(y, target) - _psnr(ref, target)) < 0.05
 
 
+@pytest.mark.parametrize("H,W", [(1, 1), (2, 3), (5, 7), (8, 1024), (256, 8), (31, 257), (64, 20)])
+def test_ragged_shapes_all_modes(H, W, shipped_weights, models):
+    """Shapes the planner has to special-case: smaller than one tile, one pixel, very wide / very tall strips, sizes that are not
+    multiples of 4 (zero padded bottom/right and never cropped, lpsr.py:107-111).  Checked against the reference arithmetic on CPU."""
+    x = torch.rand(2, 3, H, W, generator=torch.Generator().manual_seed(H * 1000 + W))
+    ref = port.lpsr_forward(x, port.to_torch_weights(shipped_weights))
+    assert tuple(ref.shape) == (2, 1, (H + 3) // 4 * 4, (W + 3) // 4 * 4)
+    for prec, tol in (("fp32", FP32_TOL), ("fp16", HALF_TOL), ("bf16", 6e-2)):
+        y = models[prec](x.to(DEV)).cpu()
+        assert y.shape == ref.shape and torch.isfinite(y).all()
+        assert float((y - ref).abs().max()) <= tol, (prec, H, W, float((y - ref).abs().max()))
+
+
 def test_fp32_batch256_matches_torch_port(shipped_weights, models):
     """BASELINE config 2: fp32, B=256 of 3x64x192, vs the reference arithmetic on CPU."""
     x = torch.rand(256, 3, 64, 192, generator=torch.Generator().manual_seed(0))
