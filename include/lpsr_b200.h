@@ -132,6 +132,15 @@ int lpsr_abi_version(void);
 /* compute capability major*10+minor of the handle's device, 0 on error */
 int lpsr_device_sm(const lpsr_handle* h);
 
+/* -- pre-processing in front of the forward ------------------------------------- */
+/* Batched replacement of the reference's per-plate `preprocess_for_sr` (inference/run.py:80-96): B BGR uint8 crops of arbitrary
+ * sizes (packed HWC, device memory; crop i starts at byte offsets[i], heights[i] x widths[i]; the three arrays are host memory)
+ * -> RGB -> Pillow's antialiased bicubic resize to out_w x out_h (bit-exact with PIL.Image.resize(..., Image.BICUBIC)) -> / 255
+ * -> fp32 NCHW [B,3,out_h,out_w] on the device, i.e. exactly the tensor the reference feeds to LPSR.forward.  Asynchronous on
+ * `cuda_stream`; the host arrays may be reused when the call returns. */
+int lpsr_preprocess_resize(lpsr_handle* h, const uint8_t* crops_bgr_dev, const int64_t* offsets, const int32_t* heights,
+                           const int32_t* widths, int32_t B, int32_t out_h, int32_t out_w, float* x_nchw_dev, void* cuda_stream);
+
 /* -- operator-level entry points (unit parity tests; same kernels the forward uses) -------------- */
 /* nn.PixelUnshuffle(2) / nn.PixelShuffle(2) on device fp32 NCHW tensors (lpsr.py:72,79,88,95) through the
  * NHWC address maps the fused DConv kernels use; bit-exact index remaps. */

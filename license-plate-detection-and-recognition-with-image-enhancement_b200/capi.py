@@ -18,7 +18,7 @@ EXPORTS = [
     "lpsr_create", "lpsr_destroy", "lpsr_load_weights", "lpsr_num_live_tensors", "lpsr_live_tensor_name",
     "lpsr_live_tensor_numel", "lpsr_output_shape", "lpsr_workspace_bytes", "lpsr_forward", "lpsr_forward_profiled", "lpsr_forward_host",
     "lpsr_forward_launch_count", "lpsr_debug_read_tap", "lpsr_debug_umma_trace", "lpsr_last_error", "lpsr_abi_version", "lpsr_device_sm",
-    "lpsr_op_pixel_unshuffle2", "lpsr_op_pixel_shuffle2", "lpsr_op_conv2d",
+    "lpsr_op_pixel_unshuffle2", "lpsr_op_pixel_shuffle2", "lpsr_op_conv2d", "lpsr_preprocess_resize",
 ]
 
 
@@ -71,6 +71,7 @@ def load_library() -> C.CDLL:
     lib.lpsr_last_error.restype = C.c_char_p
     lib.lpsr_abi_version.argtypes = []
     lib.lpsr_device_sm.argtypes = [vp]
+    lib.lpsr_preprocess_resize.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp]
     lib.lpsr_op_pixel_unshuffle2.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     lib.lpsr_op_pixel_shuffle2.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     lib.lpsr_op_conv2d.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]

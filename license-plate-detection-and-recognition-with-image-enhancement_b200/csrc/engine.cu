@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -14,6 +15,7 @@
 
 #include "cuda_core_kernels.cuh"
 #include "engine_internal.h"
+#include "preprocess.cuh"
 #include "umma_conv.cuh"
 
 using namespace lpsr;
@@ -529,6 +531,9 @@ int lpsr_destroy(lpsr_handle* h) {
   if (h->arena.base) cudaFree(h->arena.base);
   if (h->host_x) cudaFree(h->host_x);
   if (h->host_y) cudaFree(h->host_y);
+  if (h->pre_host) cudaFreeHost(h->pre_host);
+  if (h->pre_dev) cudaFree(h->pre_dev);
+  if (h->pre_ev) cudaEventDestroy(h->pre_ev);
   if (h->host_ws) cudaFree(h->host_ws);
   if (h->host_ws2) cudaFree(h->host_ws2);
   if (h->host_stream2) cudaStreamDestroy(h->host_stream2);
@@ -771,6 +776,78 @@ int lpsr_debug_umma_trace(long long* dst_host) {
   long long* t = umma_trace_buffer();
   if (!t || !dst_host) return LPSR_ERR_INVALID_ARG;
   return cudaMemcpy(dst_host, t, 512 * 8 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? LPSR_OK : LPSR_ERR_CUDA;
+}
+
+int lpsr_preprocess_resize(lpsr_handle* h, const uint8_t* crops, const int64_t* offsets, const int32_t* heights, const int32_t* widths,
+                           int32_t B, int32_t out_h, int32_t out_w, float* x_out, void* stream) {
+  if (!h || !crops || !offsets || !heights || !widths || !x_out) return fail(h, LPSR_ERR_INVALID_ARG, "null argument");
+  if (B < 0 || out_h < 1 || out_w < 1) return fail(h, LPSR_ERR_INVALID_ARG, "bad shape");
+  if (B == 0) return LPSR_OK;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // host side: Pillow's weight tables (double precision, Pillow's operation order) per distinct source size, crop descriptors
+  std::vector<int> tab;
+  std::vector<ResampleCrop> desc((size_t)B);
+  std::map<std::pair<int, int>, std::array<int, 3>> cache;   // (in, out) -> {bounds offset, weights offset, ksize}
+  auto coeffs = [&](int in_size, int out_size) {
+    auto it = cache.find({in_size, out_size});
+    if (it != cache.end()) return it->second;
+    std::array<int, 3> r{};
+    resample_coeffs(in_size, out_size, tab, r[0], r[1], r[2]);
+    cache[{in_size, out_size}] = r;
+    return r;
+  };
+  long long tmp_total = 0;
+  for (int i = 0; i < B; ++i) {
+    const int H = heights[i], W = widths[i];
+    if (H < 1 || W < 1) return fail(h, LPSR_ERR_INVALID_ARG, "crop %d has size %dx%d", i, H, W);
+    ResampleCrop& d = desc[i];
+    d.src = offsets[i]; d.H = H; d.W = W;
+    d.need_h = (W != out_w); d.need_v = (H != out_h);
+    d.y0 = 0; d.rows = H;
+    if (d.need_v) {
+      const auto v = coeffs(H, out_h);
+      d.vb = v[0]; d.vk = v[1]; d.vks = v[2];
+    }
+    if (d.need_h) {
+      const auto hc = coeffs(W, out_w);
+      d.hb = hc[0]; d.hk = hc[1]; d.hks = hc[2];
+    }
+    d.tmp = tmp_total;
+    tmp_total += (long long)H * out_w * 3;
+  }
+  // Pillow's horizontal pass only produces the rows the vertical pass reads; with the full-image box that is every row whose
+  // weight can be non-zero, so processing all H rows gives the same values (the vertical bounds index the unshifted rows)
+  const size_t tab_bytes = tab.size() * sizeof(int), desc_bytes = desc.size() * sizeof(ResampleCrop);
+  const size_t need_dev = align_up(tab_bytes, 256) + align_up(desc_bytes, 256) + (size_t)tmp_total;
+  if (h->pre_ev) CUDA_TRY(h, cudaEventSynchronize(h->pre_ev));            // the previous call's table upload has left the staging buffer
+  else CUDA_TRY(h, cudaEventCreateWithFlags(&h->pre_ev, cudaEventDisableTiming));
+  if (h->pre_host_cap < tab_bytes + desc_bytes) {
+    if (h->pre_host) cudaFreeHost(h->pre_host);
+    h->pre_host = nullptr; h->pre_host_cap = 0;
+    CUDA_TRY(h, cudaMallocHost(&h->pre_host, (tab_bytes + desc_bytes) * 2));
+    h->pre_host_cap = (tab_bytes + desc_bytes) * 2;
+  }
+  if (h->pre_dev_cap < need_dev) {
+    CUDA_TRY(h, cudaDeviceSynchronize());                                  // earlier launches may still read the old buffer
+    if (h->pre_dev) cudaFree(h->pre_dev);
+    h->pre_dev = nullptr; h->pre_dev_cap = 0;
+    CUDA_TRY(h, cudaMalloc(&h->pre_dev, need_dev * 2));
+    h->pre_dev_cap = need_dev * 2;
+  }
+  char* hp = static_cast<char*>(h->pre_host);
+  memcpy(hp, tab.data(), tab_bytes);
+  memcpy(hp + tab_bytes, desc.data(), desc_bytes);
+  char* dp = static_cast<char*>(h->pre_dev);
+  int* d_tab = reinterpret_cast<int*>(dp);
+  ResampleCrop* d_desc = reinterpret_cast<ResampleCrop*>(dp + align_up(tab_bytes, 256));
+  uint8_t* d_tmp = reinterpret_cast<uint8_t*>(dp + align_up(tab_bytes, 256) + align_up(desc_bytes, 256));
+  CUDA_TRY(h, cudaMemcpyAsync(d_tab, hp, tab_bytes, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaMemcpyAsync(d_desc, hp + tab_bytes, desc_bytes, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaEventRecord(h->pre_ev, st));
+  preprocess_resize_kernel<<<B, 256, 0, st>>>(crops, d_desc, d_tab, d_tmp, x_out, out_h, out_w);
+  CUDA_TRY(h, cudaGetLastError());
+  return LPSR_OK;
 }
 
 int lpsr_op_conv2d(lpsr_handle* h, const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t Cin, int32_t Cout,

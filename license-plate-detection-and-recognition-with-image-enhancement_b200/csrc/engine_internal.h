@@ -67,6 +67,9 @@ struct lpsr_handle {
   cudaEvent_t host_ev[16] = {};
   void* host_x = nullptr; void* host_y = nullptr; void* host_ws = nullptr; void* host_ws2 = nullptr;
   size_t host_x_cap = 0, host_y_cap = 0, host_ws_cap = 0, host_ws2_cap = 0;
+  // lpsr_preprocess_resize: pinned staging + device buffer for the weight tables, crop descriptors and the inter-pass scratch
+  void* pre_host = nullptr; void* pre_dev = nullptr; size_t pre_host_cap = 0, pre_dev_cap = 0;
+  cudaEvent_t pre_ev = nullptr;
   char err[512] = "";
 };
 

@@ -47,3 +47,38 @@ def conv2d(model, x: torch.Tensor, weight: torch.Tensor, bias=None, relu: bool =
         capi.check(lib.lpsr_op_conv2d(h, x.data_ptr(), weight.data_ptr(), bptr, y.data_ptr(), B, Cin, Cout, k, H, W,
                                       1 if relu else 0, _stream(x)), h, "lpsr_op_conv2d")
     return y
+
+
+def preprocess_for_sr_batch(model, plates, target_size=(192, 32), device=None) -> torch.Tensor:
+    """Batched, on-device version of the reference's per-plate ``preprocess_for_sr`` (inference/run.py:80-96):
+    ``plates`` is a list of BGR uint8 HxWx3 numpy arrays (any sizes, e.g. all plates of a frame); the result is the float32
+    ``[B, 3, H_t, W_t]`` CUDA tensor ``torch.cat([preprocess_for_sr(p) for p in plates])`` would give (BGR->RGB, Pillow bicubic
+    resize, / 255), bit for bit, ready for ``model(x)``.  One packed H2D copy and one kernel launch for the whole batch."""
+    import numpy as np
+    lib = capi.load_library()
+    dev = torch.device(device) if device is not None else next(model.parameters()).device
+    if dev.type != "cuda":
+        raise RuntimeError("preprocess_for_sr_batch needs a CUDA device (there is no CPU fallback)")
+    W_t, H_t = int(target_size[0]), int(target_size[1])
+    B = len(plates)
+    out = torch.empty((B, 3, H_t, W_t), dtype=torch.float32, device=dev)
+    if B == 0:
+        return out
+    hs, ws, offs, total = [], [], [], 0
+    for p in plates:
+        if p.dtype != np.uint8 or p.ndim != 3 or p.shape[2] != 3 or p.shape[0] < 1 or p.shape[1] < 1:
+            raise ValueError("plates must be non-empty uint8 HxWx3 (BGR) arrays")
+        hs.append(p.shape[0]); ws.append(p.shape[1]); offs.append(total)
+        total += p.shape[0] * p.shape[1] * 3
+    packed = torch.empty(total, dtype=torch.uint8).pin_memory()
+    pk = packed.numpy()
+    for p, o in zip(plates, offs):
+        pk[o:o + p.size] = np.ascontiguousarray(p).reshape(-1)
+    h = model._handle(dev)
+    with torch.cuda.device(dev):
+        crops = packed.to(dev, non_blocking=True)
+        a_off = np.asarray(offs, dtype=np.int64); a_h = np.asarray(hs, dtype=np.int32); a_w = np.asarray(ws, dtype=np.int32)
+        capi.check(lib.lpsr_preprocess_resize(h, crops.data_ptr(), a_off.ctypes.data, a_h.ctypes.data, a_w.ctypes.data, B, H_t, W_t,
+                                              out.data_ptr(), _stream(out)), h, "lpsr_preprocess_resize")
+        crops.record_stream(torch.cuda.current_stream(dev))
+    return out

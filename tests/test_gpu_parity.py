@@ -264,3 +264,27 @@ def test_launch_count_and_errors(models):
     h = m._handle(torch.device(DEV))
     assert lib.lpsr_forward(h, None, None, 1, 32, 192, None, 0, None) == -1
     assert b"null" in lib.lpsr_last_error(h)
+
+
+def test_preprocess_batch_bit_exact_with_reference(models):
+    """one batched device call == the reference's per-plate preprocess_for_sr (run.py:80-96) on every fixture,
+    bit for bit (integer resample, exact float division), mixed sizes in one batch; and the forward of that tensor equals the forward
+    of the reference-preprocessed tensor."""
+    from oracle import preprocess_oracle as pre
+    d = np.load(os.path.join(GOLDEN, "preprocess_cases.npz"))
+    n = sum(1 for k in d.files if k.startswith("in_"))
+    plates = [d[f"in_{i}"] for i in range(n)]
+    m = models["fp32"]
+    x = lpsr_b200.preprocess_for_sr_batch(m, plates)
+    assert x.shape == (n, 3, 32, 192) and x.dtype == torch.float32 and x.is_cuda
+    ref = np.concatenate([d[f"out_{i}"] for i in range(n)])
+    assert np.array_equal(x.cpu().numpy(), ref)
+    assert torch.equal(m(x), m(torch.from_numpy(ref).to(DEV)))
+    # random batch of ragged crops against the oracle (up- and down-scaling, one-pass cases W == 192 / H == 32)
+    rng = np.random.default_rng(5)
+    sizes = [(int(rng.integers(1, 90)), int(rng.integers(1, 420))) for _ in range(40)] + [(32, 77), (50, 192), (32, 192)]
+    plates = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in sizes]
+    got = lpsr_b200.preprocess_for_sr_batch(m, plates).cpu().numpy()
+    for i, p in enumerate(plates):
+        assert np.array_equal(got[i:i + 1], pre.preprocess_for_sr(p)), sizes[i]
+    assert lpsr_b200.preprocess_for_sr_batch(m, []).shape == (0, 3, 32, 192)

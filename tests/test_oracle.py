@@ -140,3 +140,17 @@ def test_dconv_is_one_dense_conv(shipped_weights):
     dense_w = pw[:, :, 0, 0][:, :, None, None] * dw[:, 0][None]
     dense_b = pwb + pw[:, :, 0, 0] @ dwb
     assert np.abs(orc.conv2d(x, dense_w, dense_b) - ref).max() <= 1e-5
+
+
+def test_preprocess_oracle_matches_reference_golden(golden_dir):
+    """the oracle's restatement of Pillow's bicubic resample + BGR->RGB + ToTensor is bit-exact with the
+    reference's own library calls (tests/golden/make_golden_preprocess.py) on every fixture."""
+    import os
+    from oracle import preprocess_oracle as pre
+    d = np.load(os.path.join(golden_dir, "preprocess_cases.npz"))
+    n = sum(1 for k in d.files if k.startswith("in_"))
+    assert n >= 10
+    for i in range(n):
+        got = pre.preprocess_for_sr(d[f"in_{i}"])
+        assert got.dtype == np.float32 and got.shape == (1, 3, 32, 192)
+        assert np.array_equal(got, d[f"out_{i}"]), i
