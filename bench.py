@@ -117,6 +117,43 @@ def ncu_traffic():
     return json.load(open(p)) if os.path.exists(p) else None
 
 
+def preprocess_bench(model, dev, n=1024, with_cpu=True):
+    """SURVEY 8f row n1 (the step in front of the hot path): `preprocess_for_sr` (inference/run.py:80-96) batched on the device.
+    Times the whole public call (packing into pinned memory, one H2D copy, one kernel) over n synthetic BGR crops of ragged sizes,
+    and -- as the reported baseline -- the reference's own per-plate recipe (cv2 + Pillow + torchvision) on a bounded sample."""
+    import lpsr_b200
+    rng = np.random.default_rng(0)
+    plates = [rng.integers(0, 256, (int(rng.integers(16, 72)), int(rng.integers(60, 320)), 3), dtype=np.uint8) for _ in range(n)]
+    for _ in range(2):
+        lpsr_b200.preprocess_for_sr_batch(model, plates, device=dev)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        x = lpsr_b200.preprocess_for_sr_batch(model, plates, device=dev)
+    torch.cuda.synchronize(dev)
+    dt = (time.perf_counter() - t0) / reps
+    in_bytes = sum(p.size for p in plates)
+    out = {"value": n / dt, "unit": "crops/s", "ms_per_batch": 1e3 * dt, "batch": n, "h2d_bytes_per_batch": in_bytes,
+           "out_bytes_per_batch": int(x.numel() * 4), "api": "lpsr_b200.preprocess_for_sr_batch -> lpsr_preprocess_resize (C ABI)",
+           "parity": "bit-exact with cv2.cvtColor + PIL.Image.resize(BICUBIC) + ToTensor (tests/golden/preprocess_cases.npz)"}
+    if with_cpu:
+        try:
+            import cv2
+            import torchvision.transforms as T
+            from PIL import Image
+            tf = T.Compose([T.ToTensor()])
+            sample = plates[:128]
+            t0 = time.perf_counter()
+            for p in sample:
+                tf(Image.fromarray(cv2.cvtColor(p, cv2.COLOR_BGR2RGB)).resize((192, 32), Image.BICUBIC)).unsqueeze(0)
+            out["cpu_reference"] = {"value": len(sample) / (time.perf_counter() - t0), "unit": "crops/s", "cores": 1, "kind": "reference",
+                                    "sample": f"{len(sample)} crops, the reference's per-plate recipe (cv2 + Pillow + torchvision), host only"}
+        except Exception as exc:   # the libraries are optional on the GPU box
+            out["cpu_reference"] = {"unavailable": repr(exc)}
+    return out
+
+
 def load_shipped_weights():
     return dict(np.load(os.path.join(ROOT, "tests", "golden", "weights_best_model.npz")))
 
@@ -317,6 +354,8 @@ def run_ours(args):
            "api": "LPSR.forward_host -> lpsr_forward_host (C ABI, pinned host buffers)"}
     checksum = float(y_host.double().mean())
 
+    pre_stats = preprocess_bench(model, dev, with_cpu=not args.no_cpu_baseline) if rank == 0 and world == 1 else None
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_reference_run(args, steps=1000, warmup=1, sample_b=16, budget_s=args.cpu_budget)
@@ -331,7 +370,7 @@ def run_ours(args):
                 "conv_roofline_frac_whole_forward": conv_frac_whole,
                 "kernel_ms_per_forward": {k: round(v[0], 4) for k, v in per_kernel.items()},
                 "layer_ms_per_forward": {k: round(v, 4) for k, v in fam_ms.items()},
-                "cpu_baseline": cpu_base, "output_mean": checksum, "umma": os.environ.get("LPSR_UMMA", "1")}
+                "cpu_baseline": cpu_base, "preprocess": pre_stats, "output_mean": checksum, "umma": os.environ.get("LPSR_UMMA", "1")}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -70,10 +70,9 @@ def preprocess_for_sr_batch(model, plates, target_size=(192, 32), device=None) -
             raise ValueError("plates must be non-empty uint8 HxWx3 (BGR) arrays")
         hs.append(p.shape[0]); ws.append(p.shape[1]); offs.append(total)
         total += p.shape[0] * p.shape[1] * 3
-    packed = torch.empty(total, dtype=torch.uint8).pin_memory()
-    pk = packed.numpy()
-    for p, o in zip(plates, offs):
-        pk[o:o + p.size] = np.ascontiguousarray(p).reshape(-1)
+    # pinned staging from torch's caching host allocator (reuse is stream-ordered by the allocator itself)
+    packed = torch.empty(total, dtype=torch.uint8, pin_memory=True)
+    np.concatenate([np.ascontiguousarray(p).reshape(-1) for p in plates], out=packed.numpy())
     h = model._handle(dev)
     with torch.cuda.device(dev):
         crops = packed.to(dev, non_blocking=True)
