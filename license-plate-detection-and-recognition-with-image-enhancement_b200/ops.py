@@ -81,3 +81,18 @@ def preprocess_for_sr_batch(model, plates, target_size=(192, 32), device=None) -
                                               out.data_ptr(), _stream(out)), h, "lpsr_preprocess_resize")
         crops.record_stream(torch.cuda.current_stream(dev))
     return out
+
+
+def enhance_plates(model, plates, target_size=(192, 32)):
+    """The LPSR stage of the reference's per-plate loop (inference/run.py:200-203) for ALL plates of a frame / clip at once:
+    ``preprocess_for_sr`` -> ``sr_model(...)`` -> ``.squeeze(0).cpu().permute(1, 2, 0).numpy() * 255`` -> ``astype(np.uint8)``.
+    Returns a list of uint8 ``[H_t, W_t, 1]`` arrays (what the reference hands to its OCR step before the colour conversion), using one
+    packed H2D copy, one pre-processing launch, one forward and one uint8 D2H copy instead of a sync per plate."""
+    x = preprocess_for_sr_batch(model, plates, target_size)
+    if x.shape[0] == 0:
+        return []
+    with torch.no_grad():
+        y = model(x)
+    # numpy's float32 * 255 followed by astype(uint8) truncates toward zero; the sigmoid output is in (0, 1) so no wrap-around
+    u8 = (y * 255.0).to(torch.uint8).permute(0, 2, 3, 1).contiguous().cpu().numpy()
+    return [u8[i] for i in range(u8.shape[0])]

@@ -288,3 +288,22 @@ def test_preprocess_batch_bit_exact_with_reference(models):
     for i, p in enumerate(plates):
         assert np.array_equal(got[i:i + 1], pre.preprocess_for_sr(p)), sizes[i]
     assert lpsr_b200.preprocess_for_sr_batch(m, []).shape == (0, 3, 32, 192)
+
+
+def test_enhance_plates_matches_reference_stage(shipped_weights, models):
+    """SURVEY 8f row n2 (first slice): the whole LPSR stage of run.py:200-203 for a batch of ragged plates.  The reference recipe is
+    evaluated on CPU (pre-processing oracle + reference arithmetic + `* 255` + astype(uint8)); the pre-processing is bit-exact, the
+    forward differs by <= 1e-4 in fp32 mode, so after the truncating uint8 conversion at most a few pixels sit on the other side of
+    an integer boundary, and never by more than one level."""
+    from oracle import preprocess_oracle as pre
+    rng = np.random.default_rng(11)
+    plates = [rng.integers(0, 256, (int(rng.integers(12, 60)), int(rng.integers(40, 260)), 3), dtype=np.uint8) for _ in range(6)]
+    got = lpsr_b200.enhance_plates(models["fp32"], plates)
+    assert len(got) == 6 and all(g.shape == (32, 192, 1) and g.dtype == np.uint8 for g in got)
+    Wt = port.to_torch_weights(shipped_weights)
+    for p, g in zip(plates, got):
+        y = port.lpsr_forward(torch.from_numpy(pre.preprocess_for_sr(p)), Wt)
+        ref = (y.squeeze(0).permute(1, 2, 0).numpy() * 255).astype(np.uint8)
+        diff = np.abs(ref.astype(np.int32) - g.astype(np.int32))
+        assert diff.max() <= 1 and float((diff != 0).mean()) <= 0.01
+    assert lpsr_b200.enhance_plates(models["fp32"], []) == []
