@@ -19,13 +19,13 @@
 // Work decomposition: the image is cut into column strips of TW pixels (pitch = TW+2 with the halo columns); a work item
 // is k tiles of 128 (126 when folded) consecutive linear positions of one strip of one crop (1x1 convs: k*128 consecutive
 // pixels of the whole batch, 2-D tensor map).  Persistent CTAs (one per SM) loop over items; item buffers form a ring of
-// 2-4 so 50-130 KB of TMA loads are in flight per SM.  The MMA loop runs tile-outer / K-inner: G tile accumulators
-// (G x N fp32 TMEM columns) rotate between the MMA warp and G epilogue groups.
-// Warp roles ((4G+2) warps, G = kEpiGroups = 3 epilogue groups / TMEM tile accumulators):
-//     warps 0..4G-1   G epilogue groups (group g owns TMEM accumulator g; TMEM lane quadrant = warp id % 4):
-//                     tcgen05.ld, dx shifted sum, bias/ReLU/residual (or the CSAR gate), 16-byte stores
-//     warp  4G        MMA issuer: tcgen05.mma (M=128, N, K=16) from one elected lane, tcgen05.commit to mbarriers
-//     warp  4G+1      TMA producer: one elected lane arms the item's mbarrier (expect_tx) and issues the box copies
+// 2 so 50-100 KB of TMA loads are in flight per SM.  The MMA loop runs tile-outer / K-inner: G tile accumulators
+// (G x N fp32 TMEM columns), each with its own MMA warp and epilogue group.
+// Warp roles ((5G+1) warps, G = kEpiGroups = 3 epilogue groups / TMEM tile accumulators):
+//     warps 0..4G-1    G epilogue groups (group g owns TMEM accumulator g and walks the tiles t % G == g; TMEM lane quadrant =
+//                      warp id % 4): tcgen05.ld, dx shifted sum, compile-time epilogue variant, one 256-bit store per row and chunk
+//     warps 4G..5G-1   one MMA issuer per accumulator: tcgen05.mma (M=128, N, K=16) from one elected lane, tcgen05.commit to mbarriers
+//     warp  5G         TMA producer: one elected lane arms the item's mbarrier (expect_tx) and issues the box copies
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
