@@ -592,7 +592,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
     const int grp = warp >> 2, wq = warp & 3;                   // group == TMEM accumulator (0..G-1), wq == TMEM lane quadrant
     const int row = wq * 32 + lane;                             // accumulator row
     constexpr int CH = 16;                                      // output channels handled per pass (bounds registers)
-    constexpr int NRES = LFF ? kLffN * 2 / 16 : (NOUT <= 32 ? NOUT * 2 / 16 : 1);   // raw residual registers (uint4) prefetched per tile
+    // raw residual registers (uint4) prefetched per tile, before the accumulator wait
+    constexpr int NRES = (EPI == kEpiReluResidual && NOUT <= 48) ? NOUT * 2 / 16 : (NOUT <= 32 ? NOUT * 2 / 16 : 1);
     constexpr int NB = NOUT <= 32 ? NOUT : 1;
     T* out = static_cast<T*>(p.out);
     const T* res = static_cast<const T*>(p.res);
@@ -662,7 +663,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
         }
         // operands that do not depend on the accumulator are requested before waiting for it
         uint4 rsd_raw[NRES];                                    // raw 16-bit residual: converted only after the accumulator arrived
-        if constexpr (EPI == kEpiResidual && NOUT <= 32 && !LFF) {
+        if constexpr ((EPI == kEpiResidual && NOUT <= 32 && !LFF) || (EPI == kEpiReluResidual && NOUT <= 48)) {
           if (pix >= 0) {
 #pragma unroll
             for (int i = 0; i < NRES; ++i) rsd_raw[i] = *reinterpret_cast<const uint4*>(res + (size_t)pix * res_pitch + res_off + i * 8);
@@ -892,10 +893,16 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
 
             if constexpr (EPI == kEpiReluResidual) {
               if (valid) {
-                float r[CH];
-                load_vec<T, CH>(res + (size_t)pix * res_pitch + res_off + cc, r);
+                if constexpr (NOUT <= 48) {
+                  const T* re = reinterpret_cast<const T*>(rsd_raw) + cc;
 #pragma unroll
-                for (int c = 0; c < CH; ++c) v[c] = fmaxf(v[c], 0.f) + r[c];
+                  for (int c = 0; c < CH; ++c) v[c] = fmaxf(v[c], 0.f) + to_f32<T>(re[c]);
+                } else {
+                  float r[CH];
+                  load_vec<T, CH>(res + (size_t)pix * res_pitch + res_off + cc, r);
+#pragma unroll
+                  for (int c = 0; c < CH; ++c) v[c] = fmaxf(v[c], 0.f) + r[c];
+                }
               }
             }
             if constexpr (EPI == kEpiResidual) {
