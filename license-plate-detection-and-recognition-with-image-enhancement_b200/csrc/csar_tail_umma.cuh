@@ -146,40 +146,52 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
     const uint32_t ones_lo = umma_desc_lo(ptx::smem_u32(ones_s), 128 * 16);
     const uint32_t b3_lo = umma_desc_lo(ptx::smem_u32(b3_s), 64 * 16), b4_lo = umma_desc_lo(ptx::smem_u32(b4_s), 32 * 16),
                    bo_lo = umma_desc_lo(ptx::smem_u32(bo_s), 32 * 16), id_lo = umma_desc_lo(ptx::smem_u32(id_s), 32 * 16);
-    for (int base = 0; base < n_my; base += G) {
-      const uint32_t par = ((uint32_t)(base / G)) & 1u;
-#pragma unroll 1
-      for (int phase = 0; phase < 3; ++phase) {
-#pragma unroll 1
-        for (int s = 0; s < G && base + s < n_my; ++s) {
-          ptx::mbar_wait(bar(s, phase * 2), par);                          // a1_full / a2_ready / a3_ready
+    // Event driven: every slot walks its own tile sequence (slot s: tiles s, s+G, ...) through the three phases; the issuing thread polls
+    // the slots round robin and issues whatever is ready.  (A lock-step "phase p for all slots" loop drained the pipeline once per G
+    // tiles: ncu showed the epilogue warps 77 % of their time in long-scoreboard stalls on the h_full / s_full / o_full barriers.)
+    if (leader) {
+      int tile_s[G], phase_s[G];
+      uint32_t par_s[G];
+#pragma unroll
+      for (int s = 0; s < G; ++s) { tile_s[s] = s; phase_s[s] = 0; par_s[s] = 0; }
+      int remaining = n_my;
+      uint32_t idle = 0;
+      while (remaining > 0) {
+        bool progressed = false;
+#pragma unroll
+        for (int s = 0; s < G; ++s) {
+          if (tile_s[s] >= n_my) continue;
+          const int phase = phase_s[s];
+          if (!ptx::mbar_test_wait(bar(s, phase * 2), par_s[s])) continue;   // a1_full / a2_ready / a3_ready
           ptx::tc_fence_after();
-          if (leader) {
-            const uint32_t slot16 = ptx::smem_u32(slots + (size_t)s * kSlot) >> 4;
-            const uint32_t d = tmem_base + (uint32_t)(s * 64);     // 64 columns per slot: H, then S in [0,32) and O in [32,64)
-            if (phase == 0) {          // hid = b3 + x_in (128x32, swizzle-64B rows) * W3^T -> 64 columns
-              ptx::tc_mma_f16_lohi(d, ones_lo, kUmmaDescHi, b3_lo, kUmmaDescHi, idesc64, 0u);
+          const uint32_t slot16 = ptx::smem_u32(slots + (size_t)s * kSlot) >> 4;
+          const uint32_t d = tmem_base + (uint32_t)(s * 64);     // 64 columns per slot: H, then S in [0,32) and O in [32,64)
+          if (phase == 0) {          // hid = b3 + x_in (128x32, swizzle-64B rows) * W3^T -> 64 columns
+            ptx::tc_mma_f16_lohi(d, ones_lo, kUmmaDescHi, b3_lo, kUmmaDescHi, idesc64, 0u);
 #pragma unroll
-              for (int ks = 0; ks < 2; ++ks)
-                ptx::tc_mma_f16_lohi(d, (slot16 + 2u * ks) | (1u << 16), a1_hi, w3_lo + (uint32_t)(ks * 2 * 64), kUmmaDescHi, idesc64, 1u);
-            } else {                   // bias (+ residual * I) + 128x64 planar operand ([8 cg][128 rows][16 B]) * W^T -> 32 columns
-              const uint32_t a16 = slot16 + ((2 * kA1) >> 4);
-              const uint32_t w_lo = phase == 1 ? w4_lo : wo_lo;
-              const uint32_t dd = d + (phase == 1 ? 0u : 32u);
-              ptx::tc_mma_f16_lohi(dd, ones_lo, kUmmaDescHi, phase == 1 ? b4_lo : bo_lo, kUmmaDescHi, idesc32, 0u);
-              if (phase == 2) {
+            for (int ks = 0; ks < 2; ++ks)
+              ptx::tc_mma_f16_lohi(d, (slot16 + 2u * ks) | (1u << 16), a1_hi, w3_lo + (uint32_t)(ks * 2 * 64), kUmmaDescHi, idesc64, 1u);
+          } else {                   // bias (+ residual * I) + 128x64 planar operand ([8 cg][128 rows][16 B]) * W^T -> 32 columns
+            const uint32_t a16 = slot16 + ((2 * kA1) >> 4);
+            const uint32_t w_lo = phase == 1 ? w4_lo : wo_lo;
+            const uint32_t dd = d + (phase == 1 ? 0u : 32u);
+            ptx::tc_mma_f16_lohi(dd, ones_lo, kUmmaDescHi, phase == 1 ? b4_lo : bo_lo, kUmmaDescHi, idesc32, 0u);
+            if (phase == 2) {
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks)                             // + x: the residual tile (swizzle-64B rows) times the identity
-                  ptx::tc_mma_f16_lohi(dd, (slot16 + (kA1 >> 4) + 2u * ks) | (1u << 16), a1_hi, id_lo + (uint32_t)(ks * 2 * 32), kUmmaDescHi, idesc32, 1u);
-              }
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
-                ptx::tc_mma_f16_lohi(dd, (a16 + (uint32_t)(ks * 2 * 128)) | (128u << 16), kUmmaDescHi, w_lo + (uint32_t)(ks * 2 * 32), kUmmaDescHi, idesc32, 1u);
+              for (int ks = 0; ks < 2; ++ks)                             // + x: the residual tile (swizzle-64B rows) times the identity
+                ptx::tc_mma_f16_lohi(dd, (slot16 + (kA1 >> 4) + 2u * ks) | (1u << 16), a1_hi, id_lo + (uint32_t)(ks * 2 * 32), kUmmaDescHi, idesc32, 1u);
             }
-            ptx::tc_commit(bar(s, phase * 2 + 1));                         // h_full / s_full / o_full
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              ptx::tc_mma_f16_lohi(dd, (a16 + (uint32_t)(ks * 2 * 128)) | (128u << 16), kUmmaDescHi, w_lo + (uint32_t)(ks * 2 * 32), kUmmaDescHi, idesc32, 1u);
           }
-          __syncwarp();
+          ptx::tc_commit(bar(s, phase * 2 + 1));                         // h_full / s_full / o_full
+          progressed = true;
+          if (phase == 2) { phase_s[s] = 0; par_s[s] ^= 1u; tile_s[s] += G; --remaining; }
+          else phase_s[s] = phase + 1;
         }
+        if (progressed) idle = 0;
+        else if (++idle > (1u << 27)) __trap();                            // bounded: a protocol bug becomes a CUDA error
       }
     }
   } else {
