@@ -18,7 +18,8 @@
 namespace lpsr {
 
 constexpr int kTailGroups = 6;   // tile slots in flight (4 x 128 TMEM columns); one tile's three-phase chain is latency bound
-constexpr int kTailThreads = (4 * kTailGroups + 2) * 32;
+constexpr int kTailMmaWarps = 2;   // MMA issuers (slots s % 2): one thread issuing 15 MMAs per tile at ~70 clk each was the bottleneck
+constexpr int kTailThreads = (4 * kTailGroups + kTailMmaWarps + 1) * 32;
 
 struct TailUmmaParams {
   const void* x_in;            // [BP][32] dense
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
   ptx::griddep_wait();
   const int n_my = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
 
-  if (warp == 4 * G + 1) {
+  if (warp == 4 * G + kTailMmaWarps) {
     // =================================== TMA producer ==============================================
     if (ptx::elect_one()) {
       ptx::prefetch_tmap(&tm.m);
@@ -136,8 +137,8 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
         ptx::tma_load_2d(ptx::smem_u32(slots + (size_t)s * kSlot + kA1), &tm.r, bar(s, 0), p.res_off, (int)(tile * 128));
       }
     }
-  } else if (warp == 4 * G) {
-    // =================================== MMA issuer ================================================
+  } else if (warp >= 4 * G) {
+    // =================================== MMA issuers ================================================
     const bool leader = ptx::elect_one();
     constexpr uint32_t idesc64 = umma_idesc_f16(IsBf16<T>::value, 64), idesc32 = umma_idesc_f16(IsBf16<T>::value, 32);
     const uint32_t w3_lo = umma_desc_lo(ptx::smem_u32(w3_s), 64 * 16), w4_lo = umma_desc_lo(ptx::smem_u32(w4_s), 32 * 16),
@@ -154,13 +155,17 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
       uint32_t par_s[G];
 #pragma unroll
       for (int s = 0; s < G; ++s) { tile_s[s] = s; phase_s[s] = 0; par_s[s] = 0; }
-      int remaining = n_my;
+      const int mw = warp - 4 * G;                                // this warp issues for slots mw, mw + kTailMmaWarps, ...
+      int remaining = 0;
+#pragma unroll
+      for (int s = 0; s < G; ++s)
+        if (s % kTailMmaWarps == mw && s < n_my) remaining += (n_my - s + G - 1) / G;
       uint32_t idle = 0;
       while (remaining > 0) {
         bool progressed = false;
 #pragma unroll
         for (int s = 0; s < G; ++s) {
-          if (tile_s[s] >= n_my) continue;
+          if (s % kTailMmaWarps != mw || tile_s[s] >= n_my) continue;
           const int phase = phase_s[s];
           if (!ptx::mbar_test_wait(bar(s, phase * 2), par_s[s])) continue;   // a1_full / a2_ready / a3_ready
           ptx::tc_fence_after();
