@@ -400,6 +400,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
   int* slot_base_s = reinterpret_cast<int*>(steps + kUmmaMaxSteps);   // [R] written by the producer, read by the MMA warp
   // fused layer: per group a 4 KB K=16 operand, two planes of [128 rows][8 ch] (no-swizzle K-major: row stride 16 B, LBO = 2048 B)
   uint8_t* a2_all = reinterpret_cast<uint8_t*>(slot_base_s + 8);
+  // wide layers (N > 32): the bias vector lives in shared memory (broadcast LDS.128) -- per-chunk __ldg loads left the epilogue's
+  // FADDs waiting on L2 latency (ncu: long-scoreboard stalls on every bias add of the N = 128 shallowF1 kernel)
+  float* bias_s = reinterpret_cast<float*>(a2_all);            // same place as the fused layer's operands (that layer has N = 16)
   // fused layer: the additions of its two epilogue passes run on the tensor core (its pipe has slack, the epilogue warps do not): a
   // "ones" operand times {hi(bias), lo(bias)} starts the accumulator at the biases (b3 in the dx = 1 block, lff's in columns 48..79),
   // and x (chunk 0 of the staged block, centre tap) times a 32x32 identity adds the residual exactly.
@@ -412,6 +415,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
     const uint4* src = reinterpret_cast<const uint4*>(p.w);
     uint4* dst = reinterpret_cast<uint4*>(w_smem);
     for (uint32_t i = threadIdx.x; i < w_bytes / 16; i += kUmmaThreads) dst[i] = __ldg(src + i);
+  }
+  if constexpr (NOUT > 32) {
+    for (uint32_t i = threadIdx.x; i < (uint32_t)NOUT; i += kUmmaThreads) bias_s[i] = __ldg(p.bias + i);
   }
   if constexpr (LFF) {
     T* ones = reinterpret_cast<T*>(ones_s);
@@ -830,7 +836,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
           } else {
 #pragma unroll
             for (int c = 0; c < CH; c += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cc + c));
+              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + cc + c);
               v[c] += b4.x; v[c + 1] += b4.y; v[c + 2] += b4.z; v[c + 3] += b4.w;
             }
           }
@@ -1083,7 +1089,8 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
 #endif
   }
   const size_t w_bytes = ((size_t)ntap * w.cin * NMMA * 2 + (lff ? 2 * kLffN * 16 : 0) + 127) & ~(size_t)127;
-  const size_t a2_bytes = lff ? (size_t)kEpiGroups * 4096 + 2 * 128 * 16 + 2 * kLffCols * 16 + 4 * 32 * 16 : 0;   // g3 operands, ones, biases, identity
+  const size_t a2_bytes = lff ? (size_t)kEpiGroups * 4096 + 2 * 128 * 16 + 2 * kLffCols * 16 + 4 * 32 * 16   // g3 operands, ones, biases, identity
+                              : (N > 32 ? (size_t)N * 4 : 0);                                                   // wide layers: bias vector
   const size_t fixed = w_bytes + (2 * kUmmaMaxBufs + 4 * kEpiGroups + 2) * 8 + xch_bytes + a2_bytes + 640 /*steps, slot_base*/ + 1024 /*alignment slack*/ + 256;
   const size_t smem_cap = 227 * 1024 - fixed;
   auto item_buf_bytes = [&](size_t npx) {                      // every chunk is 1024-aligned inside the buffer
