@@ -61,15 +61,15 @@ def preprocess_for_sr_batch(model, plates, target_size=(192, 32), device=None) -
         raise RuntimeError("preprocess_for_sr_batch needs a CUDA device (there is no CPU fallback)")
     W_t, H_t = int(target_size[0]), int(target_size[1])
     B = len(plates)
-    out = torch.empty((B, 3, H_t, W_t), dtype=torch.float32, device=dev)
-    if B == 0:
-        return out
     hs, ws, offs, total = [], [], [], 0
     for p in plates:
-        if p.dtype != np.uint8 or p.ndim != 3 or p.shape[2] != 3 or p.shape[0] < 1 or p.shape[1] < 1:
+        if not isinstance(p, np.ndarray) or p.dtype != np.uint8 or p.ndim != 3 or p.shape[2] != 3 or p.shape[0] < 1 or p.shape[1] < 1:
             raise ValueError("plates must be non-empty uint8 HxWx3 (BGR) arrays")
         hs.append(p.shape[0]); ws.append(p.shape[1]); offs.append(total)
         total += p.shape[0] * p.shape[1] * 3
+    out = torch.empty((B, 3, H_t, W_t), dtype=torch.float32, device=dev)
+    if B == 0:
+        return out
     # pinned staging from torch's caching host allocator (reuse is stream-ordered by the allocator itself)
     packed = torch.empty(total, dtype=torch.uint8, pin_memory=True)
     np.concatenate([np.ascontiguousarray(p).reshape(-1) for p in plates], out=packed.numpy())

@@ -101,6 +101,17 @@ def test_cpu_input_fails_loudly_no_fallback():
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful on a box without a GPU")
+def test_preprocess_batch_fails_loudly_without_gpu_and_validates_inputs():
+    """the batched pre-processing has no CPU path either (the oracle is test-only), and rejects malformed crops."""
+    m = lpsr_b200.LPSR(3, 32, 16, 4, 4, None)
+    plate = np.zeros((20, 60, 3), dtype=np.uint8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        lpsr_b200.preprocess_for_sr_batch(m, [plate])
+    for bad in (np.zeros((20, 60), np.uint8), np.zeros((20, 60, 3), np.float32), np.zeros((0, 60, 3), np.uint8)):
+        with pytest.raises(ValueError):
+            lpsr_b200.preprocess_for_sr_batch(m, [bad], device="cuda:0")   # validated before any device work
+
+
 def test_create_without_gpu_reports_error_not_fallback():
     lib = lpsr_b200.capi.load_library()
     cfg = lpsr_b200.capi.LpsrConfig(1, 0, 3, 32, 16, 4, 4, 1, 0)
