@@ -138,3 +138,33 @@ def test_shard_bounds_cover_batch_exactly():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(G - 1))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_resample_weight_tables_match_oracle(tmp_path):
+    """Host logic of the pre-processing (csrc/preprocess.cuh: resample_coeffs = Pillow's precompute_coeffs + normalize_coeffs_8bpc) against
+    the oracle's restatement, without a GPU: a tiny nvcc-built host program prints the tables for several (in, out) sizes."""
+    import shutil
+    import subprocess
+    from oracle import preprocess_oracle as pre
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    cases = [(47, 192), (300, 192), (192, 192), (11, 32), (100, 32), (1, 32), (5, 192), (960, 192)]
+    src = tmp_path / "coeffs.cu"
+    csrc = os.path.join(ROOT, "license-plate-detection-and-recognition-with-image-enhancement_b200", "csrc")
+    body = "".join(f"  dump({a}, {b});\n" for a, b in cases)
+    src.write_text('#include <cstdio>\n#include "preprocess.cuh"\n'
+                   'static void dump(int in, int out) { std::vector<int> t; int b, k, ks; lpsr::resample_coeffs(in, out, t, b, k, ks);\n'
+                   '  printf("%d %d %d", in, out, ks); for (int v : t) printf(" %d", v); printf("\\n"); }\n'
+                   f'int main() {{\n{body}  return 0; }}\n')
+    exe = tmp_path / "coeffs"
+    subprocess.run([nvcc, "-I", csrc, "-o", str(exe), str(src)], check=True, capture_output=True)
+    lines = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    assert len(lines) == len(cases)
+    for line, (a, b) in zip(lines, cases):
+        vals = [int(v) for v in line.split()]
+        assert vals[:2] == [a, b]
+        bounds, kk = pre.precompute_coeffs(a, b)
+        assert vals[2] == kk.shape[1]
+        assert vals[3:3 + 2 * b] == bounds.reshape(-1).tolist()
+        assert vals[3 + 2 * b:] == kk.reshape(-1).tolist()
