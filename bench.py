@@ -6,10 +6,13 @@
         bench.py --gpus N --steps K --warmup W
     python bench.py --impl reference ...        # the reference arithmetic on the box's host cores (torch CPU port)
 
-A step = one LPSR forward over one batch of B synthetic crops per GPU (weak scaling: per-GPU batch fixed, the path
-shards by batch with no data-path collective).  `value` = crops/s with inputs resident in HBM; `e2e` = the
-same metric through the C-ABI host-buffer call (lpsr_forward_host: pinned H2D + forward + D2H inside the timed region).
-Prints ONE JSON line on rank 0.
+A step = one LPSR forward over one batch of B synthetic crops per GPU PLUS (N > 1) the one collective of the path, the NCCL
+all-gather of the fp32 outputs over NVLink, inside the timed region.  Default = weak scaling (per-GPU batch
+fixed at 1024); `--scaling strong` runs BASELINE configs[2] as written (global batch 1024, 1024/N crops per GPU); the
+default line also carries the strong-scaling measurement of the same run under `strong_scaling`.  `value` = crops/s with
+inputs resident in HBM; `e2e` = the same metric through the C-ABI host-buffer call (lpsr_forward_host: pinned H2D +
+forward + D2H inside the timed region).  The default 16-bit mode is fp16: it is the one that meets the 1e-2 bound on
+smooth crops (tests/test_gpu_parity.py); bf16 is kept as a switch.  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -113,8 +116,13 @@ class ClockSampler:
 def ncu_traffic():
     """DRAM bytes per forward of the tensor-core conv launches / CSAR tail launches from the committed `ncu --set full`
     capture (profiles/r1_ncu_traffic.json, written by tools/ncu_traffic.py); scaled linearly with the batch."""
-    p = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
-    return json.load(open(p)) if os.path.exists(p) else None
+    for name in ("r2_ncu_traffic.json", "r1_ncu_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            d = json.load(open(p))
+            d["source"] = f"profiles/{name}"
+            return d
+    return None
 
 
 def preprocess_bench(model, dev, n=1024, with_cpu=True):
@@ -205,15 +213,134 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, batch, precision, note=None):
+def workload_config(args, batch, precision, note=None, scaling="weak"):
+    gb = batch * args.gpus
     cfg = {"workload": f"LPSR forward {precision}, batch {batch} of 3x{args.height}x{args.width} synthetic crops per GPU "
-                       f"(BASELINE.json configs[2])", "per_gpu_batch": batch, "global_batch": batch * args.gpus,
+                       f"(BASELINE.json configs[2]{', global batch 1024 sharded 1024/N' if scaling == 'strong' else ''})",
+           "per_gpu_batch": batch, "global_batch": gb,
            "crop": [3, args.height, args.width], "precision": precision, "weights": "reference best_model.pth (fixture)",
-           "parallelism": f"batch-sharded x{args.gpus}, replicated weights, no per-layer collective",
+           "parallelism": f"batch-sharded x{args.gpus}, replicated weights, no per-layer collective; the one NCCL all-gather of the "
+                          f"fp32 outputs is inside the timed region (side stream, overlapping the next forward)",
            "l2": "inputs (151 MB/step at B=1024) and activations (GBs) exceed the 126 MB L2; no explicit flush"}
     if note:
         cfg["note"] = note
     return cfg
+
+
+def pin_to_gpu_numa(local_rank: int):
+    """Pin this process (and the pinned buffers it is about to first-touch) to the CPUs of its GPU's NUMA node: with 8 ranks each
+    moving ~200 MB per step between pinned host memory and its GPU, cross-socket traffic is what limited e2e scaling (round 1: 0.88)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return {"numa_node": node, "pinned": False}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"numa_node": node, "pinned": True, "cpus": len(cpus)}
+        return {"numa_node": node, "pinned": False}
+    except Exception as exc:   # best effort: single-socket boxes, containers without /sys
+        return {"pinned": False, "why": repr(exc)[:80]}
+
+
+def timed_loop(dev, steps, step_fn, finish_fn, barrier, max_over_ranks):
+    """EXACTLY `steps` calls of step_fn bracketed by barrier + synchronize; device time by CUDA events, max over ranks."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        step_fn()
+    finish_fn()
+    e1.record()
+    barrier()
+    return max_over_ranks(e0.elapsed_time(e1))
+
+
+def context_baselines(args, dev, model_factory, rank0_weights):
+    """Reported context, not targets: the reference arithmetic run by PyTorch eager + cuDNN on this same B200
+    (TF32 on, PyTorch's default, and off), this library at BASELINE configs[3] (3x128x384) and at the call-site shape B=1 32x192
+    (stream launches and CUDA-graph replay), and the fp32 mode at configs[1]."""
+    out = {}
+    from oracle import lpsr_torch_port as port   # context baseline = the reference arithmetic through ATen/cuDNN on the GPU
+
+    def ev_time(fn, n, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / n
+
+    try:
+        Wg = {k: v.to(dev) for k, v in port.to_torch_weights(rank0_weights).items()}
+        xb = torch.rand(256, 3, 64, 192, device=dev)
+        x1 = torch.rand(1, 3, 32, 192, device=dev)
+        eager = {}
+        for tf32 in (True, False):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            ms = ev_time(lambda: port.lpsr_forward(xb, Wg), 5)
+            ms1 = ev_time(lambda: port.lpsr_forward(x1, Wg), 20)
+            eager["tf32_on" if tf32 else "tf32_off"] = {"crops_per_s_b256_64x192": 256 / (ms * 1e-3), "ms_b256": ms, "latency_us_b1_32x192": 1e3 * ms1}
+        torch.backends.cudnn.allow_tf32 = True
+        torch.backends.cuda.matmul.allow_tf32 = True
+        eager["what"] = ("reference graph (oracle/lpsr_torch_port.py: the same ATen ops in the same order as my_models/lpsr.py) in PyTorch "
+                         f"eager + cuDNN, fp32 NCHW, torch {torch.__version__}, same GPU")
+        out["eager_cudnn"] = eager
+        del Wg, xb
+    except Exception as exc:
+        out["eager_cudnn"] = {"unavailable": repr(exc)[:200]}
+    pk = peaks()
+    try:   # BASELINE configs[3]: 3x128x384 (activation-bandwidth stress), B = 256 (equal pixels to 1024 x 64x192)
+        m = model_factory(args.precision)
+        x4 = torch.rand(256, 3, 128, 384, device=dev)
+        ms = ev_time(lambda: m(x4), 5)
+        cps = 256 / (ms * 1e-3)
+        out["config4_128x384_b256"] = {"crops_per_s": cps, "ms_per_step": ms, "precision": args.precision,
+                                       "conv_roofline_frac_burst": cps * 128 * 384 * DENSE_FLOP_PER_PIXEL / 1e12 / pk["tf_burst"],
+                                       "launches": m.launch_count(256, 128, 384)}
+        del x4
+        # call-site shape: batch 1 of 3x32x192 (inference/run.py:200-202)
+        x1 = torch.rand(1, 3, 32, 192, device=dev)
+        lat = {"stream_launches_us": 1e3 * ev_time(lambda: m(x1), 50)}
+        sgraph = torch.cuda.Stream(dev)
+        with torch.cuda.stream(sgraph):
+            m(x1)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=sgraph):
+            m(x1)
+        lat["graph_replay_us"] = 1e3 * ev_time(g.replay, 50)
+        lat["launches"] = m.launch_count(1, 32, 192)
+        out["latency_b1_32x192"] = lat
+        del g
+    except Exception as exc:
+        out["config4_or_latency_error"] = repr(exc)[:200]
+    try:   # BASELINE configs[1]: fp32 mode, B = 256
+        m32 = model_factory("fp32")
+        xb = torch.rand(256, 3, 64, 192, device=dev)
+        ms = ev_time(lambda: m32(xb), 3, warm=2)
+        out["config2_fp32_b256"] = {"crops_per_s": 256 / (ms * 1e-3), "ms_per_step": ms,
+                                    "conv_roofline_frac_burst": 256 / (ms * 1e-3) * 64 * 192 * DENSE_FLOP_PER_PIXEL / 1e12 / pk["tf_burst"]}
+    except Exception as exc:
+        out["config2_error"] = repr(exc)[:200]
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -226,16 +353,25 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = pin_to_gpu_numa(local) if world > 1 or args.pin_numa else {"pinned": False, "why": "single process"}
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    B, H, Wd = args.batch, args.height, args.width
+    strong = args.scaling == "strong"
+    B_weak = args.batch
+    B_strong = max(1, args.batch // world)
+    B, H, Wd = (B_strong if strong else B_weak), args.height, args.width
+    Hp, Wp = (H + 3) // 4 * 4, (Wd + 3) // 4 * 4
+    weights = load_shipped_weights()
 
-    model = lpsr_b200.LPSR(3, 32, 16, 4, 4, None, precision=args.precision)
-    model.load_live_weights(load_shipped_weights())
-    model = model.to(dev).eval()
+    def model_factory(precision):
+        m = lpsr_b200.LPSR(3, 32, 16, 4, 4, None, precision=precision)
+        m.load_live_weights(weights)
+        return m.to(dev).eval()
+
+    model = model_factory(args.precision)
     g = torch.Generator().manual_seed(1000 + rank)
     x_host = torch.rand(B, 3, H, Wd, generator=g).pin_memory()
     x = x_host.to(dev)
@@ -254,23 +390,70 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---------------- device-resident throughput -------------------------------------------------------
+    main_stream = torch.cuda.current_stream(dev)
+    side = torch.cuda.Stream(dev) if world > 1 else None
+
+    def make_step(xs):
+        """forward of this rank's shard + (N > 1) the all-gather of the outputs on a side stream (overlaps the next forward)."""
+        bs = xs.shape[0]
+        full = torch.empty((world * bs, 1, Hp, Wp), dtype=torch.float32, device=dev) if world > 1 else None
+        state = {"y": None}
+
+        def step():
+            y = model(xs)
+            if world > 1:
+                side.wait_stream(main_stream)
+                with torch.cuda.stream(side):
+                    dist.all_gather_into_tensor(full, y)
+                y.record_stream(side)
+            state["y"] = y
+
+        def finish():
+            if world > 1:
+                main_stream.wait_stream(side)
+
+        return step, finish, state, full
+
+    # ---------------- device-resident throughput: forward (+ gather) ---------------------------------------------------
+    step, finish, state, full = make_step(x)
     for _ in range(max(args.warmup, 3)):
-        y = model(x)
+        step()
+    finish()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        y = model(x)
-    e1.record()
-    barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_total = timed_loop(dev, args.steps, step, finish, barrier, max_over_ranks)
     clocks = sampler.stop()
+    y = state["y"]
     ms_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total * 1e-3)
+
+    gather = None
+    other_scaling = None
+    if world > 1:
+        # the collective alone (same buffers): bytes and time reported separately
+        yg = y
+        def gstep():
+            dist.all_gather_into_tensor(full, yg)
+        for _ in range(3):
+            gstep()
+        g_ms = timed_loop(dev, args.steps, gstep, lambda: None, barrier, max_over_ranks) / args.steps
+        nb = yg.numel() * 4
+        gather = {"collective": "ncclAllGather (torch.distributed.all_gather_into_tensor) of the fp32 [B/G,1,H,W] outputs",
+                  "bytes_sent_per_rank": nb, "bytes_received_per_rank": nb * (world - 1), "ms_alone": g_ms,
+                  "algbw_GBps": nb * world / (g_ms * 1e-3) / 1e9, "in_timed_region": True, "overlap": "side stream, under the next forward"}
+        # the other scaling mode, same process: strong = BASELINE configs[2] as written (global 1024, 1024/N per GPU)
+        Bo = B_weak if strong else B_strong
+        xo = torch.rand(Bo, 3, H, Wd, generator=torch.Generator().manual_seed(2000 + rank)).to(dev)
+        ostep, ofinish, _, _ = make_step(xo)
+        for _ in range(3):
+            ostep()
+        ofinish()
+        o_ms = timed_loop(dev, args.steps, ostep, ofinish, barrier, max_over_ranks)
+        other_scaling = {"scaling": "weak" if strong else "strong", "per_gpu_batch": Bo, "global_batch": Bo * world,
+                         "value": world * Bo * args.steps / (o_ms * 1e-3), "unit": UNIT, "ms_per_step": o_ms / args.steps,
+                         "launches_per_step": model.launch_count(Bo, H, Wd), "gather_in_timed_region": True}
+        del xo
 
     # ---------------- per-kernel device times (CUDA events between launches, same stream) --------------------------
     lib = capi.load_library()
@@ -290,56 +473,69 @@ def run_ours(args):
         for i, name in enumerate(names):
             fam_ms[name] = fam_ms.get(name, 0.0) + ms[i] / n_prof
     pk = peaks()
-    P = ((H + 3) // 4 * 4) * ((Wd + 3) // 4 * 4)
+    P = Hp * Wp
     per_kernel = {}
     for name, t in fam_ms.items():
         kind = name.split(":")[1]
         per_kernel.setdefault(kind, [0.0, 0])
         per_kernel[kind][0] += t
         per_kernel[kind][1] += names.count(name)
-    is_umma = lambda n_: n_.split(":")[1].startswith("umma_conv") or n_.endswith(":csar_tail_umma")
-    umma_ms = sum(t for n_, t in fam_ms.items() if is_umma(n_))
-    umma_tags = {n_.split(":")[0] for n_ in names if is_umma(n_)}
-    umma_flops = 2.0 * B * P * sum(v for k, v in UMMA_MAC_PER_PIXEL.items() if k in umma_tags)
-    n_umma = sum(1 for n_ in names if is_umma(n_))
+    # the dominant kernel family: the tcgen05 implicit-GEMM convolutions (umma_conv_kernel instantiations + the fused RDB chain);
+    # the CSAR tail kernel (also tcgen05, HBM bound) is reported separately under roofline_csar
+    is_conv = lambda n_: n_.split(":")[1].startswith(("umma_conv", "rdb_chain"))
+    is_tail = lambda n_: ".tail:" in n_
+    conv_ms = sum(t for n_, t in fam_ms.items() if is_conv(n_))
+    conv_tags = {n_.split(":")[0] for n_ in names if is_conv(n_)}
+    # SURVEY 8(d) numerator: DENSE-conv FLOPs only (depthwise and linear arithmetic excluded); the AutoEncoder's pointwise 1x1s
+    # are the dense part of its DConvs
+    dense_mac = dict(UMMA_MAC_PER_PIXEL)
+    dense_mac.update({"ae.enc0": 12 * 12, "ae.enc1": 48 * 12 / 4, "ae.dec0": 48 * 48 / 16, "ae.dec1": 12 * 48 / 4})
+    conv_flops = 2.0 * B * P * sum(v for k, v in dense_mac.items() if k in conv_tags and not k.endswith(".tail"))
+    n_conv = sum(1 for n_ in names if is_conv(n_))
     esz = 4 if args.precision == "fp32" else 2
-    # CSAR tail = everything after conv_in: pooling, channel gate, spatial MLP, gating, conv_out, residual
-    tail_ms = sum(t for n_, t in fam_ms.items() if ".tail:" in n_)
-    n_tail = sum(1 for n_ in names if ".tail:" in n_)
+    tail_ms = sum(t for n_, t in fam_ms.items() if is_tail(n_))
+    n_tail = sum(1 for n_ in names if is_tail(n_))
     tail_bytes = 2.0 * B * P * CSAR_TAIL_ELEMS_PER_PIXEL * esz
     total_prof_ms = sum(fam_ms.values())
     tr = ncu_traffic()
     scale = (B * P) / float(tr["batch"] * tr["pixels_per_crop"]) if tr else 0.0
-    if n_umma:
-        ach = umma_flops / (umma_ms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "kernel": f"umma_conv_kernel (tcgen05 implicit-GEMM conv, {n_umma} launches/forward)",
-                    "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                    "peak_kind": f"bf16 dense sustained, of {pk['src']}",
+    if n_conv:
+        ach = conv_flops / (conv_ms * 1e-3) / 1e12
+        kinds = sorted({n_.split(":")[1] for n_ in names if is_conv(n_)})
+        roofline = {"bound": "tensor", "kernel": f"tcgen05 implicit-GEMM convolutions ({', '.join(kinds)}; {n_conv} launches/forward)",
+                    "achieved": ach, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"],
+                    "peak_kind": f"bf16 dense BURST (timed region {ms_total:.0f} ms), of {pk['src']}",
+                    "frac_vs_sustained": ach / pk["tf_sustained"], "peak_sustained": pk["tf_sustained"],
                     "traffic": (tr["umma_dram_bytes_per_forward"] * scale) if tr else None,
-                    "traffic_note": "sum of dram__bytes_read+write over the family's launches of one forward (ncu --set full, profiles/), scaled to this batch",
-                    "algorithmic_flops_per_forward": umma_flops, "kernel_ms_per_forward": umma_ms,
-                    "share_of_step": umma_ms / total_prof_ms}
+                    "traffic_note": (f"sum of dram__bytes_read+write over the family's launches of one forward (ncu --set full, {tr['source']}), "
+                                     "scaled to this batch; not measured in this run") if tr else None,
+                    "algorithmic_flops_per_forward": conv_flops,
+                    "algorithmic_note": "SURVEY 8(d) dense-conv FLOPs of the layers this family executes (CSAR tail 1x1s excluded: roofline_csar)",
+                    "kernel_ms_per_forward": conv_ms, "share_of_step": conv_ms / total_prof_ms}
     else:   # fp32 mode: FFMA direct convolution dominates; still reported against the bf16 tensor peak
         d_ms = sum(t for n_, t in fam_ms.items() if n_.endswith(":conv_direct"))
         fl = 2.0 * B * P * (DENSE_FLOP_PER_PIXEL / 2 - 12288)
         ach = fl / (d_ms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "kernel": "conv_direct_kernel (FFMA, fp32 parity mode)", "achieved": ach, "peak": pk["tf_sustained"],
-                    "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"], "peak_kind": f"bf16 dense sustained, of {pk['src']}",
-                    "traffic": None, "share_of_step": d_ms / total_prof_ms}
-    roofline_csar = {"bound": "hbm", "kernel": f"CSAR tail (pool + channel gate + spatial MLP + gating + conv_out + residual; {n_tail} launches/forward)", "achieved": tail_bytes / (tail_ms * 1e-3) / 1e9,
-                     "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": tail_bytes / (tail_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+        roofline = {"bound": "tensor", "kernel": "conv_direct_kernel (FFMA, fp32 parity mode)", "achieved": ach, "peak": pk["tf_burst"],
+                    "unit": "TFLOP/s", "frac": ach / pk["tf_burst"], "peak_kind": f"bf16 dense burst, of {pk['src']}",
+                    "frac_vs_sustained": ach / pk["tf_sustained"], "traffic": None, "share_of_step": d_ms / total_prof_ms}
+    roofline_csar = {"bound": "hbm", "kernel": f"CSAR tail (csar_tail_umma_kernel + channel_gate_kernel: pool finalize + channel gate + spatial MLP + gating + conv_out + residual; {n_tail} launches/forward)",
+                     "achieved": tail_bytes / (tail_ms * 1e-3) / 1e9 if tail_ms else None,
+                     "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": (tail_bytes / (tail_ms * 1e-3) / 1e9 / pk["hbm_gbs"]) if tail_ms else None,
                      "peak_kind": f"copy bandwidth, of {pk['src']}", "traffic": (tr["tail_dram_bytes_per_forward"] * scale) if tr else None,
                      "algorithmic_bytes_per_forward": tail_bytes, "kernel_ms_per_forward": tail_ms}
-    conv_frac_whole = value / world * P * DENSE_FLOP_PER_PIXEL / 1e12 / pk["tf_sustained"]
+    whole = value / world * P * DENSE_FLOP_PER_PIXEL / 1e12
+    conv_frac_whole = {"achieved_tflops": whole, "frac_burst": whole / pk["tf_burst"], "frac_sustained": whole / pk["tf_sustained"],
+                       "note": "whole-step rate x 297,104 dense FLOP/px (SURVEY 8d) per GPU; the north-star target is 0.50 of burst"}
     lw_bytes = float(B) * P * LAYERWISE_ELEMS_PER_PIXEL * esz
     roofline_layerwise = {"bound": "hbm", "kernel": "whole forward, layer-by-layer activation traffic of the reference graph",
                           "achieved": lw_bytes / (ms_step * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                           "frac": lw_bytes / (ms_step * 1e-3) / 1e9 / pk["hbm_gbs"], "peak_kind": f"copy bandwidth, of {pk['src']}",
                           "algorithmic_bytes_per_forward": lw_bytes,
-                          "note": "fused kernels move fewer bytes than this; > 1.0 would mean the layer-by-layer HBM bound is beaten"}
+                          "note": "fused kernels move fewer bytes than this; > 1.0 means the layer-by-layer HBM bound is beaten"}
 
     # ---------------- end to end through the C-ABI host-buffer call --------------------------------------------------
-    y_host = torch.empty((B, 1, (H + 3) // 4 * 4, (Wd + 3) // 4 * 4), dtype=torch.float32).pin_memory()
+    y_host = torch.empty((B, 1, Hp, Wp), dtype=torch.float32).pin_memory()
     for _ in range(2):
         model.forward_host(x_host, out=y_host, device=local)
     barrier()
@@ -351,26 +547,31 @@ def run_ours(args):
     barrier()
     e2e = {"value": world * B * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
            "d2h_bytes_per_step": y_host.numel() * 4, "ms_per_step": 1e3 * e2e_s / args.steps,
-           "api": "LPSR.forward_host -> lpsr_forward_host (C ABI, pinned host buffers)"}
+           "api": "LPSR.forward_host -> lpsr_forward_host (C ABI, pinned host buffers)", "numa": numa}
     checksum = float(y_host.double().mean())
 
-    pre_stats = preprocess_bench(model, dev, with_cpu=not args.no_cpu_baseline) if rank == 0 and world == 1 else None
+    extras = rank == 0 and world == 1 and not args.no_extras
+    pre_stats = preprocess_bench(model, dev, with_cpu=not args.no_cpu_baseline) if extras else None
+    ctx_base = context_baselines(args, dev, model_factory, weights) if extras else None
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_reference_run(args, steps=1000, warmup=1, sample_b=16, budget_s=args.cpu_budget)
         cpu_base = {k: cpu_base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu_base["note"] = "B=16 fp32 on the host cores vs this arm's batch: crops/s is a per-crop rate, so the two are comparable"
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[args.precision], "data": "synthetic",
-                "config": workload_config(args, B, args.precision), "clocks": clocks, "e2e": e2e, "gpu_launches": launches * args.steps,
-                "launches_per_step": launches, "roofline": roofline, "roofline_csar": roofline_csar, "roofline_layerwise_hbm": roofline_layerwise,
-                "conv_roofline_frac_whole_forward": conv_frac_whole,
+                "config": workload_config(args, B, args.precision, scaling=args.scaling), "clocks": clocks, "e2e": e2e,
+                "gpu_launches": launches * args.steps, "launches_per_step": launches, "roofline": roofline, "roofline_csar": roofline_csar,
+                "roofline_layerwise_hbm": roofline_layerwise, "conv_roofline_whole_forward": conv_frac_whole,
                 "kernel_ms_per_forward": {k: round(v[0], 4) for k, v in per_kernel.items()},
                 "layer_ms_per_forward": {k: round(v, 4) for k, v in fam_ms.items()},
-                "cpu_baseline": cpu_base, "preprocess": pre_stats, "output_mean": checksum, "umma": os.environ.get("LPSR_UMMA", "1")}
+                "gather": gather, ("weak_scaling" if strong else "strong_scaling"): other_scaling,
+                "cpu_baseline": cpu_base, "context_baselines": ctx_base, "preprocess": pre_stats, "output_mean": checksum,
+                "umma": os.environ.get("LPSR_UMMA", "1")}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -382,8 +583,13 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("LPSR_BENCH_PRECISION", "bf16"), choices=["bf16", "fp16", "fp32"])
-    ap.add_argument("--batch", type=int, default=1024, help="crops per GPU per step")
+    # fp16 is the 16-bit mode that meets the 1e-2 parity bound on smooth crops with the trained checkpoint (tests/test_gpu_parity.py)
+    ap.add_argument("--precision", default=os.environ.get("LPSR_BENCH_PRECISION", "fp16"), choices=["bf16", "fp16", "fp32"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch crops per GPU; strong: --batch crops in total, batch/N per GPU (BASELINE configs[2] as written)")
+    ap.add_argument("--no-extras", action="store_true", help="skip context baselines / config 4 / B=1 latency / preprocess lines")
+    ap.add_argument("--pin-numa", action="store_true", help="pin to the GPU's NUMA node even at N=1")
+    ap.add_argument("--batch", type=int, default=1024, help="crops per GPU per step (weak) or in total (strong)")
     ap.add_argument("--height", type=int, default=64)
     ap.add_argument("--width", type=int, default=192)
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")

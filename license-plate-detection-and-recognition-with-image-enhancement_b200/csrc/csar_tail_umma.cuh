@@ -260,16 +260,12 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
           for (int j = 0; j < 4; ++j) {
             const float x = to_f32<T>(xe[c + j]);
             const float zh = v[c + j];                                       // (W4 hid + b4) / 2, bias and halving done by the MMA
-            float sg;
-            if constexpr (IsBf16<T>::value) {
-              // logistic through one MUFU: 0.5 + 0.5 * tanh(z / 2); tanh.approx's 2^-11 error is below the bf16 rounding of the product
-              float th;
-              asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(zh));
-              sg = fmaf(0.5f, th, 0.5f);
-            } else {
-              sg = __fdividef(1.f, 1.f + __expf(-2.f * zh));
-            }
-            ga[c + j] = x * (x * ss4[j]);                                    // channel branch x_in^2 * s_c (lpsr.py:133-135)
+            // logistic through one MUFU: 0.5 + 0.5 * tanh(z / 2); tanh.approx's 2^-11 error (2^-12 on the logistic) is at the level of
+            // the 16-bit rounding of the product in both modes (bf16 2^-9, fp16 2^-12 relative)
+            float th;
+            asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(zh));
+            const float sg = fmaf(0.5f, th, 0.5f);
+            ga[c + j] = x * (x * ss4[j]);                                    // channel branch x_in^2 * s_c / 16 (lpsr.py:133-135; kCsarChanScale)
             v[c + j] = x * sg;                                               // spatial branch x_in * s_s  (lpsr.py:150-153)
           }
         }
@@ -322,11 +318,12 @@ inline const char* csar_tail_umma_launch(const TailUmmaParams& pin, bool fp16, i
   constexpr size_t kSlot = 2 * 128 * 64 + 128 * 128;
   const size_t smem = 1024 + kTailGroups * kSlot + 32 * 64 * 2 + 2 * 64 * 32 * 2 + (2 * 128 + 2 * 64 + 2 * 32 + 2 * 32 + 4 * 32) * 16 +
                       (7 * kTailGroups + 2) * 8 + 64;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};
+  bool* flag = func_configured_flag(configured);
+  if (!flag || !*flag) {
     cudaError_t e = cudaFuncSetAttribute(csar_tail_umma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return cudaGetErrorString(e);
-    configured = true;
+    if (flag) *flag = true;
   }
   cudaError_t e = launch_pdl(csar_tail_umma_kernel<T>, dim3(std::min(p.n_tiles, num_sms)), dim3(kTailThreads), smem, st, p, tm);
   if (e == cudaSuccess) e = cudaGetLastError();

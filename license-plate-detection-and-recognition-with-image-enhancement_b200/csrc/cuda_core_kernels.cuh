@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(kThreads) gap_partial_kernel(const T* __restri
 // ---------------------------------------------------------------------------------------------------
 static __global__ void __launch_bounds__(256) channel_gate_kernel(const float* __restrict__ partial, int S, int P, const float* __restrict__ w1,
                                                            const float* __restrict__ b1, const float* __restrict__ w2,
-                                                           const float* __restrict__ b2, float* __restrict__ s_c) {
+                                                           const float* __restrict__ b2, float* __restrict__ s_c, float out_scale) {
   __shared__ float s_part[8][32], s_mean[32], s_hid[8];
   asm volatile("griddepcontrol.wait;" ::: "memory");   // programmatic dependent launch (see umma_conv.cuh)
   const int b = blockIdx.x, c = threadIdx.x & 31, wv = threadIdx.x >> 5;
@@ -452,7 +452,7 @@ static __global__ void __launch_bounds__(256) channel_gate_kernel(const float* _
   __syncwarp();
   float g = __ldg(b2 + c);
   for (int j = 0; j < 8; ++j) g = fmaf(s_hid[j], __ldg(w2 + c * 8 + j), g);
-  s_c[(size_t)b * 32 + c] = sigmoid_f32(g);
+  s_c[(size_t)b * 32 + c] = out_scale * sigmoid_f32(g);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -357,6 +357,15 @@ int pack_all(lpsr_handle* h) {
   ok &= pack_conv(h, h->csar_sa1, "rdn.csar.sa.block.0", F, 2 * F, 1, true);    // tensor-core CSAR tail (16-bit modes)
   ok &= pack_conv(h, h->csar_sa2, "rdn.csar.sa.block.2", 2 * F, F, 1, true);
   ok &= pack_conv(h, h->csar_co, "rdn.csar.conv_out", 2 * F, F, 1, true);
+  if (half_mode(h) && h->csar_co.u.packed) {
+    // tensor-core packing only: input columns [0, F) (channel branch) x kCsarChanScale; the channel gate kernel writes s_c / kCsarChanScale
+    const std::vector<float>& w = W(h, "rdn.csar.conv_out.weight");   // [F][2F]
+    std::vector<float> pw((size_t)2 * F * F);
+    for (int co = 0; co < F; ++co)
+      for (int ci = 0; ci < 2 * F; ++ci) pw[(size_t)ci * F + co] = (ci < F ? kCsarChanScale : 1.f) * w[(size_t)co * 2 * F + ci];
+    ok &= umma_pack_weights(h->csar_co.u, pw.data(), W(h, "rdn.csar.conv_out.bias").data(), 1, 2 * F, F, h->cfg.precision == LPSR_PREC_FP16,
+                            [&](const std::vector<uint16_t>& v) { return arena_put(h, v); }, [&](const std::vector<float>& v) { return arena_put(h, v); });
+  }
   h->ca_w1 = arena_put(h, W(h, "rdn.csar.ca.block.2.weight"));
   h->ca_b1 = arena_put(h, W(h, "rdn.csar.ca.block.2.bias"));
   h->ca_w2 = arena_put(h, W(h, "rdn.csar.ca.block.4.weight"));
@@ -719,7 +728,13 @@ int lpsr_forward_host(lpsr_handle* h, const float* x_host, float* y_host, int32_
     CUDA_TRY(h, cudaStreamWaitEvent(cs, h->host_ev[2 * i], 0));
     rc = lpsr_forward(h, reinterpret_cast<const float*>(dx + x_crop * lo), reinterpret_cast<float*>(dy + y_crop * lo), n, H, W,
                       (dual && (i & 1)) ? h->host_ws2 : h->host_ws, (dual && (i & 1)) ? h->host_ws2_cap : h->host_ws_cap, cs);
-    if (rc) return rc;
+    if (rc) {   // earlier chunks' async copies still reference the caller's buffers: drain them before reporting the error
+      cudaStreamSynchronize(h->copy_in_stream);
+      cudaStreamSynchronize(h->host_stream);
+      cudaStreamSynchronize(h->host_stream2);
+      cudaStreamSynchronize(h->copy_out_stream);
+      return rc;
+    }
     CUDA_TRY(h, cudaEventRecord(h->host_ev[2 * i + 1], cs));
     CUDA_TRY(h, cudaStreamWaitEvent(h->copy_out_stream, h->host_ev[2 * i + 1], 0));
     CUDA_TRY(h, cudaMemcpyAsync(hy + y_crop * lo, dy + y_crop * lo, y_crop * n, cudaMemcpyDeviceToHost, h->copy_out_stream));

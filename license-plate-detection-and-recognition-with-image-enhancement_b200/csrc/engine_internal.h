@@ -35,6 +35,11 @@ struct ConvW {
   UmmaWeights u;           // tensor-core packing (16-bit modes)
 };
 
+// Tensor-core CSAR tail: the channel branch x_in^2 * s_c (lpsr.py:133-135,182-184) reaches a few thousand with the shipped checkpoint
+// (|x_in| ~ 100).  It is carried as x_in^2 * (s_c / 16) with conv_out's first 32 input columns multiplied by 16 at pack time: exact
+// (powers of two) in bf16 and fp16, and it keeps 16x more headroom below the fp16 maximum (65504) on adversarial inputs.
+constexpr float kCsarChanScale = 16.f;
+
 struct DConvW { float *dw_w, *dw_b, *pw_w, *pw_b; int cin, cout; };
 
 }  // namespace lpsr

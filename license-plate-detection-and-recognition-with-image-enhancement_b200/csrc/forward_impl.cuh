@@ -105,10 +105,11 @@ void launch_dconv(Ctx& c, const DConvW& w, const void* in, int in_pitch, void* o
   p.B = B; p.H = H; p.W = Wd;
   const int tiles_x = (Wd + kDcTileW - 1) / kDcTileW, tiles_y = (H + kDcTileH - 1) / kDcTileH;
   const size_t smem = dconv_smem_bytes<T, CIN>(COUT);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(dconv_fused_kernel<T, CIN, COUT, MODE, ADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
+  static bool configured[kMaxDevices] = {};   // the attribute is per device
+  bool* flag = func_configured_flag(configured);
+  if (!flag || !*flag) {
+    if (cudaFuncSetAttribute(dconv_fused_kernel<T, CIN, COUT, MODE, ADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess && flag)
+      *flag = true;
   }
   const long long n_tiles = (long long)tiles_x * tiles_y * B;
   const int grid = (int)std::min<long long>(n_tiles, (long long)c.h->num_sms * 2);   // persistent: weights staged once per CTA
@@ -169,7 +170,7 @@ void csar_block(Ctx& c, const WsLayout& L, char* ws, int B, size_t in_t, size_t 
       c.begin("channel_gate");
       if (!c.dry && c.rc == LPSR_OK) {
         cudaError_t e = launch_pdl(channel_gate_kernel, dim3(B), dim3(256), 0, c.st, (const float*)pool, pool_slots, L.P, (const float*)h->ca_w1,
-                                   (const float*)h->ca_b1, (const float*)h->ca_w2, (const float*)h->ca_b2, sc);
+                                   (const float*)h->ca_b1, (const float*)h->ca_w2, (const float*)h->ca_b2, sc, 1.f / kCsarChanScale);
         if (e == cudaSuccess) e = cudaGetLastError();
         if (e != cudaSuccess) c.rc = fail(h, LPSR_ERR_CUDA, "channel_gate launch: %s", cudaGetErrorString(e));
       }

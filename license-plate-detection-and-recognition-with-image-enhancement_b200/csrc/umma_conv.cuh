@@ -312,6 +312,19 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     uint32_t r;
     asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
     return r;
+  } else if constexpr (IsBf16<T>::value) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+  } else if constexpr (sizeof(T) == 2 && RELU) {
+    // fp16: saturate to +-65504 instead of inf (same guarantee as from_f32<__half>), ReLU folded in: one instruction per pair
+    uint32_t r;
+    asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+  } else if constexpr (sizeof(T) == 2) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
   } else {
     if constexpr (RELU) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
     T t[2] = {from_f32<T>(a), from_f32<T>(b)};
@@ -1194,13 +1207,23 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
+// cudaFuncSetAttribute is per device (context): one flag per kernel instantiation AND device ordinal.  The flags are only ever set
+// to true after the attribute call succeeded, so a race between two host threads costs at most a redundant call.
+constexpr int kMaxDevices = 64;
+inline bool* func_configured_flag(bool (&flags)[kMaxDevices]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;   // unknown device: configure every time
+  return &flags[dev];
+}
+
 template <typename T, int N, int MODE, int EPI, typename TOUT = T>
 inline const char* umma_launch_inst(const UmmaPlan& plan, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};
+  bool* flag = func_configured_flag(configured);
+  if (!flag || !*flag) {
     cudaError_t e = cudaFuncSetAttribute(umma_conv_kernel<T, N, MODE, EPI, TOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return cudaGetErrorString(e);
-    configured = true;
+    if (flag) *flag = true;
   }
   cudaError_t e = launch_pdl(umma_conv_kernel<T, N, MODE, EPI, TOUT>, dim3(plan.grid), dim3(kUmmaThreads), plan.smem_bytes, st, plan.p, plan.tm);
   if (e == cudaSuccess) e = cudaGetLastError();

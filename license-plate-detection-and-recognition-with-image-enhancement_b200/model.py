@@ -102,10 +102,30 @@ class LPSR(nn.Module):
         rdn.gff = _slots(_conv(F * NB, F, 1), _conv(F, F, 3))
         self.rdn = rdn
         self.final_conv = _conv(F, OC, 3)
-        # ---- native state (not part of state_dict)
-        self._handles: Dict[Tuple[int, str], int] = {}
-        self._weights_key: Dict[Tuple[int, str], tuple] = {}
-        self._workspaces: Dict[Tuple[int, int, int, int, str], torch.Tensor] = {}
+        self._reset_native_state()
+
+    # ---- native state (not part of state_dict, never copied or pickled) --------------------------------
+    _NATIVE_ATTRS = ("_handles", "_weights_key", "_workspaces", "_live_refs", "_ws_streams")
+
+    def _reset_native_state(self):
+        # raw lpsr_handle pointers, the (data_ptr, version) key of the weights they were packed from, scratch tensors, and the
+        # (owner module, attribute) path of every live tensor (resolved once per handle)
+        self.__dict__["_handles"] = {}
+        self.__dict__["_weights_key"] = {}
+        self.__dict__["_workspaces"] = {}
+        self.__dict__["_live_refs"] = {}
+        self.__dict__["_ws_streams"] = {}      # streams that used each workspace, most recent last
+
+    def __getstate__(self):
+        # copy.deepcopy / pickle / torch.save(model): a copy must never share (and later double-free) the native handles
+        state = self.__dict__.copy()
+        for k in self._NATIVE_ATTRS:
+            state.pop(k, None)
+        return state
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._reset_native_state()
 
     # ------------------------------------------------------------------------------------------------
     def live_tensors(self) -> Dict[str, torch.Tensor]:
@@ -137,16 +157,26 @@ class LPSR(nn.Module):
             capi.check(lib.lpsr_create(C.byref(out), C.byref(cfg)), None, "lpsr_create")
             h = out.value
             self._handles[key] = h
-        # (re)pack when parameters changed: load_state_dict, .to(), optimiser steps bump _version / data_ptr
-        n = lib.lpsr_num_live_tensors(h)
-        names = [lib.lpsr_live_tensor_name(h, i).decode() for i in range(n)]
-        params = dict(self.named_parameters(remove_duplicate=True))
-        wkey = tuple((params[nm].data_ptr(), params[nm]._version) for nm in names)
+        # (re)pack when parameters changed: load_state_dict, .to(), optimiser steps bump _version / data_ptr.  The per-call cost is
+        # 64 getattr + data_ptr reads (the call site runs batch 1, inference/run.py:200-202): the name -> (module, attribute) paths
+        # are resolved once per handle instead of walking named_parameters() on every forward.
+        refs = self._live_refs.get(key)
+        if refs is None:
+            n = lib.lpsr_num_live_tensors(h)
+            refs = []
+            for i in range(n):
+                nm = lib.lpsr_live_tensor_name(h, i).decode()
+                mod_path, _, attr = nm.rpartition(".")
+                refs.append((nm, self.get_submodule(mod_path) if mod_path else self, attr))
+            self._live_refs[key] = refs
+        n = len(refs)
+        live = [getattr(owner, attr) for _, owner, attr in refs]
+        wkey = tuple((t.data_ptr(), t._version) for t in live)
         if self._weights_key.get(key) != wkey:
             descs = (capi.LpsrTensorDesc * n)()
             keep = []
-            for i, nm in enumerate(names):
-                t = params[nm].detach()
+            for i, (nm, _, _) in enumerate(refs):
+                t = live[i].detach()
                 if t.dtype != torch.float32 or not t.is_contiguous():
                     t = t.float().contiguous()
                 if t.is_cuda and t.device.index != key[0]:
@@ -165,9 +195,12 @@ class LPSR(nn.Module):
         if ws is None:
             lib = capi.load_library()
             nbytes = lib.lpsr_workspace_bytes(h, B, H, W)
-            # keep at most one workspace per device/precision: shapes change rarely at the call sites
+            # keep at most one workspace per device/precision: shapes change rarely at the call sites.  Kernels of an earlier forward
+            # (possibly on another stream) may still be using the old scratch: tell the caching allocator before dropping it.
             for k in [k for k in self._workspaces if k[0] == dev and k[4] == self.precision]:
-                del self._workspaces[k]
+                old = self._workspaces.pop(k)
+                for st in self._ws_streams.pop(k, ()):
+                    old.record_stream(st)
             ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=torch.device("cuda", dev))
             self._workspaces[key] = ws
         return ws
@@ -200,15 +233,25 @@ class LPSR(nn.Module):
             if B == 0:
                 return y
             ws = self._workspace(h, dev, B, H, W)
-            stream = torch.cuda.current_stream(dev).cuda_stream
+            cur = torch.cuda.current_stream(dev)
+            # the scratch is shared by every forward of this shape: a forward on a different stream than the previous one waits for it
+            used = self._ws_streams.setdefault((dev, B, H, W, self.precision), [])
+            if used and used[-1] != cur:
+                cur.wait_stream(used[-1])
+            if cur not in used:
+                used.append(cur)
+            elif used[-1] != cur:
+                used.remove(cur); used.append(cur)
             capi.check(lib.lpsr_forward(h, xin.data_ptr(), y.data_ptr(), B, H, W, self._aligned_ptr(ws),
-                                        ws.numel() - (self._aligned_ptr(ws) - ws.data_ptr()), stream), h, "lpsr_forward")
+                                        ws.numel() - (self._aligned_ptr(ws) - ws.data_ptr()), cur.cuda_stream), h, "lpsr_forward")
         return y
 
     @torch.no_grad()
     def forward_host(self, x_cpu: torch.Tensor, out: Optional[torch.Tensor] = None, device: Optional[int] = None) -> torch.Tensor:
         """`sr_model(x.to(device)).cpu()` of the reference call site (inference/run.py:201-202) as ONE C-ABI call on
         host buffers: H2D copy, forward and D2H copy happen inside ``lpsr_forward_host``."""
+        if not isinstance(x_cpu, torch.Tensor) or x_cpu.dim() != 4 or x_cpu.shape[1] != self._dims[0]:
+            raise RuntimeError(f"LPSR.forward_host expects a [B,{self._dims[0]},H,W] tensor, got {tuple(getattr(x_cpu, 'shape', ()))}")
         if x_cpu.is_cuda:
             raise RuntimeError("forward_host takes a CPU tensor")
         lib = capi.load_library()
@@ -216,8 +259,14 @@ class LPSR(nn.Module):
         x_cpu = x_cpu.float().contiguous()
         B, _, H, W = x_cpu.shape
         Hp, Wp = (H + 3) // 4 * 4, (W + 3) // 4 * 4
+        shape = (B, self._dims[5], Hp, Wp)
         if out is None:
-            out = torch.empty((B, self._dims[5], Hp, Wp), dtype=torch.float32, pin_memory=True)
+            out = torch.empty(shape, dtype=torch.float32, pin_memory=torch.cuda.is_available())
+        elif (not isinstance(out, torch.Tensor) or out.is_cuda or out.dtype != torch.float32 or tuple(out.shape) != shape
+              or not out.is_contiguous()):
+            raise RuntimeError(f"forward_host: `out` must be a contiguous CPU float32 tensor of shape {shape}")
+        if B == 0 or H == 0 or W == 0:
+            return out
         h = self._handle(torch.device("cuda", dev))
         capi.check(lib.lpsr_forward_host(h, x_cpu.data_ptr(), out.data_ptr(), B, H, W), h, "lpsr_forward_host")
         return out
@@ -268,8 +317,11 @@ class LPSR(nn.Module):
 
     def __del__(self):
         try:
-            lib = capi.load_library()
-            for h in self._handles.values():
-                lib.lpsr_destroy(h)
+            handles = self.__dict__.get("_handles") or {}
+            if handles:
+                lib = capi.load_library()
+                for h in list(handles.values()):
+                    lib.lpsr_destroy(h)
+                handles.clear()
         except Exception:
             pass

@@ -134,6 +134,11 @@ def main():
         "u_b1_33x193_pad": uniform_input(1, 33, 193, 6),
         "u_b2_4x4": uniform_input(2, 4, 4, 3),
         "u_b1_128x384": uniform_input(1, 128, 384, 11)[:, :, :, :],  # config 4 crop
+        # smooth crops are what real plates look like after the bicubic resize of the call site, and the class on which 16-bit
+        # operand rounding is amplified most: a batch at the benchmark crop, the call-site crop and the pad-to-4 path
+        "s_b8_64x192": smooth_input(8, 64, 192, 21),
+        "s_b4_32x192": smooth_input(4, 32, 192, 22),
+        "s_b2_30x190_pad": smooth_input(2, 30, 190, 23),
     }
     # zeros / ones / impulse in one batch (pins padding + shuffle indexing)
     sp = torch.zeros(3, 3, 16, 24)

@@ -157,14 +157,13 @@ def test_half_modes_match_reference_golden(case, prec, shipped_weights, models):
     assert y.shape == d["y"].shape and np.isfinite(y).all()
     err = float(np.abs(y - d["y"]).max())
     psnr = _psnr(y, d["y"])
-    if prec == "bf16" and (case.startswith(("s_", "special")) or "pad" in case):
-        # with the TRAINED checkpoint plain bf16 operands reach 1.2e-2..5.5e-2 max-abs on smooth inputs
-        # and on crops with flat (zero-padded) regions: the net amplifies operand rounding; measured on B200: 1.9e-2 smooth,
-        # 1.27e-2 pad-to-4 case.  PSNR-vs-reference stays > 50 dB.  fp16 mode meets 1e-2 everywhere.
-        assert err <= 6e-2 and psnr >= 50.0
-    else:
-        assert err <= HALF_TOL, f"{case} {prec}: {err}"
-        assert psnr >= 50.0
+    assert psnr >= 50.0
+    if prec == "bf16" and err > HALF_TOL and (case.startswith(("s_", "special")) or "pad" in case):
+        # bf16 is NOT the benchmarked / recommended 16-bit mode (fp16 is, see bench.py): with the TRAINED checkpoint bf16 storage
+        # rounding (8 mantissa bits) is amplified to 1e-2..5e-2 max-abs on smooth / flat crops (reproduced on CPU by
+        # tools/bf16_emulation.py).  The north-star bound stays asserted; the known miss is reported as an expected failure.
+        pytest.xfail(f"bf16 storage exceeds the 1e-2 bound on {case}: {err:.3e} (documented; use precision='fp16')")
+    assert err <= HALF_TOL, f"{case} {prec}: {err}"
 
 
 @pytest.mark.parametrize("prec", ["bf16", "fp16"])
@@ -188,10 +187,29 @@ def test_ragged_shapes_all_modes(H, W, shipped_weights, models):
     x = torch.rand(2, 3, H, W, generator=torch.Generator().manual_seed(H * 1000 + W))
     ref = port.lpsr_forward(x, port.to_torch_weights(shipped_weights))
     assert tuple(ref.shape) == (2, 1, (H + 3) // 4 * 4, (W + 3) // 4 * 4)
-    for prec, tol in (("fp32", FP32_TOL), ("fp16", HALF_TOL), ("bf16", 6e-2)):
+    for prec, tol in (("fp32", FP32_TOL), ("fp16", HALF_TOL)):
         y = models[prec](x.to(DEV)).cpu()
         assert y.shape == ref.shape and torch.isfinite(y).all()
         assert float((y - ref).abs().max()) <= tol, (prec, H, W, float((y - ref).abs().max()))
+    y = models["bf16"](x.to(DEV)).cpu()                      # legacy mode: same planner paths, shape / finiteness / PSNR only
+    assert y.shape == ref.shape and torch.isfinite(y).all()
+    assert _psnr(y.numpy(), ref.numpy()) >= 45.0
+
+
+@pytest.mark.parametrize("H,W", [(64, 192), (32, 192), (30, 190)])
+def test_smooth_batches_default_16bit_mode(H, W, shipped_weights, models):
+    """The class real plates belong to (bicubic-resized, smooth) at the benchmark crop, the call-site crop and the pad-to-4 path, in
+    the 16-bit mode bench.py runs (fp16): max|err| <= 1e-2 against the reference arithmetic on CPU, several seeds."""
+    Wt = port.to_torch_weights(shipped_weights)
+    worst = 0.0
+    for seed in (31, 32, 33):
+        g = torch.Generator().manual_seed(seed)
+        lo = torch.rand(8, 3, max(H // 8, 1), max(W // 8, 1), generator=g)
+        x = F.interpolate(lo, size=(H, W), mode="bicubic", align_corners=False).clamp(0, 1).contiguous()
+        ref = port.lpsr_forward(x, Wt)
+        y = models["fp16"](x.to(DEV)).cpu()
+        worst = max(worst, float((y - ref).abs().max()))
+    assert worst <= HALF_TOL, worst
 
 
 def test_fp32_batch256_matches_torch_port(shipped_weights, models):
@@ -209,7 +227,7 @@ def test_batch_composition_independence_full_size(models):
     """Size-independent property at BASELINE's full batch (1024): a crop's output does not depend on what else is in the
     batch, so tiling a base set of 8 crops 128x must reproduce the B=8 result."""
     base = torch.rand(8, 3, 64, 192, generator=torch.Generator().manual_seed(9)).to(DEV)
-    for prec in ("bf16", "fp32"):
+    for prec in ("fp16", "bf16", "fp32"):
         m = models[prec]
         y8 = m(base)
         yb = m(base.repeat(128, 1, 1, 1))
@@ -222,7 +240,7 @@ def test_batch_composition_independence_full_size(models):
 @pytest.mark.parametrize("batch", [5, 130, 520])     # 1, 2 and 4 pipelined chunks inside lpsr_forward_host
 def test_forward_host_equals_forward(models, batch):
     x = torch.rand(batch, 3, 32, 96, generator=torch.Generator().manual_seed(4))
-    for prec in ("fp32", "bf16"):
+    for prec in ("fp32", "fp16", "bf16"):
         m = models[prec]
         y_dev = m(x.to(DEV)).cpu()
         y_host = m.forward_host(x.pin_memory())
@@ -307,3 +325,70 @@ def test_enhance_plates_matches_reference_stage(shipped_weights, models):
         diff = np.abs(ref.astype(np.int32) - g.astype(np.int32))
         assert diff.max() <= 1 and float((diff != 0).mean()) <= 0.01
     assert lpsr_b200.enhance_plates(models["fp32"], []) == []
+
+
+def test_cuda_graph_capture_call_site_batch1(models):
+    """The call site runs batch 1 at 32x192 (inference/run.py:200-202): one forward captured in a CUDA graph replays bit-identically
+    (no host work, no allocation, no synchronisation inside lpsr_forward), also after the input buffer is refilled."""
+    m = models["fp16"]
+    x = torch.rand(1, 3, 32, 192, generator=torch.Generator().manual_seed(12)).to(DEV)
+    y_ref = m(x).clone()
+    s = torch.cuda.Stream(DEV)
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            m(x)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        y_g = m(x)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(y_g, y_ref)
+    x2 = torch.rand(1, 3, 32, 192, generator=torch.Generator().manual_seed(13)).to(DEV)
+    x.copy_(x2)
+    g.replay()
+    torch.cuda.synchronize()
+    y_new = y_g.clone()          # the graph's output buffer, before the eager forward below reuses the scratch
+    assert torch.equal(y_new, m(x2))
+
+
+def test_deepcopy_and_pickle_do_not_share_native_handles(shipped_weights):
+    """copy.deepcopy (EMA / per-worker clones) and pickling must not duplicate the raw lpsr_handle pointers (double free)."""
+    import copy
+    import pickle
+    m = _model(shipped_weights, "fp32")
+    x = torch.rand(1, 3, 16, 32, generator=torch.Generator().manual_seed(14)).to(DEV)
+    y = m(x)
+    assert len(m._handles) == 1
+    m2 = copy.deepcopy(m)
+    m3 = pickle.loads(pickle.dumps(m)).to(DEV)
+    assert m2._handles == {} and m3._handles == {}
+    assert torch.equal(m2(x), y) and torch.equal(m3(x), y)
+    assert set(m2._handles.values()).isdisjoint(m._handles.values())
+    del m2, m3
+    assert torch.equal(m(x), y)               # the original handle survived the copies' destruction
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_in_one_process(shipped_weights):
+    """cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: the second GPU used by one process must get it too."""
+    x = torch.rand(2, 3, 32, 64, generator=torch.Generator().manual_seed(15))
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        for prec in ("fp16", "fp32"):
+            m = lpsr_b200.LPSR(3, 32, 16, 4, 4, None, precision=prec)
+            m.load_live_weights(shipped_weights)
+            m = m.to(dev).eval()
+            outs.append((prec, m(x.to(dev)).cpu()))
+    assert torch.equal(outs[0][1], outs[2][1]) and torch.equal(outs[1][1], outs[3][1])
+
+
+def test_forward_host_validates_arguments(models):
+    m = models["fp32"]
+    with pytest.raises(RuntimeError):
+        m.forward_host(torch.rand(1, 4, 8, 8))                                   # wrong channel count
+    with pytest.raises(RuntimeError):
+        m.forward_host(torch.rand(1, 3, 8, 8), out=torch.empty(1, 1, 8, 4))       # wrong output shape
+    with pytest.raises(RuntimeError):
+        m.forward_host(torch.rand(1, 3, 8, 8), out=torch.empty(1, 1, 8, 8, dtype=torch.float64))
+    assert m.forward_host(torch.empty(0, 3, 8, 8)).shape == (0, 1, 8, 8)
