@@ -332,6 +332,36 @@ def context_baselines(args, dev, model_factory, rank0_weights):
         del g
     except Exception as exc:
         out["config4_or_latency_error"] = repr(exc)[:200]
+    try:   # BASELINE configs[4]: headless inference/run.py:153-214 on synthetic 1080p frames with injected boxes, LPSR stage timed
+        from lpsr_b200 import pipeline as pl
+        frames, boxes = pl.synthetic_clip(32, 3, seed=0)
+        m = model_factory(args.precision)
+        pl.enhance_frames(m, frames[:2], boxes[:2])                       # warm-up
+        per_frame, per_clip = pl.StageTimes(), pl.StageTimes()
+        for f, b in zip(frames, boxes):                                   # the reference's granularity: one frame (<= 3 plates) at a time
+            pl.enhance_frames(m, [f], [b], times=per_frame)
+        for _ in range(3):                                                # the whole clip in one call (96 plates)
+            pl.enhance_frames(m, frames, boxes, times=per_clip)
+        x1 = torch.rand(1, 3, 32, 192)
+        t0 = time.perf_counter()
+        for _ in range(20):                                               # the reference's own per-plate device round trip (run.py:201-202)
+            m(x1.to(dev)).squeeze(0).cpu()
+        per_plate_sync_us = 1e6 * (time.perf_counter() - t0) / 20
+        out["config5_pipeline"] = {
+            "what": "lpsr_b200.pipeline.enhance_frames on 32 synthetic 1080p frames x 3 injected plate boxes (crop 32x192); CUDA-event time "
+                    "of pre-processing + forward + uint8 conversion",
+            "per_frame_call": {"plates_per_call": 3, "lpsr_stage_us_per_plate": 1e3 * per_frame.lpsr_ms / per_frame.plates,
+                               "forward_us_per_plate": 1e3 * per_frame.forward_ms / per_frame.plates,
+                               "d2h_us_per_plate": 1e3 * per_frame.d2h_ms / per_frame.plates,
+                               "host_us_per_plate": 1e3 * per_frame.host_ms / per_frame.plates},
+            "per_clip_call": {"plates_per_call": 96, "lpsr_stage_us_per_plate": 1e3 * per_clip.lpsr_ms / per_clip.plates,
+                              "forward_us_per_plate": 1e3 * per_clip.forward_ms / per_clip.plates,
+                              "d2h_us_per_plate": 1e3 * per_clip.d2h_ms / per_clip.plates,
+                              "host_us_per_plate": 1e3 * per_clip.host_ms / per_clip.plates},
+            "reference_style_per_plate_roundtrip_us": per_plate_sync_us,
+            "precision": args.precision}
+    except Exception as exc:
+        out["config5_error"] = repr(exc)[:200]
     try:   # BASELINE configs[1]: fp32 mode, B = 256
         m32 = model_factory("fp32")
         xb = torch.rand(256, 3, 64, 192, device=dev)

@@ -137,6 +137,7 @@ bool pack_conv(lpsr_handle* h, ConvW& cw, const std::string& prefix, int cin, in
     cw.b = nullptr;
   }
   if (half_mode(h) && umma_supported(ks, cin, cout)) {
+    quantize_conv_sum_preserving(pw, ks * ks, cin, cout, h->cfg.precision == LPSR_PREC_FP16);   // 16-bit packing only (cw.w stays exact)
     if (!umma_pack_weights(cw.u, pw.data(), bias ? pb.data() : nullptr, ks, cin, cout,
                            h->cfg.precision == LPSR_PREC_FP16, [&](const std::vector<uint16_t>& v) { return arena_put(h, v); },
                            [&](const std::vector<float>& v) { return arena_put(h, v); }))
@@ -229,37 +230,49 @@ bool pack_ae_tensor_core(lpsr_handle* h) {
   bool ok = true;
   // conv_in 3 -> 12 (3x3, no bias) on the half grid: operand = ae_unshuffle_in_kernel's [(i*2+j)*3 + c] (12 real of 16), output =
   // PixelUnshuffle(c0): 48 channels
+  // Weight rounding is what the trained checkpoint amplifies most on smooth crops (CPU emulation: conv_in's fp16 weights alone -> 1.6e-2
+  // at the output, conv_out 1.4e-3): those two stages carry their weights as hi + lo (their K is 16 / 48: the extra MMAs are free);
+  // the composed DConv stages and shallowF1 use sum-preserving rounding of the fine kernel (umma_weights.h).
+  auto sum_preserve = [&](DenseConv& d) {   // d.w: [co][ci][ks*ks]
+    if (!sum_preserving_enabled()) return;
+    for (int f = 0; f < d.cout * d.cin; ++f) quantize_taps_sum_preserving(d.w.data() + (size_t)f * d.ks * d.ks, d.ks * d.ks, 1, fp16);
+  };
   DenseConv cin;
   cin.cin = 3; cin.cout = 12; cin.ks = 3; cin.w = W(h, "auto_encoder.conv_in.weight");
   s2d_weights(cin, 16, 48, [](int c, int i, int j) { return (i * 2 + j) * 3 + c; }, unshuffle_idx, pw, pb);
-  ok &= umma_pack_weights(h->aet_in, pw.data(), nullptr, 3, 16, 48, fp16, put16, put32);
+  ok &= umma_pack_weights_wsplit(h->aet_in, pw.data(), nullptr, 3, 16, 48, fp16, put16, put32);
   // encoder.0: DConv 12 -> 12 at full resolution + PixelUnshuffle == 48 -> 48 on the half grid (lpsr.py:71-73)
-  const DenseConv e0 = compose_dconv(h, "auto_encoder.encoder.0.dConv.", 12, 12, 5);
+  DenseConv e0 = compose_dconv(h, "auto_encoder.encoder.0.dConv.", 12, 12, 5);
+  sum_preserve(e0);
   s2d_weights(e0, 48, 48, unshuffle_idx, unshuffle_idx, pw, pb);
   ok &= umma_pack_weights(h->aet_enc0, pw.data(), pb.data(), 3, 48, 48, fp16, put16, put32);
   // encoder.3: DConv 48 -> 12 on the half grid (5x5 taps); PixelUnshuffle + ReLU in the store (lpsr.py:74-80)
-  const DenseConv e1 = compose_dconv(h, "auto_encoder.encoder.3.dConv.", 48, 12, 5);
+  DenseConv e1 = compose_dconv(h, "auto_encoder.encoder.3.dConv.", 48, 12, 5);
+  sum_preserve(e1);
   plain_weights(e1, 48, 16, [](int co) { return co; }, pw, pb);
   ok &= umma_pack_weights(h->aet_enc1, pw.data(), pb.data(), 5, 48, 16, fp16, put16, put32);
   // decoder.0: DConv 48 -> 48 on the quarter grid + PixelShuffle + ReLU (lpsr.py:83-89): output channel c*4 + i*2 + j goes to column
   // (i*2 + j)*16 + c, so the epilogue stores four 16-channel (12 real) half-grid pixels per quarter-grid pixel
-  const DenseConv d0 = compose_dconv(h, "auto_encoder.decoder.0.dConv.", 48, 48, 5);
+  DenseConv d0 = compose_dconv(h, "auto_encoder.decoder.0.dConv.", 48, 48, 5);
+  sum_preserve(d0);
   plain_weights(d0, 48, 64, [](int co) { return (co & 3) * 16 + (co >> 2); }, pw, pb);
   ok &= umma_pack_weights(h->aet_dec0, pw.data(), pb.data(), 5, 48, 64, fp16, put16, put32);
   // decoder.3: DConv 12 -> 48 on the half grid (lpsr.py:90-96); its 48 outputs per half-grid pixel ARE PixelUnshuffle of the
   // full-resolution 12 channels, the layout of c0 (residual, lpsr.py:115) and of conv_out's operand: plain ReLU + residual store
-  const DenseConv d1 = compose_dconv(h, "auto_encoder.decoder.3.dConv.", 12, 48, 5);
+  DenseConv d1 = compose_dconv(h, "auto_encoder.decoder.3.dConv.", 12, 48, 5);
+  sum_preserve(d1);
   plain_weights(d1, 16, 48, [](int co) { return co; }, pw, pb);
   ok &= umma_pack_weights(h->aet_dec1, pw.data(), pb.data(), 5, 16, 48, fp16, put16, put32);
   // conv_out 12 -> 3 (3x3, no bias) on the half grid: the output stays PixelUnshuffle(ae_out), 12 real of 16 columns
   DenseConv co;
   co.cin = 12; co.cout = 3; co.ks = 3; co.w = W(h, "auto_encoder.conv_out.weight");
   s2d_weights(co, 48, 16, unshuffle_idx, unshuffle_idx, pw, pb);
-  ok &= umma_pack_weights(h->aet_out, pw.data(), nullptr, 3, 48, 16, fp16, put16, put32);
+  ok &= umma_pack_weights_wsplit(h->aet_out, pw.data(), nullptr, 3, 48, 16, fp16, put16, put32);
   // RDN shallowF1 (7x7, 3 -> 32, lpsr.py:195-197) on the half grid: 5x5 coarse taps over the 12 (of 16) unshuffled channels, four
   // 32-channel full-resolution pixels per half-grid pixel (N = 128), written by the epilogue in the trunk's element type
   DenseConv s1;
   s1.cin = 3; s1.cout = 32; s1.ks = 7; s1.w = W(h, "rdn.shallowF1.weight"); s1.b = W(h, "rdn.shallowF1.bias");
+  sum_preserve(s1);
   s2d_weights(s1, 16, 128, unshuffle_idx, [](int c, int I, int J) { return (I * 2 + J) * 32 + c; }, pw, pb);
   ok &= umma_pack_weights(h->aet_sfe1, pw.data(), pb.data(), 5, 16, 128, fp16, put16, put32);
   return ok;
@@ -347,6 +360,7 @@ int pack_all(lpsr_handle* h) {
       for (int co = 0; co < F; ++co)
         for (int ci = 0; ci < cin + G; ++ci) pl[(size_t)ci * F + co] = alpha * wl[(size_t)co * (cin + G) + ci];
       for (auto& v : bl) v *= alpha;
+      quantize_conv_sum_preserving(p3, 9, cin, G, h->cfg.precision == LPSR_PREC_FP16);
       ok &= umma_pack_fused_lff(h->rdb_fused[r], p3.data(), W(h, p + ".layers." + std::to_string(L - 1) + ".conv.bias").data(), pl.data(), bl.data(),
                                 cin, h->cfg.precision == LPSR_PREC_FP16, [&](const std::vector<uint16_t>& v) { return arena_put(h, v); },
                                 [&](const std::vector<float>& v) { return arena_put(h, v); });
@@ -393,6 +407,7 @@ int pack_all(lpsr_handle* h) {
     for (int ci = 0; ci < F; ++ci)
       for (int t = 0; t < 9; ++t) pw[((size_t)t * F + ci) * 16] = w[(size_t)ci * 9 + t];
     pb[0] = W(h, "final_conv.bias")[0];
+    quantize_conv_sum_preserving(pw, 9, F, 16, h->cfg.precision == LPSR_PREC_FP16);
     ok &= umma_pack_weights(h->fin_u, pw.data(), pb.data(), 3, F, 16, h->cfg.precision == LPSR_PREC_FP16,
                             [&](const std::vector<uint16_t>& v) { return arena_put(h, v); }, [&](const std::vector<float>& v) { return arena_put(h, v); });
   }

@@ -56,7 +56,8 @@ constexpr int kUmmaMaxK = 16;           // max M-tiles per item
 constexpr int kUmmaMaxBufs = 4;         // item buffers in the shared-memory ring
 
 struct UmmaParams {
-  int n_ks;                         // K-slices of 16 channels
+  int n_ks;                         // K-slices of 16 channels (weights split into hi + lo terms: twice the activation K-slices)
+  int n_ks_real;                    // K-slices staged in shared memory; K-slice ks >= n_ks_real re-reads the tile of ks - n_ks_real
   // A operand = n_chunks TMA boxes per item: chunk c has chunk_ch[c] channels (16/32/64 -> swizzle 32/64/128 B) starting at
   // channel coordinate chunk_coff[c] of tensor map chunk_map[c], and lives at byte offset chunk_smem[c] of the item buffer
   int n_chunks;
@@ -478,6 +479,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
         for (int kk = 0; kk < (p.chunk_ch[c] >> 4); ++kk, ++ks)
           steps[ks] = make_uint4((p.chunk_smem[c] >> 4) + 2u * (uint32_t)kk, rb16, umma_desc_hi_swizzled(rb16 << 4), (uint32_t)p.pitch * rb16);
       }
+      for (; ks < p.n_ks; ++ks) steps[ks] = steps[ks - p.n_ks_real];   // lo-weight K-slices: same activation tiles
     }
   }
   ptx::fence_proxy_async();      // weights were written with st.shared: make them visible to the tensor core proxy
@@ -1041,8 +1043,10 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
   const size_t xch_bytes = fold ? (size_t)kEpiGroups * 2 * 4 * 2 * (fold5 ? 3 : 1) * N * 4 : 0;
   p.halo = halo;
   p.n_ks = w.cin / 16;                                       // 7x7: 28 pixel-pair steps (UmmaWeights::cin = 448 pseudo channels)
+  p.n_ks_real = w.wsplit ? p.n_ks / 2 : p.n_ks;
   if (p.n_ks > kUmmaMaxSteps) return "too many K-steps";
-  if (!c7 && cp.n_chunks != p.n_ks) return "chunk table does not match Cin/16";
+  if (w.wsplit && (lff || c7)) return "hi + lo weights are not supported by this mode";
+  if (!c7 && cp.n_chunks != p.n_ks_real) return "chunk table does not match Cin/16";
   if (!fp32_out && (cp.out_pitch % 16 || cp.out_off % 16 || reinterpret_cast<uintptr_t>(cp.out) % 32)) return "output pitch/offset not 32-byte aligned (256-bit stores)";
   if (cp.res && (cp.res_pitch % 8 || cp.res_off % 8)) return "residual pitch/offset not 16-byte aligned";
   if (kEpiGroups * NMMA > 512) return "N too large for the TMEM accumulators";
@@ -1058,9 +1062,9 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
     p.chunk_ch[0] = 8; p.chunk_coff[0] = 0; p.chunk_map[0] = 0;
     chunk_base[0] = cp.in; chunk_pitch[0] = cp.in_pitch;
   }
-  for (int k = 0; !c7 && k < p.n_ks;) {
+  for (int k = 0; !c7 && k < p.n_ks_real;) {
     int run = 1;
-    while (k + run < p.n_ks && base_of(k + run) == base_of(k) && cp.chunk_off[k + run] == cp.chunk_off[k] + 16 * run) ++run;
+    while (k + run < p.n_ks_real && base_of(k + run) == base_of(k) && cp.chunk_off[k + run] == cp.chunk_off[k] + 16 * run) ++run;
     int off = cp.chunk_off[k];
     if (off % 8 || pitch_of(k) % 8) return "chunk offset/pitch not 16-byte aligned";
     if (reinterpret_cast<uintptr_t>(base_of(k)) % 16) return "input base not 16-byte aligned";

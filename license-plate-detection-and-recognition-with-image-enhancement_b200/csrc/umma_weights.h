@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -18,6 +19,8 @@ struct UmmaWeights {
   uint16_t* w = nullptr;   // 16-bit (bf16 or fp16): 1x1 [cin/8][cout][8]; 3x3 [dy][cin/8][dx*cout + co][8] (dx folded into N)
   float* bias = nullptr;   // [cout] (zeros if the conv has no bias)
   bool fused_lff = false;  // kConv3x3FoldLff: w = [dy][cin/8][48 folded + 32 lff][8] then lff's g3 slice [2][32][8]; bias = [16] + [32]
+  bool wsplit = false;     // weights carried as hi + lo (two 16-bit terms): cin is DOUBLED, K-slices [cin/2, cin) hold the lo terms and
+                           // re-read the activations of K-slices [0, cin/2) (no second copy in shared memory)
 };
 
 inline bool umma_enabled() {
@@ -54,6 +57,70 @@ inline uint16_t f32_to_f16_bits(float f) {
   return b;
 }
 
+inline float bits16_to_f32(uint16_t b, bool fp16) {
+  if (fp16) { __half h; memcpy(&h, &b, 2); return __half2float(h); }
+  uint32_t u = (uint32_t)b << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+inline uint16_t f32_to_bits16(float f, bool fp16) { return fp16 ? f32_to_f16_bits(f) : f32_to_bf16_bits(f); }
+// the 16-bit neighbours of w: lo <= w <= hi (equal when w is representable); sign-magnitude formats: +-1 on the bit pattern
+inline void neighbours16(float w, bool fp16, float& lo, float& hi) {
+  const uint16_t q = f32_to_bits16(w, fp16);
+  const float fq = bits16_to_f32(q, fp16);
+  if (fq == w || !std::isfinite(fq)) { lo = hi = fq; return; }
+  auto step = [&](uint16_t b, bool up) -> uint16_t {          // next representable value above / below
+    const bool neg = (b & 0x8000u) != 0;
+    if ((b & 0x7fffu) == 0) return up ? (uint16_t)0x0001u : (uint16_t)0x8001u;
+    return (uint16_t)((neg != up) ? b + 1 : b - 1);
+  };
+  if (fq < w) { lo = fq; hi = bits16_to_f32(step(q, true), fp16); }
+  else { hi = fq; lo = bits16_to_f32(step(q, false), fp16); }
+}
+
+// Sum-preserving rounding of one filter (the `n` taps of one (cout, cin) pair, element i at v[i * stride]) to the 16-bit grid.
+// Round-to-nearest leaves every tap with an independent error of up to half an ulp, and on the smooth crops this network sees
+// (bicubic-resized plates) the taps of a filter multiply nearly equal inputs: the output error is (sum of the tap errors) x input, the same
+// at every pixel, and the trained checkpoint amplifies it (CPU emulation, shipped weights, smooth crops: max|err| 3.0e-3 -> 0.7e-3 for the
+// CSAR 3x3 pair, 1.7e-3 -> 1.0e-3 for the RDB layers).  Here every tap is still rounded to one of its two neighbours, but the directions
+// are chosen greedily so that the SUM of the rounded taps stays within a fraction of an ulp of the exact sum: the DC gain of every
+// (cout, cin) filter is preserved.  Values are replaced in place by 16-bit representable floats, so the later conversion is exact.
+inline void quantize_taps_sum_preserving(float* v, int n, size_t stride, bool fp16) {
+  double deficit = 0.0;                                        // sum(w) - sum(current choice); start with every tap rounded DOWN
+  std::vector<float> lo(n), hi(n);
+  std::vector<int> order(n);
+  for (int i = 0; i < n; ++i) {
+    neighbours16(v[i * stride], fp16, lo[i], hi[i]);
+    deficit += (double)v[i * stride] - (double)lo[i];
+    order[i] = i;
+  }
+  // taps closest to their upper neighbour go up first
+  std::sort(order.begin(), order.end(), [&](int a, int b) {
+    const double fa = hi[a] > lo[a] ? ((double)v[a * stride] - lo[a]) / ((double)hi[a] - lo[a]) : 0.0;
+    const double fb = hi[b] > lo[b] ? ((double)v[b * stride] - lo[b]) / ((double)hi[b] - lo[b]) : 0.0;
+    return fa > fb;
+  });
+  std::vector<char> up(n, 0);
+  for (int k = 0; k < n; ++k) {
+    const int i = order[k];
+    const double st = (double)hi[i] - (double)lo[i];
+    if (st > 0.0 && std::fabs(deficit - st) < std::fabs(deficit)) { up[i] = 1; deficit -= st; }
+  }
+  for (int i = 0; i < n; ++i) v[i * stride] = up[i] ? hi[i] : lo[i];
+}
+inline bool sum_preserving_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("LPSR_SUM_PRESERVING"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+// pw: [taps][cin][cout]; one filter = the taps of one (cin, cout) pair
+inline void quantize_conv_sum_preserving(std::vector<float>& pw, int taps, int cin, int cout, bool fp16) {
+  if (taps < 2 || !sum_preserving_enabled()) return;
+  for (int ci = 0; ci < cin; ++ci)
+    for (int co = 0; co < cout; ++co) quantize_taps_sum_preserving(pw.data() + (size_t)ci * cout + co, taps, (size_t)cin * cout, fp16);
+}
+
 // pw: fp32 [taps][cin][cout] (tap = dy*3+dx) -> device 16-bit, tcgen05 no-swizzle K-major core-matrix order:
 //   1x1: [cin/8][cout][8]    3x3 / 5x5 per-tap: [tap][cin/8][cout][8]    3x3 folded (Cout=16): [dy][cin/8][dx*cout + co][8]
 template <typename PutU16, typename PutF32>
@@ -86,6 +153,26 @@ bool umma_pack_weights(UmmaWeights& u, const float* pw, const float* bias, int k
   u.ks = ks; u.cin = cin; u.cout = cout;
   u.packed = (u.w != nullptr && u.bias != nullptr);
   return u.packed;
+}
+
+// Weights as hi + lo: w = hi + lo with hi = rn16(w), lo = rn16(w - hi) (22 significant bits in fp16).  Packed as a convolution over 2*cin
+// input channels [hi rows ; lo rows]; the kernel's K-step table points the second half at the same activation tiles.  Used where a
+// filter's rounding error is amplified most and the extra MMAs are free (AutoEncoder conv_in / conv_out: K = 16 / 48 on the half grid).
+template <typename PutU16, typename PutF32>
+bool umma_pack_weights_wsplit(UmmaWeights& u, const float* pw, const float* bias, int ks, int cin, int cout, bool fp16, PutU16 put16, PutF32 put32) {
+  const int taps = ks * ks;
+  std::vector<float> p2((size_t)taps * 2 * cin * cout);
+  for (int t = 0; t < taps; ++t)
+    for (int ci = 0; ci < cin; ++ci)
+      for (int co = 0; co < cout; ++co) {
+        const float w = pw[((size_t)t * cin + ci) * cout + co];
+        const float hi = bits16_to_f32(f32_to_bits16(w, fp16), fp16);
+        p2[((size_t)t * 2 * cin + ci) * cout + co] = hi;
+        p2[((size_t)t * 2 * cin + cin + ci) * cout + co] = w - hi;
+      }
+  const bool ok = umma_pack_weights(u, p2.data(), bias, ks, 2 * cin, cout, fp16, put16, put32);
+  u.wsplit = true;
+  return ok;
 }
 
 // Last dense layer of an RDB (3x3, cin -> 16, ReLU) fused with the block's local feature fusion (1x1 over cin + 16 channels -> 32,

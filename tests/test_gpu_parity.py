@@ -392,3 +392,36 @@ def test_forward_host_validates_arguments(models):
     with pytest.raises(RuntimeError):
         m.forward_host(torch.rand(1, 3, 8, 8), out=torch.empty(1, 1, 8, 8, dtype=torch.float64))
     assert m.forward_host(torch.empty(0, 3, 8, 8)).shape == (0, 1, 8, 8)
+
+
+def test_enhance_frames_matches_reference_per_plate_loop(shipped_weights, models):
+    """BASELINE configs[4] / SURVEY 8f n2: the batched LPSR stage over a synthetic clip with injected boxes against the reference's
+    per-plate recipe (run.py:188-206) evaluated on CPU: crop -> format_long_plate -> preprocess_for_sr (oracle, bit-exact) -> reference
+    arithmetic -> *255 -> uint8 -> gray->BGR -> restack_to_square.  fp32 mode: at most one level on <= 1 % of the pixels."""
+    from lpsr_b200 import pipeline as pl
+    from oracle import preprocess_oracle as pre
+    frames, boxes = pl.synthetic_clip(3, 3, seed=2)
+    times = pl.StageTimes()
+    res = pl.enhance_frames(models["fp32"], frames, boxes, times=times)
+    assert len(res) == 9 and times.plates == 9 and times.lpsr_ms > 0 and times.calls == 1
+    Wt = port.to_torch_weights(shipped_weights)
+    n_fmt = 0
+    for r in res:
+        x1, y1, x2, y2 = r.box
+        raw = frames[r.frame][y1:y2, x1:x2]
+        long_img, changed = pl.format_long_plate(raw)
+        assert changed == r.was_formatted
+        n_fmt += changed
+        y = port.lpsr_forward(torch.from_numpy(pre.preprocess_for_sr(np.ascontiguousarray(long_img))), Wt)
+        ref = np.repeat((y.squeeze(0).permute(1, 2, 0).numpy() * 255).astype(np.uint8), 3, axis=2)
+        assert r.sr_bgr.shape == (32, 192, 3) and r.sr_bgr.dtype == np.uint8
+        diff = np.abs(ref.astype(np.int32) - r.sr_bgr.astype(np.int32))
+        assert diff.max() <= 1 and float((diff != 0).mean()) <= 0.01
+        want = pl.restack_to_square(ref) if changed else ref
+        assert r.sr_for_ocr.shape == want.shape == ((64, 96, 3) if changed else (32, 192, 3))
+    assert 0 < n_fmt < 9                                   # the clip holds one-row and two-row plates
+    # the 16-bit mode the bench runs: same stage, <= 3 levels (1e-2 * 255)
+    res16 = pl.enhance_frames(models["fp16"], frames, boxes)
+    for a, b in zip(res, res16):
+        assert np.abs(a.sr_bgr.astype(np.int32) - b.sr_bgr.astype(np.int32)).max() <= 3
+    assert pl.enhance_frames(models["fp32"], frames[:1], [[]]) == []

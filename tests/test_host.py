@@ -168,3 +168,35 @@ def test_resample_weight_tables_match_oracle(tmp_path):
         assert vals[2] == kk.shape[1]
         assert vals[3:3 + 2 * b] == bounds.reshape(-1).tolist()
         assert vals[3 + 2 * b:] == kk.reshape(-1).tolist()
+
+
+def test_pipeline_array_steps_match_reference_vectors(golden_dir):
+    """format_long_plate / restack_to_square (inference/run.py:21-78) and the gray -> BGR step (run.py:204) against
+    vectors produced by the reference's own functions and OpenCV (tests/golden/make_golden_pipeline.py), bit for bit."""
+    from lpsr_b200 import pipeline as pl
+    d = np.load(os.path.join(golden_dir, "pipeline_cases.npz"))
+    n = int(d["n"])
+    assert n >= 10
+    n_changed = 0
+    for i in range(n):
+        f, changed = pl.format_long_plate(d[f"in_{i}"])
+        assert changed == bool(d[f"changed_{i}"])
+        n_changed += changed
+        assert np.array_equal(f, d[f"fmt_{i}"])
+        assert np.array_equal(pl.restack_to_square(f), d[f"restack_{i}"])
+        assert np.array_equal(pl.restack_to_square(d[f"in_{i}"]), d[f"restack_raw_{i}"])
+        assert np.array_equal(pl.gray_to_bgr(d[f"gray_{i}"]), d[f"bgr_{i}"])
+    assert 0 < n_changed < n
+    e = np.zeros((0, 5, 3), np.uint8)
+    assert pl.format_long_plate(e)[1] is False and pl.restack_to_square(e) is e
+    assert pl.select_plates([(0, 0, 2, 2), (0, 0, 10, 10), (0, 0, 5, 5), (0, 0, 1, 1)]) == [(0, 0, 10, 10), (0, 0, 5, 5), (0, 0, 2, 2)]
+
+
+def test_synthetic_clip_is_deterministic_and_boxed():
+    from lpsr_b200 import pipeline as pl
+    f1, b1 = pl.synthetic_clip(2, 3, seed=4)
+    f2, b2 = pl.synthetic_clip(2, 3, seed=4)
+    assert b1 == b2 and all(np.array_equal(a, b) for a, b in zip(f1, f2))
+    assert f1[0].shape == (1080, 1920, 3) and f1[0].dtype == np.uint8 and len(b1[0]) == 3
+    for (x1, y1, x2, y2) in b1[0]:
+        assert 0 <= x1 < x2 <= 1920 and 0 <= y1 < y2 <= 1080
