@@ -27,7 +27,7 @@ struct TailUmmaParams {
   void* out; int out_pitch, out_off;
   const uint16_t* w3; const float* b3;   // 1x1 32->64, packed [32/8][64][8]
   const uint16_t* w4; const float* b4;   // 1x1 64->32, packed [64/8][32][8]
-  const uint16_t* wo; const float* bo;   // 1x1 64->32
+  const uint16_t* wo; const float* bo;   // 1x1 64->32 as hi + lo weights: packed [128/8][32][8], K-slices 4..7 hold the lo terms
   const float* s_c;            // [B][32]
   long long total_px;
   int px_per_crop;
@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
   constexpr int G = kTailGroups;
   // bytes: x_in tile, residual tile, and ONE 64-channel planar operand: the hidden map, then (once MMA2 has consumed it) the gated map
   constexpr uint32_t kA1 = 128 * 64, kA2 = 128 * 128, kSlot = 2 * kA1 + kA2;
-  constexpr uint32_t kW3 = 32 * 64 * 2, kW4 = 64 * 32 * 2;
+  constexpr uint32_t kW3 = 32 * 64 * 2, kW4 = 64 * 32 * 2, kWo = 2 * kW4;
   // The additions of the three epilogues run on the tensor core as well (its pipe is mostly idle here, the epilogue warps are the
   // bottleneck): a constant "ones" operand times a K=16 bias operand {hi(b), lo(b), 0...} starts every accumulator at its bias
   // (hi + lo keeps the fp32 bias to 2^-17), and the residual tile times a 32x32 identity adds x exactly (1.0 * 16-bit value).
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
   uint8_t* w3_s = smem + (size_t)G * kSlot;
   uint8_t* w4_s = w3_s + kW3;
   uint8_t* wo_s = w4_s + kW4;
-  uint8_t* ones_s = wo_s + kW4;                                // [2 planes][128 rows][8]: channels 0 and 1 are 1.0
+  uint8_t* ones_s = wo_s + kWo;                                // [2 planes][128 rows][8]: channels 0 and 1 are 1.0
   uint8_t* b3_s = ones_s + kOnes;                              // [2][64][8]: k = 0 -> hi(b3[n]), k = 1 -> lo(b3[n])
   uint8_t* b4_s = b3_s + kB3;
   uint8_t* bo_s = b4_s + kB4;
@@ -72,8 +72,8 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
 #pragma unroll
     for (int j = 0; j < 8; ++j) we[j] = from_f32<T>(0.5f * to_f32<T>(we[j]));
     reinterpret_cast<uint4*>(w4_s)[i] = w;
-    reinterpret_cast<uint4*>(wo_s)[i] = __ldg(reinterpret_cast<const uint4*>(p.wo) + i);
   }
+  for (uint32_t i = threadIdx.x; i < kWo / 16; i += kTailThreads) reinterpret_cast<uint4*>(wo_s)[i] = __ldg(reinterpret_cast<const uint4*>(p.wo) + i);
   {
     T* ones = reinterpret_cast<T*>(ones_s);
     for (uint32_t i = threadIdx.x; i < 2 * 128 * 8; i += kTailThreads) ones[i] = from_f32<T>((i < 128 * 8 && (i & 7) < 2) ? 1.f : 0.f);
@@ -189,6 +189,11 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
               ptx::tc_mma_f16_lohi(dd, (a16 + (uint32_t)(ks * 2 * 128)) | (128u << 16), kUmmaDescHi, w_lo + (uint32_t)(ks * 2 * 32), kUmmaDescHi, idesc32, 1u);
+            if (phase == 2) {                                               // conv_out: the lo terms of the weights over the same gated operand
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                ptx::tc_mma_f16_lohi(dd, (a16 + (uint32_t)(ks * 2 * 128)) | (128u << 16), kUmmaDescHi, w_lo + (uint32_t)((4 + ks) * 2 * 32), kUmmaDescHi, idesc32, 1u);
+            }
           }
           ptx::tc_commit(bar(s, phase * 2 + 1));                         // h_full / s_full / o_full
           progressed = true;
@@ -316,7 +321,7 @@ inline const char* csar_tail_umma_launch(const TailUmmaParams& pin, bool fp16, i
   if (const char* msg = umma_make_tmap(&tm.m, p.x_in, fp16, 32, 32, false, 0, 0, 0, 128, 0, p.total_px)) return msg;
   if (const char* msg = umma_make_tmap(&tm.r, p.res, fp16, p.res_pitch, 32, false, 0, 0, 0, 128, 0, p.total_px)) return msg;
   constexpr size_t kSlot = 2 * 128 * 64 + 128 * 128;
-  const size_t smem = 1024 + kTailGroups * kSlot + 32 * 64 * 2 + 2 * 64 * 32 * 2 + (2 * 128 + 2 * 64 + 2 * 32 + 2 * 32 + 4 * 32) * 16 +
+  const size_t smem = 1024 + kTailGroups * kSlot + 32 * 64 * 2 + 3 * 64 * 32 * 2 + (2 * 128 + 2 * 64 + 2 * 32 + 2 * 32 + 4 * 32) * 16 +
                       (7 * kTailGroups + 2) * 8 + 64;
   static bool configured[kMaxDevices] = {};
   bool* flag = func_configured_flag(configured);

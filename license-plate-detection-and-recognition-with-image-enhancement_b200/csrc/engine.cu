@@ -17,6 +17,7 @@
 #include "engine_internal.h"
 #include "preprocess.cuh"
 #include "umma_conv.cuh"
+#include "rdb_chain.cuh"
 
 using namespace lpsr;
 
@@ -377,8 +378,10 @@ int pack_all(lpsr_handle* h) {
     std::vector<float> pw((size_t)2 * F * F);
     for (int co = 0; co < F; ++co)
       for (int ci = 0; ci < 2 * F; ++ci) pw[(size_t)ci * F + co] = (ci < F ? kCsarChanScale : 1.f) * w[(size_t)co * 2 * F + ci];
-    ok &= umma_pack_weights(h->csar_co.u, pw.data(), W(h, "rdn.csar.conv_out.bias").data(), 1, 2 * F, F, h->cfg.precision == LPSR_PREC_FP16,
-                            [&](const std::vector<uint16_t>& v) { return arena_put(h, v); }, [&](const std::vector<float>& v) { return arena_put(h, v); });
+    // hi + lo weights (K doubled): conv_out multiplies the largest operands of the network (x_in^2 * s_c reaches thousands) and its
+    // weight rounding is one of the two largest single contributions to the output error (CPU emulation); the tail is not MMA bound
+    ok &= umma_pack_weights_wsplit(h->csar_co.u, pw.data(), W(h, "rdn.csar.conv_out.bias").data(), 1, 2 * F, F, h->cfg.precision == LPSR_PREC_FP16,
+                                   [&](const std::vector<uint16_t>& v) { return arena_put(h, v); }, [&](const std::vector<float>& v) { return arena_put(h, v); });
   }
   h->ca_w1 = arena_put(h, W(h, "rdn.csar.ca.block.2.weight"));
   h->ca_b1 = arena_put(h, W(h, "rdn.csar.ca.block.2.bias"));
@@ -399,6 +402,17 @@ int pack_all(lpsr_handle* h) {
   h->co_b = arena_put(h, W(h, "rdn.csar.conv_out.bias"));
   ok &= h->ca_w1 && h->ca_b1 && h->ca_w2 && h->ca_b2 && h->sa_w1 && h->sa_b1 && h->sa_w2 && h->sa_b2 && h->co_w && h->co_b;
   ok &= pack_conv(h, h->gff0, "rdn.gff.0", F * h->cfg.num_blocks, F, 1, true);
+  if (half_mode(h) && h->gff0.u.packed && !getenv("LPSR_NO_WSPLIT")) {
+    // 1x1 over the 128-channel concatenation of block outputs (|f| up to ~800 with the shipped checkpoint): weights as hi + lo.  The
+    // launch is HBM bound (96 % of peak), the 8 extra MMAs per tile are free.
+    const std::vector<float>& w = W(h, "rdn.gff.0.weight");   // [F][4F]
+    const int cin = F * h->cfg.num_blocks;
+    std::vector<float> pw((size_t)cin * F);
+    for (int co = 0; co < F; ++co)
+      for (int ci = 0; ci < cin; ++ci) pw[(size_t)ci * F + co] = w[(size_t)co * cin + ci];
+    ok &= umma_pack_weights_wsplit(h->gff0.u, pw.data(), W(h, "rdn.gff.0.bias").data(), 1, cin, F, h->cfg.precision == LPSR_PREC_FP16,
+                                   [&](const std::vector<uint16_t>& v) { return arena_put(h, v); }, [&](const std::vector<float>& v) { return arena_put(h, v); });
+  }
   ok &= pack_conv(h, h->gff1, "rdn.gff.1", F, F, 3, true);
   ok &= pack_conv(h, h->fin, "final_conv", F, h->cfg.out_channels, 3, true);
   if (half_mode(h) && umma_supported(3, F, 16)) {   // tensor-core final conv: pad Cout 1 -> 16 with zero filters
@@ -455,6 +469,15 @@ WsLayout ws_layout(const lpsr_handle* h, int B, int H, int W) {
   if (half_mode(h)) {   // tensor-core CSAR tail: 64-channel hidden map and the gated concat [x_in^2*s_c | x_in*s_s]
     L.hid = take(BP * 64, es);
     L.gate = take(BP * 64, es);
+  }
+  L.chain_scr = 0;
+  L.chain_scr_bytes = 0;
+  if (half_mode(h) && chain_enabled()) {   // fused RDB: per-CTA scratch for the growths g0..g2 of one band (stays in L2)
+    const ChainGeom g = chain_geometry(L.Hp, L.Wp, h->num_sms);
+    if (g.ok) {
+      L.chain_scr_bytes = g.scr_bytes;
+      L.chain_scr = take(g.scr_bytes, 1);
+    }
   }
   L.total = off;
   return L;

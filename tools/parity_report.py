@@ -32,9 +32,17 @@ refs = {k: port.lpsr_forward(v, Wt) for k, v in sets.items()}
 for prec in precs:
     m = lpsr_b200.LPSR(3, 32, 16, 4, 4, None, precision=prec).load_live_weights(W).to("cuda:0").eval()
     worst = 0.0
+    errs = []
     for k, x in sets.items():
         y = m(x.to("cuda:0")).cpu()
-        e = float((y - refs[k]).abs().max())
+        d = (y - refs[k]).abs()
+        e = float(d.max())
         worst = max(worst, e)
-        print(f"{prec} {k:22s} max|err| {e:.3e}  mean {float((y - refs[k]).abs().mean()):.2e}", flush=True)
-    print(f"{prec} WORST {worst:.3e}")
+        errs.append(d.flatten())
+        if os.environ.get("PARITY_VERBOSE", "1") == "1":
+            print(f"{prec} {k:22s} max|err| {e:.3e}  mean {float(d.mean()):.2e}", flush=True)
+    allerr = torch.cat(errs)
+    n = allerr.numel()
+    q = lambda f: float(allerr.kthvalue(max(1, int(f * n))).values)
+    print(f"{prec} SUMMARY worst {worst:.3e}  p99.99 {q(0.9999):.3e}  p99.9 {q(0.999):.3e}  rms {float((allerr.double() ** 2).mean().sqrt()):.3e}  "
+          f"n>5e-3 {int((allerr > 5e-3).sum())}  n>1e-2 {int((allerr > 1e-2).sum())}  of {n}")
