@@ -106,7 +106,7 @@ inline size_t elem_size(const lpsr_handle* h) { return half_mode(h) ? 2 : 4; }
 // f[0..3] = block0..3 outputs (32 ch each; f[1] is also RDB#2's input).  Dense concatenation (lpsr.py:39-40) and the final
 // torch.cat (lpsr.py:224) are channel-chunk gather lists over these tensors (ConvParams::chunk_ptr), never copies.
 struct WsLayout {
-  size_t xu, c0, e0, e1, d0, s, ae, sfe1, x0, f[4], grow[2][4], t, xin, g0, g, pool, hid, gate, sc, chain_scr, chain_scr_bytes, total;
+  size_t xu, c0, e0, e1, d0, s, ae, sfe1, x0, f[4], grow[2][4], t, xin, g0, g, pool, hid, gate, sc, total;
   int Hp, Wp, P, S;
   int pool_slots;   // 16-bit modes: capacity (per crop) of the pooled partial sums written by conv_in.2's epilogue (0: not used)
 };

@@ -8,7 +8,6 @@
 #include "engine_internal.h"
 #include "umma_conv.cuh"
 #include "csar_tail_umma.cuh"
-#include "rdb_chain.cuh"
 
 namespace lpsr {
 
@@ -232,19 +231,6 @@ void rdb_block(Ctx& c, const WsLayout& L, char* ws, int B, int r, size_t x_t, si
   T* out = reinterpret_cast<T*>(ws + out_t);
   T* g[4];
   for (int i = 0; i < 4; ++i) g[i] = reinterpret_cast<T*>(ws + L.grow[r][i]);
-  if constexpr (sizeof(T) == 2) {
-    if (h->rdb_fused[r].packed && L.chain_scr_bytes > 0 && chain_enabled()) {
-      // the whole block in ONE launch: growths g0..g2 live in an L2-resident per-CTA scratch (rdb_chain.cuh)   (lpsr.py:43-61)
-      c.begin("rdb_chain");
-      if (c.dry || c.rc != LPSR_OK) return;
-      const UmmaWeights* w[kChainLayers] = {&h->rdb[r][0].u, &h->rdb[r][1].u, &h->rdb[r][2].u, &h->rdb_fused[r]};
-      ChainPlan plan;
-      const char* msg = rdb_chain_plan(plan, w, x, out, ws + L.chain_scr, B, L.Hp, L.Wp, h->num_sms, h->cfg.precision == LPSR_PREC_FP16);
-      if (!msg) msg = rdb_chain_launch<T>(plan, c.st);
-      if (msg) c.rc = fail(h, LPSR_ERR_CUDA, "rdb_chain launch: %s", msg);
-      return;
-    }
-  }
   // dense layers: conv3x3(cat[x, g0..g(i-1)]) -> ReLU -> its own 16-channel tensor g[i]              (lpsr.py:31-40)
   dense_conv<T>(c, h->rdb[r][0], conv_params(h->rdb[r][0], {Seg{x, 32, 0, 32}}, 16, g[0], 16, 0, B, L.Hp, L.Wp, true));
   dense_conv<T>(c, h->rdb[r][1], conv_params(h->rdb[r][1], {Seg{x, 32, 0, 32}, Seg{g[0], 16, 0, 16}}, 16, g[1], 16, 0, B, L.Hp, L.Wp, true));

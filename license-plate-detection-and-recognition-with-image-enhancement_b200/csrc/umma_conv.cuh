@@ -47,11 +47,14 @@ namespace lpsr {
 #define LPSR_UMMA_EPI_GROUPS 3
 #endif
 constexpr int kEpiGroups = LPSR_UMMA_EPI_GROUPS;   // epilogue groups == TMEM tile accumulators in flight
-constexpr int kUmmaThreads = (5 * kEpiGroups + 1) * 32;   // G x 4 epilogue warps, G MMA warps (one per accumulator), 1 TMA producer warp
+// threads of a launch: G x 4 x CS epilogue warps, G MMA warps (one per accumulator), 1 TMA producer warp.  CS = 2 (column split): TWO
+// warps per TMEM lane quadrant and accumulator, each taking half of the output channels -- the epilogue is bound by the latency of its
+// own dependent instruction chain with only three warps per scheduler (ncu: 8.9 cycles per issued instruction), so twice the warps with
+// half the work each is what shortens it
+__host__ __device__ constexpr int umma_threads(int cs) { return (4 * kEpiGroups * cs + kEpiGroups + 1) * 32; }
+constexpr int kUmmaThreads = umma_threads(1);
 constexpr int kUmmaMaxKChunks = 8;      // TMA boxes (K-chunks of 16/32/64 channels) per item
 constexpr int kUmmaMaxSteps = 32;       // K-steps (MMAs per tap) per tile: Cin/16, or 28 pixel-pair steps of the 7x7 conv
-constexpr int kUmmaMmaWarp = 4 * kEpiGroups;               // first of the G MMA warps
-constexpr int kUmmaFirstLoaderWarp = 5 * kEpiGroups;
 constexpr int kUmmaMaxK = 16;           // max M-tiles per item
 constexpr int kUmmaMaxBufs = 4;         // item buffers in the shared-memory ring
 
@@ -223,6 +226,15 @@ __device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, float* v) {
       : "memory");
 }
 
+// 32 lanes x 8 consecutive fp32 columns, issue only
+__device__ __forceinline__ void tc_ld8_nowait(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+
 }  // namespace ptx
 
 // instruction descriptor, kind::f16: fp32 accumulate, A and B K-major, M=128
@@ -347,6 +359,16 @@ __device__ __forceinline__ void store_chunk16(T* __restrict__ out, int pitch, in
                : "memory");
 }
 
+// half a chunk (8 channels, 16 bytes) per accumulator row: the column-split epilogue (two warps share a 32-byte pixel chunk)
+template <typename T, bool RELU = false>
+__device__ __forceinline__ void store_chunk8(T* __restrict__ out, int pitch, int off, int pix, const float (&v)[8]) {
+  if (pix < 0) return;
+  T* dst = out + (size_t)pix * pitch + off;
+  asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(pack2<T, RELU>(v[0], v[1])), "r"(pack2<T, RELU>(v[2], v[3])),
+               "r"(pack2<T, RELU>(v[4], v[5])), "r"(pack2<T, RELU>(v[6], v[7]))
+               : "memory");
+}
+
 // MODE: kConv1x1 | kConv3x3Taps (one MMA per tap, N = Cout: used for Cout >= 32 where the MMA is already efficient)
 //       | kConv3x3Fold (dx folded into N = 3*Cout: used for Cout = 16 where per-tap MMAs would be issue/smem bound)
 //       | kConv7x7 (Cin = 3 padded to 8: K = 16 is a PAIR of horizontally adjacent pixels x 8 channels; 7 dy x 4 dx-pairs = 28 MMAs,
@@ -367,24 +389,39 @@ struct UmmaTmaps { CUtensorMap m[kUmmaMaxKChunks]; };   // one tiled map per K-c
 //   kEpiPlain: +bias | kEpiRelu: +bias, ReLU | kEpiResidual: +bias, +residual | kEpiGate: CSAR gates | kEpiFinalSigmoid
 // TOUT: element type of the Up2Store output (the AutoEncoder and shallowF1 run fp16 operands in both 16-bit modes; the stage that
 // feeds the trunk writes the trunk's type)
-template <typename T, int NOUT, int MODE, int EPI, typename TOUT = T>
-__global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid_constant__ UmmaParams p, const __grid_constant__ UmmaTmaps tm) {
+// NS = 2 (per-tap 3x3, Cout = 32): the weights are carried as hi + lo concatenated along GEMM-N (columns [0, NOUT) hi, [NOUT, 2 NOUT) lo).
+// An M = 128 MMA costs max(N/2, 32 + N/4) clk, so N = 64 instead of 32 is 48 instead of 45 clk: weights at 22 significant bits for ~7 % of
+// tensor time; the epilogue adds the two column blocks.
+template <typename T, int NOUT, int MODE, int EPI, typename TOUT = T, int CS = 1, int NS = 1>
+__global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __grid_constant__ UmmaParams p, const __grid_constant__ UmmaTmaps tm) {
   static_assert(sizeof(T) == 2, "16-bit operands");
+  constexpr int kThreadsAll = umma_threads(CS);
+  constexpr int kEpiWarps = 4 * kEpiGroups * CS;               // warps [0, kEpiWarps): epilogue; then G MMA warps; then the TMA producer
+  constexpr int kMmaWarp0 = kEpiWarps, kLoaderWarp = kEpiWarps + kEpiGroups;
+  static_assert(CS == 1 || (CS == 2 && NOUT == 16 && (MODE == kConv3x3FoldLff || (MODE == kConv3x3Fold && EPI == kEpiRelu))),
+                "column split: the folded Cout = 16 layers");
   constexpr bool LFF = (MODE == kConv3x3FoldLff);
   constexpr bool FOLD = (MODE == kConv3x3Fold) || LFF;
   constexpr bool FOLD5 = (MODE == kConv5x5Fold);
   constexpr int HF = FOLD5 ? 2 : (FOLD ? 1 : 0);               // rows of a tile lost on each side to the dx fold
   static_assert(!LFF || NOUT == 16, "fused layer: growth rate 16");
   constexpr bool K3 = (MODE != kConv1x1);
-  constexpr int NMMA = LFF ? kLffCols : (FOLD5 ? 5 * NOUT : (FOLD ? 3 * NOUT : NOUT));   // TMEM columns per tile (and weight rows per K core-matrix)
+  static_assert(NS == 1 || (NS == 2 && MODE == kConv3x3Taps && NOUT == 32 && CS == 1), "N-split weights: per-tap 3x3, Cout = 32");
+  constexpr int NMMA = LFF ? kLffCols : (FOLD5 ? 5 * NOUT : (FOLD ? 3 * NOUT : NOUT * NS));   // TMEM columns per tile (and weight rows per K core-matrix)
   constexpr int KSZ = (MODE == kConv5x5Taps) ? 5 : 3;          // taps per kernel row (per-tap / folded modes)
   constexpr int NTAP = (MODE == kConv1x1 || MODE == kConv7x7) ? 1 : (FOLD5 ? 5 : (FOLD ? 3 : KSZ * KSZ));   // MMAs per K-step
   // floats of warp-boundary exchange (folded epilogues): [group][parity][warp][side][rows x NOUT]; 5-wide fold: 3 rows per side
   constexpr int XROW = FOLD5 ? 3 : 1;
   constexpr int XCH = (FOLD || FOLD5) ? kEpiGroups * 2 * 4 * 2 * XROW * NOUT : 0;
   constexpr int G = kEpiGroups;
-  static_assert(G * NMMA <= 512, "accumulators exceed TMEM");
-  constexpr uint32_t kTmemCols = (G * NMMA <= 32) ? 32 : (G * NMMA <= 64) ? 64 : (G * NMMA <= 128) ? 128 : (G * NMMA <= 256) ? 256 : 512;
+  // TMEM accumulators per epilogue group.  Two (dense folded layers): the group's MMA warp issues the next tile into the second
+  // accumulator while the epilogue warps still drain the first.  Clock traces (tools/umma_trace.py) show why: with one accumulator the three
+  // MMA warps issue in the same phase (tensor pipe saturated for ~850 clk) and then all wait for their epilogues (pipe idle): the pipe is
+  // 39 % busy although a tile's own MMAs take 270 clk.  Only together with the column-split epilogue (CS = 2), which is otherwise the next
+  // limiter at ~620 clk per tile.
+  constexpr int NACC = (MODE == kConv3x3Fold && CS == 2 && 2 * G * NMMA <= 512) ? 2 : 1;
+  constexpr int GA = G * NACC;                                  // accumulators in TMEM
+  constexpr uint32_t kTmemCols = (GA * NMMA <= 32) ? 32 : (GA * NMMA <= 64) ? 64 : (GA * NMMA <= 128) ? 128 : (GA * NMMA <= 256) ? 256 : 512;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // TMA swizzle atoms need 1024-byte aligned destinations: align the carve-up by hand
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -392,7 +429,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int CG = p.n_ks * 2;                                  // 8-channel groups of the whole K extent
   const uint32_t w_main_bytes = (uint32_t)NTAP * CG * NMMA * 16;
-  const uint32_t w_bytes = w_main_bytes + (LFF ? 2u * kLffN * 16u : 0u);   // fused: + lff's g3 slice [2][32][8]
+  const uint32_t w_bytes = w_main_bytes + (LFF ? 4u * kLffN * 16u : 0u);   // fused: + lff's g3 slice, hi and lo [2 + 2][32][8]
   const uint32_t buf_bytes = p.buf_bytes;                      // multiple of 1024
   uint8_t* a_smem = smem;                                      // item buffers first (1024-aligned)
   uint8_t* w_smem = smem + (size_t)p.n_bufs * buf_bytes;
@@ -404,11 +441,11 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (R + s); };
   auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * R + a); };
-  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * R + G + a); };
-  auto a2full_bar = [&](int a) { return bar0 + 8u * (2 * R + 2 * G + a); };      // fused layer: g3 operand of group a is in shared memory
-  auto tfull2_bar = [&](int a) { return bar0 + 8u * (2 * R + 3 * G + a); };      // fused layer: lff accumulator complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * R + 4 * G);
-  float* xchg = reinterpret_cast<float*>(bars + 2 * R + 4 * G + 2);
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * R + GA + a); };
+  auto a2full_bar = [&](int a) { return bar0 + 8u * (2 * R + 2 * GA + a); };     // fused layer: g3 operand of group a is in shared memory
+  auto tfull2_bar = [&](int a) { return bar0 + 8u * (2 * R + 2 * GA + G + a); }; // fused layer: lff accumulator complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * R + 2 * GA + 2 * G);
+  float* xchg = reinterpret_cast<float*>(bars + 2 * R + 2 * GA + 2 * G + 2);
   // per-K-slice MMA operand table {A offset in 16-B units inside the item buffer, row bytes/16, descriptor hi word, dy shift/16}
   uint4* steps = reinterpret_cast<uint4*>(xchg + XCH);
   int* slot_base_s = reinterpret_cast<int*>(steps + kUmmaMaxSteps);   // [R] written by the producer, read by the MMA warp
@@ -428,16 +465,16 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.w);
     uint4* dst = reinterpret_cast<uint4*>(w_smem);
-    for (uint32_t i = threadIdx.x; i < w_bytes / 16; i += kUmmaThreads) dst[i] = __ldg(src + i);
+    for (uint32_t i = threadIdx.x; i < w_bytes / 16; i += kThreadsAll) dst[i] = __ldg(src + i);
   }
   if constexpr (NOUT > 32) {
-    for (uint32_t i = threadIdx.x; i < (uint32_t)NOUT; i += kUmmaThreads) bias_s[i] = __ldg(p.bias + i);
+    for (uint32_t i = threadIdx.x; i < (uint32_t)NOUT; i += kThreadsAll) bias_s[i] = __ldg(p.bias + i);
   }
   if constexpr (LFF) {
     T* ones = reinterpret_cast<T*>(ones_s);
-    for (uint32_t i = threadIdx.x; i < 2 * 128 * 8; i += kUmmaThreads) ones[i] = from_f32<T>((i < 128 * 8 && (i & 7) < 2) ? 1.f : 0.f);
+    for (uint32_t i = threadIdx.x; i < 2 * 128 * 8; i += kThreadsAll) ones[i] = from_f32<T>((i < 128 * 8 && (i & 7) < 2) ? 1.f : 0.f);
     T* bb = reinterpret_cast<T*>(lffb_s);
-    for (uint32_t i = threadIdx.x; i < 2 * kLffCols * 8; i += kUmmaThreads) {
+    for (uint32_t i = threadIdx.x; i < 2 * kLffCols * 8; i += kThreadsAll) {
       const uint32_t k = i & 7, col = (i >> 3) % kLffCols, plane = (i >> 3) / kLffCols;
       float v = 0.f;
       if (plane == 0 && k < 2 && ((col >= 16 && col < 32) || col >= 48)) {
@@ -448,24 +485,26 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
       bb[i] = from_f32<T>(v);
     }
     T* idm = reinterpret_cast<T*>(lffid_s);
-    for (uint32_t i = threadIdx.x; i < 4 * 32 * 8; i += kUmmaThreads) idm[i] = from_f32<T>(((i >> 8) * 8 + (i & 7)) == ((i >> 3) & 31) ? 1.f : 0.f);
+    for (uint32_t i = threadIdx.x; i < 4 * 32 * 8; i += kThreadsAll) idm[i] = from_f32<T>(((i >> 8) * 8 + (i & 7)) == ((i >> 3) & 31) ? 1.f : 0.f);
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < R; ++s) {
       ptx::mbar_init(full_bar(s), 1);                           // the producer's arrive.expect_tx; TMA completes the bytes
       ptx::mbar_init(empty_bar(s), G);                          // one tcgen05.commit per MMA warp and item
     }
-    for (int a = 0; a < G; ++a) {
+    for (int a = 0; a < GA; ++a) {
       ptx::mbar_init(tfull_bar(a), 1);
-      ptx::mbar_init(tempty_bar(a), 4);                          // one arrival per epilogue warp
+      ptx::mbar_init(tempty_bar(a), 4 * CS);                     // one arrival per epilogue warp
+    }
+    for (int a = 0; a < G; ++a) {
       if constexpr (LFF) {
-        ptx::mbar_init(a2full_bar(a), 4);
+        ptx::mbar_init(a2full_bar(a), 4 * CS);
         ptx::mbar_init(tfull2_bar(a), 1);
       }
     }
     ptx::fence_mbar_init();
   }
-  if (warp == kUmmaMmaWarp) {
+  if (warp == kMmaWarp0) {
     ptx::tmem_alloc(ptx::smem_u32(tmem_slot), kTmemCols);
     ptx::tmem_relinquish();
     if (lane == 0 && MODE == kConv7x7) {
@@ -494,9 +533,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
   const int n_my_items = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int rows_per_item = p.k * p.tstride;
 
-  if (warp >= kUmmaFirstLoaderWarp) {
+  if (warp >= kLoaderWarp) {
     // =================================== TMA producer ==============================================
-    if (warp == kUmmaFirstLoaderWarp && ptx::elect_one()) {
+    if (warp == kLoaderWarp && ptx::elect_one()) {
       for (int c = 0; c < p.n_chunks; ++c) ptx::prefetch_tmap(&tm.m[c]);
       uint32_t item_bytes = 0;
       for (int c = 0; c < p.n_chunks; ++c) item_bytes += (uint32_t)p.npx * (uint32_t)p.chunk_ch[c] * 2u;
@@ -529,12 +568,12 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
         }
       }
     }
-  } else if (warp >= kUmmaMmaWarp) {
+  } else if (warp >= kMmaWarp0) {
     // =================================== MMA issuers ===============================================
     // One MMA warp per accumulator / epilogue group: warp g issues the tiles whose turn is g.  The serial latency of one
     // tile (barrier wake-up, descriptor set-up, MMA issue, commit: ~1000 clk measured) then overlaps G ways instead of
     // bounding the whole CTA.  Each warp runs the (uniform) control flow; one elected lane issues MMAs and commits.
-    const int mg = warp - kUmmaMmaWarp;
+    const int mg = warp - kMmaWarp0;
     const bool leader = ptx::elect_one();
     constexpr uint32_t idesc = umma_idesc_f16(IsBf16<T>::value, NMMA);
     constexpr uint32_t idesc48 = umma_idesc_f16(IsBf16<T>::value, 48), idesc32 = umma_idesc_f16(IsBf16<T>::value, kLffN);
@@ -550,8 +589,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
     const uint32_t tstride = (uint32_t)p.tstride;
     const bool no_mma = (p.debug & 1) != 0;
     __syncwarp();
-    const uint32_t acc = (uint32_t)mg;
-    uint32_t acc_par = 1;                                     // parity to wait for on this warp's tmem_empty barrier
+    uint32_t asel = 0;                                        // which of this warp's NACC accumulators the next tile uses
+    uint32_t acc_bits = 3u;                                   // parities to wait for on their tmem_empty barriers (bit per accumulator)
     int turn = 0;
     int buf = 0;
     uint32_t buf_par = 0;
@@ -568,7 +607,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
         if (!mine) continue;
         LPSR_TRACE(leader, ii * k_tiles + m, 0, clock64());
         LPSR_TRACE(leader, ii * k_tiles + m, 7, m < G ? tw1 - tw0 : 0);
-        ptx::mbar_wait(tempty_bar(acc), acc_par);             // the epilogue group drained this accumulator
+        const uint32_t acc = (uint32_t)mg + (uint32_t)G * asel;
+        ptx::mbar_wait(tempty_bar(acc), (acc_bits >> asel) & 1u);   // the epilogue group drained this accumulator
         ptx::tc_fence_after();
         LPSR_TRACE(leader, ii * k_tiles + m, 1, clock64());
         if (leader) {
@@ -583,6 +623,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
               if constexpr (LFF) {
                 if (ks < 2)   // + x: channels 16 ks .. 16 ks + 15 of the block input (centre tap) times the identity -> lff columns
                   ptx::tc_mma_f16_lohi(d + 48, a0 + e.w, e.z, lffid_lo + (uint32_t)(ks * 2 * 32), kUmmaDescHi, idesc32, 1u);
+                // lo terms of lff's weights over this K-slice (stored in the lff columns of the dy = 0 weight block), centre-row operand
+                ptx::tc_mma_f16_lohi(d + 48, a0 + e.w, e.z, b_lo + 48u, kUmmaDescHi, idesc32, 1u);
               }
 #pragma unroll
               for (int t = 0; t < NTAP; ++t) {
@@ -609,12 +651,16 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
           a2_par ^= 1u;
           ptx::tc_fence_after();
           if (leader) {
-            if (!no_mma) ptx::tc_mma_f16_lohi(tmem_base + acc * NMMA + 48, a2_lo, kUmmaDescHi, w2_lo, kUmmaDescHi, idesc32, 1u);
+            if (!no_mma) {
+              ptx::tc_mma_f16_lohi(tmem_base + acc * NMMA + 48, a2_lo, kUmmaDescHi, w2_lo, kUmmaDescHi, idesc32, 1u);
+              ptx::tc_mma_f16_lohi(tmem_base + acc * NMMA + 48, a2_lo, kUmmaDescHi, w2_lo + 2u * kLffN, kUmmaDescHi, idesc32, 1u);   // lo terms
+            }
             ptx::tc_commit(tfull2_bar(acc));
           }
           __syncwarp();
         }
-        acc_par ^= 1u;
+        acc_bits ^= 1u << asel;
+        asel ^= (uint32_t)(NACC - 1);
       }
       if (leader) ptx::tc_commit(empty_bar(buf));             // this warp's MMAs on the item buffer have retired (count G)
       __syncwarp();
@@ -622,7 +668,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
     }
   } else {
     // =================================== epilogue groups ============================================
-    const int grp = warp >> 2, wq = warp & 3;                   // group == TMEM accumulator (0..G-1), wq == TMEM lane quadrant
+    const int wq = warp & 3;                                    // TMEM lane quadrant
+    const int grp = (warp >> 2) % G;                            // group == TMEM accumulator (0..G-1)
+    [[maybe_unused]] const int half = (warp >> 2) / G;          // column split: which half of the output channels (0 when CS == 1)
     const int row = wq * 32 + lane;                             // accumulator row
     constexpr int CH = 16;                                      // output channels handled per pass (bounds registers)
     // raw residual registers (uint4) prefetched per tile, before the accumulator wait
@@ -631,7 +679,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
     T* out = static_cast<T*>(p.out);
     const T* res = static_cast<const T*>(p.res);
     float* xg = xchg + (size_t)grp * (2 * 4 * 2 * XROW * NOUT);
-    const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(grp * NMMA);
+    const uint32_t taddr0 = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(grp * NMMA);
     // everything the per-tile path needs lives in registers
     const int pitch = p.pitch, tstride = p.tstride, k_tiles = p.k, Himg = p.H, Wimg = p.W, halo = p.halo, TWs = p.TW;
     const int ips = p.items_per_strip, per_crop = p.n_strips * p.items_per_strip, crop_px = p.H * p.W;
@@ -641,11 +689,15 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
     const int adv_y = K3 ? tstride / pitch : 0, adv_x = K3 ? tstride - adv_y * pitch : 0;   // one tile further along the strip
     const int advg_y = K3 ? (G * tstride) / pitch : 0, advg_x = K3 ? G * tstride - advg_y * pitch : 0;   // G tiles further (the group's next tile)
     float bias_r[NB];
-    if constexpr (NOUT <= 32) {
+    if constexpr (CS == 2) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) bias_r[c] = __ldg(p.bias + half * 8 + c);
+    } else if constexpr (NOUT <= 32) {
 #pragma unroll
       for (int c = 0; c < NB; ++c) bias_r[c] = __ldg(p.bias + c);
     }
-    uint32_t my_par = 0;                                        // parity of this group's tmem_full barrier
+    uint32_t my_par = 0;                                        // flips with every tile of this group (exchange buffers, fused layer's barriers)
+    uint32_t esel = 0, full_bits = 0;                           // accumulator of the group's next tile; parities of the tmem_full barriers
     int t0mod = 0;                                              // (index of the item's first tile in the CTA's tile sequence) % G: tiles are dealt
                                                                 // round robin to the groups, the same way the MMA warps count them
     for (int ii = 0; ii < n_my_items; ++ii) {
@@ -703,7 +755,11 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
           }
         }
         LPSR_TRACE(wq == 0 && lane == 0, ii * k_tiles + m, 3, clock64());
-        ptx::mbar_wait(tfull_bar(grp), my_par);
+        const int accI = grp + G * (int)esel;                   // this tile's accumulator
+        const uint32_t taddr = taddr0 + esel * (uint32_t)(G * NMMA);
+        ptx::mbar_wait(tfull_bar(accI), (full_bits >> esel) & 1u);
+        full_bits ^= 1u << esel;
+        esel ^= (uint32_t)(NACC - 1);
         ptx::tc_fence_after();
         LPSR_TRACE(wq == 0 && lane == 0, ii * k_tiles + m, 4, clock64());
         float* xb = xg + (size_t)my_par * (4 * 2 * XROW * NOUT);
@@ -713,8 +769,71 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
         const int pix32 = valid ? pix : -1;
         // plain accumulators are read in blocks of up to 64 columns: all TMEM loads of a block in flight at once, one wait, and after
         // the last block the accumulator goes back to the MMA warp before any math
+        if constexpr (CS == 2) {
+          // ---- column-split folded epilogue: this warp owns output channels [cb, cb + 8) of its 32 rows
+          const int cb = half * 8;
+          float lf[8], v[8], rg[8];
+          ptx::tc_ld8_nowait(taddr + cb, lf);
+          ptx::tc_ld8_nowait(taddr + NOUT + cb, v);
+          ptx::tc_ld8_nowait(taddr + 2 * NOUT + cb, rg);
+          ptx::tc_wait_ld();
+          if constexpr (!LFF) {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty_bar(accI));    // accumulator is in registers
+          }
+          // out[q] = D[q-1, dx=0] + D[q, dx=1] + D[q+1, dx=2]; warp boundaries through the small exchange (disjoint channels per half)
+          if (lane == 31) {
+            *reinterpret_cast<float4*>(&xb[(wq * 2 + 0) * NOUT + cb]) = make_float4(lf[0], lf[1], lf[2], lf[3]);
+            *reinterpret_cast<float4*>(&xb[(wq * 2 + 0) * NOUT + cb + 4]) = make_float4(lf[4], lf[5], lf[6], lf[7]);
+          }
+          if (lane == 0) {
+            *reinterpret_cast<float4*>(&xb[(wq * 2 + 1) * NOUT + cb]) = make_float4(rg[0], rg[1], rg[2], rg[3]);
+            *reinterpret_cast<float4*>(&xb[(wq * 2 + 1) * NOUT + cb + 4]) = make_float4(rg[4], rg[5], rg[6], rg[7]);
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            lf[c] = __shfl_up_sync(0xffffffffu, lf[c], 1);
+            rg[c] = __shfl_down_sync(0xffffffffu, rg[c], 1);
+          }
+          ptx::bar_sync_named(1 + grp * 2 + half, 128);
+          if (lane == 0 && wq > 0) {
+            const float4 t0 = *reinterpret_cast<const float4*>(&xb[((wq - 1) * 2 + 0) * NOUT + cb]);
+            const float4 t1 = *reinterpret_cast<const float4*>(&xb[((wq - 1) * 2 + 0) * NOUT + cb + 4]);
+            lf[0] = t0.x; lf[1] = t0.y; lf[2] = t0.z; lf[3] = t0.w; lf[4] = t1.x; lf[5] = t1.y; lf[6] = t1.z; lf[7] = t1.w;
+          }
+          if (lane == 31 && wq < 3) {
+            const float4 t0 = *reinterpret_cast<const float4*>(&xb[((wq + 1) * 2 + 1) * NOUT + cb]);
+            const float4 t1 = *reinterpret_cast<const float4*>(&xb[((wq + 1) * 2 + 1) * NOUT + cb + 4]);
+            rg[0] = t0.x; rg[1] = t0.y; rg[2] = t0.z; rg[3] = t0.w; rg[4] = t1.x; rg[5] = t1.y; rg[6] = t1.z; rg[7] = t1.w;
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c) v[c] += lf[c] + rg[c];
+          if constexpr (!LFF) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) v[c] += bias_r[c];
+            store_chunk8<T, true>(out, out_pitch, out_off + cb, pix32, v);
+          } else {
+            // stage 1: this half's 8 channels of g3 = relu(conv + b3) are one plane of the K = 16 operand (bias came from the tensor core)
+            *reinterpret_cast<uint4*>(a2_all + (size_t)grp * 4096 + half * 2048 + row * 16) =
+                make_uint4(pack2<T, true>(v[0], v[1]), pack2<T, true>(v[2], v[3]), pack2<T, true>(v[4], v[5]), pack2<T, true>(v[6], v[7]));
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(a2full_bar(grp));
+            // stage 2: this half's 16 of the 32 columns x + alpha * lff(cat[x, g0..g3]) -> block output
+            ptx::mbar_wait(tfull2_bar(grp), tile_par);
+            ptx::tc_fence_after();
+            float o[16];
+            ptx::tc_ld16_nowait(taddr + 48 + half * 16, o);
+            ptx::tc_wait_ld();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty_bar(accI));
+            store_chunk16<T>(out, out_pitch, out_off + half * 16, pix32, o);
+          }
+        } else {
         constexpr bool PRELOAD = !FOLD && !FOLD5;
-        constexpr int PB = NOUT <= 64 ? NOUT : 64;
+        constexpr int PB = NS == 2 ? 16 : (NOUT <= 64 ? NOUT : 64);   // N-split: block by block, the lo block is added right after its load
         static_assert(NOUT % PB == 0, "block size");
         [[maybe_unused]] float vall[PRELOAD ? PB : 1];
 #pragma unroll
@@ -724,11 +843,17 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
             if (cc % PB == 0) {
 #pragma unroll
               for (int c2 = 0; c2 < PB; c2 += CH) ptx::tc_ld16_nowait(taddr + cc + c2, vall + c2);
+              [[maybe_unused]] float vlo[NS == 2 ? PB : 1];
+              if constexpr (NS == 2) ptx::tc_ld16_nowait(taddr + NOUT + cc, vlo);
               ptx::tc_wait_ld();
+              if constexpr (NS == 2) {
+#pragma unroll
+                for (int c = 0; c < PB; ++c) vall[c] += vlo[c];
+              }
               if (cc + PB >= NOUT) {
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(tempty_bar(grp));
+                if (lane == 0) ptx::mbar_arrive(tempty_bar(accI));
                 LPSR_TRACE(wq == 0 && lane == 0, ii * k_tiles + m, 5, clock64());
               }
             }
@@ -745,7 +870,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
             ptx::tc_wait_ld();
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(tempty_bar(grp));
+            if (lane == 0) ptx::mbar_arrive(tempty_bar(accI));
             // rows that cross a warp boundary travel through shared memory: up side {D0@30, D0@31, D1@31}, down side {D4@0, D4@1, D3@0}
             float* up = xb + (size_t)(wq * 2 + 0) * (XROW * NOUT);
             float* dn = xb + (size_t)(wq * 2 + 1) * (XROW * NOUT);
@@ -802,7 +927,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
             if (cc + CH >= NOUT && !LFF) {
               ptx::tc_fence_before();
               __syncwarp();
-              if (lane == 0) ptx::mbar_arrive(tempty_bar(grp));  // accumulator is in registers: hand TMEM back to the MMA warp
+              if (lane == 0) ptx::mbar_arrive(tempty_bar(accI));  // accumulator is in registers: hand TMEM back to the MMA warp
             }
             if (cc + CH >= NOUT) LPSR_TRACE(wq == 0 && lane == 0, ii * k_tiles + m, 5, clock64());
             // out[q] = D[q-1, dx=0] + D[q, dx=1] + D[q+1, dx=2]: neighbours by warp shuffle; across warp boundaries lane 31's
@@ -876,7 +1001,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
             ptx::tc_wait_ld();
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(tempty_bar(grp));
+            if (lane == 0) ptx::mbar_arrive(tempty_bar(accI));
 #pragma unroll
             for (int hh = 0; hh < kLffN / CH; ++hh) {
               float oc[CH];
@@ -964,6 +1089,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
             else if (v[0] == 123.456f) out[0] = from_f32<T>(v[1] + v[5] + v[9] + v[13]);
           }
         }
+        }   // CS == 1
         LPSR_TRACE(wq == 0 && lane == 0, ii * k_tiles + m, 6, clock64());
       }
     }
@@ -972,7 +1098,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv_kernel(const __grid
   // ---- teardown -----------------------------------------------------------------------------------
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == kUmmaMmaWarp) ptx::tmem_dealloc(tmem_base, kTmemCols);   // the warp that allocated
+  if (warp == kMmaWarp0) ptx::tmem_dealloc(tmem_base, kTmemCols);   // the warp that allocated
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1038,7 +1164,7 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
   const bool k3 = (w.ks == 3) || (w.ks == 5) || c7, fold = umma_fold(w.ks, w.cout);
   const bool lff = w.fused_lff;
   const bool fold5 = fold && w.ks == 5;
-  const int N = w.cout, NMMA = lff ? kLffCols : (fold ? w.ks * N : N), ntap = fold ? w.ks : ((w.ks == 3 || w.ks == 5) ? w.ks * w.ks : 1);
+  const int N = w.cout, NMMA = lff ? kLffCols : (fold ? w.ks * N : (w.nsplit ? 2 * N : N)), ntap = fold ? w.ks : ((w.ks == 3 || w.ks == 5) ? w.ks * w.ks : 1);
   const int halo = w.ks / 2;
   const size_t xch_bytes = fold ? (size_t)kEpiGroups * 2 * 4 * 2 * (fold5 ? 3 : 1) * N * 4 : 0;
   p.halo = halo;
@@ -1046,6 +1172,7 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
   p.n_ks_real = w.wsplit ? p.n_ks / 2 : p.n_ks;
   if (p.n_ks > kUmmaMaxSteps) return "too many K-steps";
   if (w.wsplit && (lff || c7)) return "hi + lo weights are not supported by this mode";
+  if (w.nsplit && (w.ks != 3 || fold || lff || w.wsplit || N != 32)) return "N-split weights: per-tap 3x3 with Cout = 32 only";
   if (!c7 && cp.n_chunks != p.n_ks_real) return "chunk table does not match Cin/16";
   if (!fp32_out && (cp.out_pitch % 16 || cp.out_off % 16 || reinterpret_cast<uintptr_t>(cp.out) % 32)) return "output pitch/offset not 32-byte aligned (256-bit stores)";
   if (cp.res && (cp.res_pitch % 8 || cp.res_off % 8)) return "residual pitch/offset not 16-byte aligned";
@@ -1105,10 +1232,10 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
     if (tr_on) { cudaMemsetAsync(trace, 0, 512 * 8 * sizeof(long long)); p.trace = trace; umma_trace_buffer() = trace; }
 #endif
   }
-  const size_t w_bytes = ((size_t)ntap * w.cin * NMMA * 2 + (lff ? 2 * kLffN * 16 : 0) + 127) & ~(size_t)127;
+  const size_t w_bytes = ((size_t)ntap * w.cin * NMMA * 2 + (lff ? 4 * kLffN * 16 : 0) + 127) & ~(size_t)127;
   const size_t a2_bytes = lff ? (size_t)kEpiGroups * 4096 + 2 * 128 * 16 + 2 * kLffCols * 16 + 4 * 32 * 16   // g3 operands, ones, biases, identity
                               : (N > 32 ? (size_t)N * 4 : 0);                                                   // wide layers: bias vector
-  const size_t fixed = w_bytes + (2 * kUmmaMaxBufs + 4 * kEpiGroups + 2) * 8 + xch_bytes + a2_bytes + 640 /*steps, slot_base*/ + 1024 /*alignment slack*/ + 256;
+  const size_t fixed = w_bytes + (2 * kUmmaMaxBufs + 6 * kEpiGroups + 2) * 8 + xch_bytes + a2_bytes + 640 /*steps, slot_base*/ + 1024 /*alignment slack*/ + 256;
   const size_t smem_cap = 227 * 1024 - fixed;
   auto item_buf_bytes = [&](size_t npx) {                      // every chunk is 1024-aligned inside the buffer
     size_t b = 0;
@@ -1183,7 +1310,7 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
   if (bufs < 2) return "tile does not fit in shared memory";
   if (bufs > kUmmaMaxBufs) bufs = kUmmaMaxBufs;
   p.n_bufs = bufs;
-  plan.smem_bytes = (size_t)bufs * off + w_bytes + (2 * bufs + 4 * kEpiGroups + 2) * 8 + xch_bytes + a2_bytes + 640 + 1024 + 64;
+  plan.smem_bytes = (size_t)bufs * off + w_bytes + (2 * bufs + 6 * kEpiGroups + 2) * 8 + xch_bytes + a2_bytes + 640 + 1024 + 64;
   plan.grid = std::min(p.n_items, num_sms);
   // ---- tensor maps, one per K-chunk
   for (int c = 0; c < p.n_chunks; ++c)
@@ -1220,26 +1347,44 @@ inline bool* func_configured_flag(bool (&flags)[kMaxDevices]) {
   return &flags[dev];
 }
 
-template <typename T, int N, int MODE, int EPI, typename TOUT = T>
+inline bool umma_column_split() {   // LPSR_EPI_SPLIT=0: one epilogue warp per lane quadrant everywhere (the round-1 layout)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("LPSR_EPI_SPLIT"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
+template <typename T, int N, int MODE, int EPI, typename TOUT = T, int CS = 1, int NS = 1>
 inline const char* umma_launch_inst(const UmmaPlan& plan, cudaStream_t st) {
   static bool configured[kMaxDevices] = {};
   bool* flag = func_configured_flag(configured);
   if (!flag || !*flag) {
-    cudaError_t e = cudaFuncSetAttribute(umma_conv_kernel<T, N, MODE, EPI, TOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(umma_conv_kernel<T, N, MODE, EPI, TOUT, CS, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return cudaGetErrorString(e);
     if (flag) *flag = true;
   }
-  cudaError_t e = launch_pdl(umma_conv_kernel<T, N, MODE, EPI, TOUT>, dim3(plan.grid), dim3(kUmmaThreads), plan.smem_bytes, st, plan.p, plan.tm);
+  cudaError_t e = launch_pdl(umma_conv_kernel<T, N, MODE, EPI, TOUT, CS, NS>, dim3(plan.grid), dim3(umma_threads(CS)), plan.smem_bytes, st, plan.p, plan.tm);
   if (e == cudaSuccess) e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
 // epilogue selection: plain / ReLU / residual (mutually exclusive in this network) or the special modes
 template <typename T, int N, int MODE>
-inline const char* umma_launch_epi(const UmmaPlan& plan, cudaStream_t st) {
+inline const char* umma_launch_epi(const UmmaPlan& plan, cudaStream_t st, bool nsplit = false) {
   const UmmaParams& p = plan.p;
+  if constexpr (N == 32 && MODE == kConv3x3Taps) {
+    if (nsplit) {   // hi + lo weights along N (the CSAR conv_in pair)
+      if (p.mode == kEpiPlain && p.relu && !p.res) return umma_launch_inst<T, N, MODE, kEpiRelu, T, 1, 2>(plan, st);
+      if (p.mode == kEpiPlain && !p.relu && !p.res) return umma_launch_inst<T, N, MODE, kEpiPlain, T, 1, 2>(plan, st);
+      if (p.mode == kEpiPool) return umma_launch_inst<T, N, MODE, kEpiPool, T, 1, 2>(plan, st);
+      return "N-split weights: epilogue not instantiated";
+    }
+  }
+  if (nsplit) return "N-split weights: shape not instantiated";
   if (p.mode == kEpiPlain && p.relu && p.res) return "ReLU + residual epilogue is not instantiated";
   if (p.mode == kEpiPlain && p.res) return umma_launch_inst<T, N, MODE, kEpiResidual>(plan, st);
+  if constexpr (N == 16 && MODE == kConv3x3Fold) {
+    if (p.mode == kEpiPlain && p.relu && umma_column_split()) return umma_launch_inst<T, N, MODE, kEpiRelu, T, 2>(plan, st);
+  }
   if (p.mode == kEpiPlain && p.relu) return umma_launch_inst<T, N, MODE, kEpiRelu>(plan, st);
   if (p.mode == kEpiPlain) return umma_launch_inst<T, N, MODE, kEpiPlain>(plan, st);
   if constexpr (N == 32 && MODE == kConv1x1) {
@@ -1267,10 +1412,13 @@ inline const char* umma_plan_launch(const UmmaPlan& plan, const UmmaWeights& w, 
     return "5x5 conv: shape/epilogue not instantiated";
   }
   if (w.ks == 3) {
-    if (w.fused_lff) return (mode == kEpiPlain && plan.p.res) ? umma_launch_inst<T, 16, kConv3x3FoldLff, kEpiResidual>(plan, st)
-                                                               : "fused dense layer + lff needs the residual";
+    if (w.fused_lff) {
+      if (!(mode == kEpiPlain && plan.p.res)) return "fused dense layer + lff needs the residual";
+      return umma_column_split() ? umma_launch_inst<T, 16, kConv3x3FoldLff, kEpiResidual, T, 2>(plan, st)
+                                 : umma_launch_inst<T, 16, kConv3x3FoldLff, kEpiResidual>(plan, st);
+    }
     if (w.cout == 16) return umma_launch_epi<T, 16, kConv3x3Fold>(plan, st);
-    if (w.cout == 32) return umma_launch_epi<T, 32, kConv3x3Taps>(plan, st);
+    if (w.cout == 32) return umma_launch_epi<T, 32, kConv3x3Taps>(plan, st, w.nsplit);
     if (w.cout == 48 && plain) return plan.p.relu ? umma_launch_inst<T, 48, kConv3x3Taps, kEpiRelu>(plan, st)
                                                   : umma_launch_inst<T, 48, kConv3x3Taps, kEpiPlain>(plan, st);
   } else {

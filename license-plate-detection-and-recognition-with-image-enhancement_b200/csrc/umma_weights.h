@@ -18,7 +18,8 @@ struct UmmaWeights {
   int ks = 0, cin = 0, cout = 0;
   uint16_t* w = nullptr;   // 16-bit (bf16 or fp16): 1x1 [cin/8][cout][8]; 3x3 [dy][cin/8][dx*cout + co][8] (dx folded into N)
   float* bias = nullptr;   // [cout] (zeros if the conv has no bias)
-  bool fused_lff = false;  // kConv3x3FoldLff: w = [dy][cin/8][48 folded + 32 lff][8] then lff's g3 slice [2][32][8]; bias = [16] + [32]
+  bool fused_lff = false;  // kConv3x3FoldLff: w = [dy][cin/8][48 folded + 32 lff (dy = 1: hi, dy = 0: lo)][8] then lff's g3 slice [2 hi, 2 lo][32][8]; bias = [16] + [32]
+  bool nsplit = false;     // per-tap 3x3: weights carried as hi + lo along N: packed rows [0, cout) hi, [cout, 2 cout) lo; cout stays the real one
   bool wsplit = false;     // weights carried as hi + lo (two 16-bit terms): cin is DOUBLED, K-slices [cin/2, cin) hold the lo terms and
                            // re-read the activations of K-slices [0, cin/2) (no second copy in shared memory)
 };
@@ -178,14 +179,39 @@ bool umma_pack_weights_wsplit(UmmaWeights& u, const float* pw, const float* bias
   return ok;
 }
 
+// Weights as hi + lo concatenated along GEMM-N (per-tap 3x3 convs): one MMA per tap with N = 2 * cout instead of two MMAs.
+template <typename PutU16, typename PutF32>
+bool umma_pack_weights_nsplit(UmmaWeights& u, const float* pw, const float* bias, int ks, int cin, int cout, bool fp16, PutU16 put16, PutF32 put32) {
+  const int taps = ks * ks;
+  std::vector<float> p2((size_t)taps * cin * 2 * cout);
+  for (int t = 0; t < taps; ++t)
+    for (int ci = 0; ci < cin; ++ci)
+      for (int co = 0; co < cout; ++co) {
+        const float w = pw[((size_t)t * cin + ci) * cout + co];
+        const float hi = bits16_to_f32(f32_to_bits16(w, fp16), fp16);
+        p2[((size_t)t * cin + ci) * 2 * cout + co] = hi;
+        p2[((size_t)t * cin + ci) * 2 * cout + cout + co] = w - hi;
+      }
+  std::vector<float> b2(2 * cout, 0.f);
+  if (bias) for (int co = 0; co < cout; ++co) b2[co] = bias[co];
+  const bool ok = umma_pack_weights(u, p2.data(), b2.data(), ks, cin, 2 * cout, fp16, put16, put32);
+  u.cout = cout;
+  u.nsplit = true;
+  return ok;
+}
+
 // Last dense layer of an RDB (3x3, cin -> 16, ReLU) fused with the block's local feature fusion (1x1 over cin + 16 channels -> 32,
 // alpha already folded in, lpsr.py:52-61).  w3: fp32 [9][cin][16]; wl: fp32 [cin + 16][32].
 template <typename PutU16, typename PutF32>
 bool umma_pack_fused_lff(UmmaWeights& u, const float* w3, const float* b3, const float* wl, const float* bl, int cin, bool fp16, PutU16 put16,
                          PutF32 put32) {
   const int cg = cin / 8, nf = 80;
-  std::vector<uint16_t> v((size_t)3 * cg * nf * 8 + 2 * 32 * 8, 0);
+  // lff's weights are carried as hi + lo (its rounding error is one of the largest single contributions to the output error with the shipped
+  // checkpoint, tools/parity_report.py): the lo terms over the layer's own input channels sit in the otherwise unused lff columns of the
+  // dy = 0 block (no extra shared memory), the lo terms of the g3 slice follow the hi ones.
+  std::vector<uint16_t> v((size_t)3 * cg * nf * 8 + 4 * 32 * 8, 0);
   auto cvt = [&](float f) { return fp16 ? f32_to_f16_bits(f) : f32_to_bf16_bits(f); };
+  auto lo16 = [&](float f) { return cvt(f - bits16_to_f32(cvt(f), fp16)); };
   for (int dy = 0; dy < 3; ++dy)
     for (int g = 0; g < cg; ++g)
       for (int j = 0; j < 8; ++j) {
@@ -194,11 +220,16 @@ bool umma_pack_fused_lff(UmmaWeights& u, const float* w3, const float* b3, const
           for (int n = 0; n < 16; ++n) v[(((size_t)dy * cg + g) * nf + dx * 16 + n) * 8 + j] = cvt(w3[((size_t)(dy * 3 + dx) * cin + ci) * 16 + n]);
         if (dy == 1)
           for (int n = 0; n < 32; ++n) v[(((size_t)dy * cg + g) * nf + 48 + n) * 8 + j] = cvt(wl[(size_t)ci * 32 + n]);
+        if (dy == 0)
+          for (int n = 0; n < 32; ++n) v[(((size_t)dy * cg + g) * nf + 48 + n) * 8 + j] = lo16(wl[(size_t)ci * 32 + n]);
       }
   const size_t base2 = (size_t)3 * cg * nf * 8;
   for (int g = 0; g < 2; ++g)
     for (int n = 0; n < 32; ++n)
-      for (int j = 0; j < 8; ++j) v[base2 + ((size_t)g * 32 + n) * 8 + j] = cvt(wl[(size_t)(cin + g * 8 + j) * 32 + n]);
+      for (int j = 0; j < 8; ++j) {
+        v[base2 + ((size_t)g * 32 + n) * 8 + j] = cvt(wl[(size_t)(cin + g * 8 + j) * 32 + n]);
+        v[base2 + 2 * 32 * 8 + ((size_t)g * 32 + n) * 8 + j] = lo16(wl[(size_t)(cin + g * 8 + j) * 32 + n]);
+      }
   std::vector<float> b(48, 0.f);
   for (int n = 0; n < 16; ++n) b[n] = b3[n];
   for (int n = 0; n < 32; ++n) b[16 + n] = bl[n];
