@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "liblpsr_b200.so")
-SOURCES = ["engine.cu", "inst_f32.cu", "inst_bf16.cu", "inst_f16.cu"]
+SOURCES = ["engine.cu", "inst_f32.cu", "inst_bf16.cu", "inst_f16.cu", "inst_split.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + os.environ.get("LPSR_NVCC_EXTRA", "").split()
 

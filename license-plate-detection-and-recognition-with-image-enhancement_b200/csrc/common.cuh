@@ -16,7 +16,7 @@ namespace lpsr {
 constexpr int kTileH = 8;      // CUDA-core kernels: one CTA = 8x32 output pixels, one thread per pixel
 constexpr int kTileW = 32;
 constexpr int kThreads = 256;
-constexpr int kMaxChunks = 12;
+constexpr int kMaxChunks = 16;   // 16-channel chunks of a gather list (split mode: gff.0 reads 4 x 64 = 256 16-bit channels)
 
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
@@ -126,6 +126,7 @@ struct TailParams {
   const void* res; int res_pitch, res_off;      // CSAR input x (residual, lpsr.py:186)
   void* out; int out_pitch, out_off;
   void* out2; int out2_pitch, out2_off;         // optional second copy of the output (nullptr = none)
+  const float* sc;                              // [B][32] channel gates computed by channel_gate_kernel (nullptr: from pool_partial here)
   const float* pool_partial;                    // [B][S][32] per-slice channel sums of x_in
   int S;
   const float* ca_w1; const float* ca_b1;       // Linear 32->8  [8][32], [8]      (lpsr.py:126)

@@ -461,7 +461,60 @@ static __global__ void __launch_bounds__(256) channel_gate_kernel(const float* _
 //   s_s = sigmoid(W4 relu(W3 x_in + b3) + b4)  per pixel                   (SpatialAttention, lpsr.py:138-153)
 //   out = x + Wo [x_in^2 * s_c ; x_in * s_s] + bo                          (CSAR.forward, lpsr.py:182-186)
 // ---------------------------------------------------------------------------------------------------
-template <typename T>
+// split (double-fp16) rows: 32 real channels = two chunks of [16 hi | 16 lo] 16-bit values (see store_chunk16_split in umma_conv.cuh)
+__device__ __forceinline__ void load_split32(const __half* __restrict__ p, float (&out)[32]) {
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    float hi[16], lo[16];
+    load_vec<__half, 16>(p + g * 32, hi);
+    load_vec<__half, 16>(p + g * 32 + 16, lo);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) out[g * 16 + c] = hi[c] + lo[c];
+  }
+}
+__device__ __forceinline__ void store_split32(__half* __restrict__ p, const float (&v)[32]) {
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    float hi[16], lo[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      hi[c] = __half2float(from_f32<__half>(v[g * 16 + c]));
+      lo[c] = v[g * 16 + c] - hi[c];
+    }
+    store_vec<__half, 16>(p + g * 32, hi);
+    store_vec<__half, 16>(p + g * 32 + 16, lo);
+  }
+}
+// fp32 NHWC [n_chunks][16] -> split [n_chunks][16 hi | 16 lo] IN PLACE (same 64 bytes per chunk; a thread reads its chunk before writing it)
+static __global__ void f32_to_split_inplace_kernel(float* __restrict__ buf, long long n_chunks) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_chunks; i += (long long)gridDim.x * blockDim.x) {
+    float v[16], hi[16], lo[16];
+    load_vec<float, 16>(buf + i * 16, v);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      hi[c] = __half2float(from_f32<__half>(v[c]));
+      lo[c] = v[c] - hi[c];
+    }
+    __half* o = reinterpret_cast<__half*>(buf + i * 16);
+    store_vec<__half, 16>(o, hi);
+    store_vec<__half, 16>(o + 16, lo);
+  }
+}
+// split NHWC (2C 16-bit channels per pixel) -> fp32 NCHW [B][C][H][W] (debug taps)
+static __global__ void split_nhwc_to_nchw_kernel(const __half* __restrict__ src, float* __restrict__ dst, int B, int C, int H, int W) {
+  const long long total = (long long)B * C * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    const int y = (int)((i / W) % H);
+    const int c = (int)((i / ((long long)W * H)) % C);
+    const int n = (int)(i / ((long long)W * H * C));
+    const __half* p = src + ((size_t)(n * H + y) * W + x) * (2 * C) + (c / 16) * 32 + c % 16;
+    dst[i] = __half2float(p[0]) + __half2float(p[16]);
+  }
+}
+
+// SPLIT: x_in, the residual and the output are split tensors (T = __half, pitches in 16-bit elements); the arithmetic is the same fp32
+template <typename T, bool SPLIT = false>
 __global__ void __launch_bounds__(kThreads) csar_tail_kernel(const TailParams p) {
   constexpr int F = 32, F2 = 64, HID = 8;
   __shared__ __align__(16) float s_w3[F * F2];
@@ -479,10 +532,14 @@ __global__ void __launch_bounds__(kThreads) csar_tail_kernel(const TailParams p)
     s_b4[tid] = __ldg(p.sa_b2 + tid);
     s_bo[tid] = __ldg(p.co_b + tid);
     float t = 0.f;
-    for (int s = 0; s < p.S; ++s) t += p.pool_partial[((size_t)b * p.S + s) * F + tid];
+    if (!p.sc)
+      for (int s = 0; s < p.S; ++s) t += p.pool_partial[((size_t)b * p.S + s) * F + tid];
     s_mean[tid] = t / (float)p.P;
   }
   __syncthreads();
+  if (p.sc) {   // the gates of this crop were computed once per crop by channel_gate_kernel
+    if (tid < F) s_sc[tid] = p.sc[(size_t)b * F + tid];
+  } else {
   if (tid < HID) {
     float t = __ldg(p.ca_b1 + tid);
     for (int c = 0; c < F; ++c) t = fmaf(s_mean[c], __ldg(p.ca_w1 + tid * F + c), t);
@@ -494,6 +551,7 @@ __global__ void __launch_bounds__(kThreads) csar_tail_kernel(const TailParams p)
     for (int j = 0; j < HID; ++j) t = fmaf(s_hid[j], __ldg(p.ca_w2 + tid * HID + j), t);
     s_sc[tid] = sigmoid_f32(t);
   }
+  }
   __syncthreads();
 
   const int pix = blockIdx.x * kThreads + tid;
@@ -501,7 +559,8 @@ __global__ void __launch_bounds__(kThreads) csar_tail_kernel(const TailParams p)
   const size_t gp = (size_t)b * p.P + pix;
 
   float xin[F];
-  load_vec<T, F>(static_cast<const T*>(p.x_in) + gp * p.xin_pitch + p.xin_off, xin);
+  if constexpr (SPLIT) load_split32(static_cast<const __half*>(p.x_in) + gp * p.xin_pitch + p.xin_off, xin);
+  else load_vec<T, F>(static_cast<const T*>(p.x_in) + gp * p.xin_pitch + p.xin_off, xin);
 
   float acc[F];
 #pragma unroll
@@ -569,11 +628,16 @@ __global__ void __launch_bounds__(kThreads) csar_tail_kernel(const TailParams p)
     }
   }
   float r[F];
-  load_vec<T, F>(static_cast<const T*>(p.res) + gp * p.res_pitch + p.res_off, r);
+  if constexpr (SPLIT) load_split32(static_cast<const __half*>(p.res) + gp * p.res_pitch + p.res_off, r);
+  else load_vec<T, F>(static_cast<const T*>(p.res) + gp * p.res_pitch + p.res_off, r);
 #pragma unroll
   for (int c = 0; c < F; ++c) acc[c] += r[c];
-  store_vec<T, F>(static_cast<T*>(p.out) + gp * p.out_pitch + p.out_off, acc);
-  if (p.out2) store_vec<T, F>(static_cast<T*>(p.out2) + gp * p.out2_pitch + p.out2_off, acc);
+  if constexpr (SPLIT) {
+    store_split32(static_cast<__half*>(p.out) + gp * p.out_pitch + p.out_off, acc);
+  } else {
+    store_vec<T, F>(static_cast<T*>(p.out) + gp * p.out_pitch + p.out_off, acc);
+    if (p.out2) store_vec<T, F>(static_cast<T*>(p.out2) + gp * p.out2_pitch + p.out2_off, acc);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -143,6 +143,11 @@ bool pack_conv(lpsr_handle* h, ConvW& cw, const std::string& prefix, int cin, in
                            [&](const std::vector<float>& v) { return arena_put(h, v); }))
       return false;
   }
+  cw.us = UmmaWeights{};
+  if (h->fp32_split && umma_supported(ks, cin, cout) && 3 * cin / 16 <= kUmmaMaxSteps &&
+      !umma_pack_weights_split(cw.us, pw.data(), bias ? pb.data() : nullptr, ks, cin, cout, [&](const std::vector<uint16_t>& v) { return arena_put(h, v); },
+                               [&](const std::vector<float>& v) { return arena_put(h, v); }))
+    return false;
   return true;
 }
 
@@ -439,6 +444,21 @@ int pack_all(lpsr_handle* h) {
     ok &= umma_pack_weights(h->fin_u, pw.data(), pb.data(), 3, F, 16, h->cfg.precision == LPSR_PREC_FP16,
                             [&](const std::vector<uint16_t>& v) { return arena_put(h, v); }, [&](const std::vector<float>& v) { return arena_put(h, v); });
   }
+  h->fin_us = UmmaWeights{};
+  if (h->fp32_split) {   // final conv for split operands: Cout padded 1 -> 16 with zero filters
+    const std::vector<float>& w = W(h, "final_conv.weight");
+    std::vector<float> pw((size_t)9 * F * 16, 0.f), pb(16, 0.f);
+    for (int ci = 0; ci < F; ++ci)
+      for (int t = 0; t < 9; ++t) pw[((size_t)t * F + ci) * 16] = w[(size_t)ci * 9 + t];
+    pb[0] = W(h, "final_conv.bias")[0];
+    ok &= umma_pack_weights_split(h->fin_us, pw.data(), pb.data(), 3, F, 16, [&](const std::vector<uint16_t>& v) { return arena_put(h, v); },
+                                  [&](const std::vector<float>& v) { return arena_put(h, v); });
+    ok &= h->sfe2.us.packed && h->gff0.us.packed && h->gff1.us.packed && h->csar_c1.us.packed && h->csar_c2.us.packed;
+    for (int r = 0; r < 2; ++r) {
+      ok &= h->lff[r].us.packed;
+      for (int i = 0; i < L; ++i) ok &= h->rdb[r][i].us.packed;
+    }
+  }
   if (!ok) return fail(h, LPSR_ERR_CUDA, "weight packing failed (arena %zu/%zu bytes): %s", h->arena.used, h->arena.cap,
                        cudaGetErrorString(cudaGetLastError()));
   h->packed = true;
@@ -477,7 +497,7 @@ WsLayout ws_layout(const lpsr_handle* h, int B, int H, int W) {
   L.g0 = take(BP * 32, es);
   L.g = take(BP * 32, es);
   // 16-bit modes: one partial per (tile, epilogue warp) of conv_in.2; a crop has at most ~1.3 x P/126 tiles (halo rows of its strips)
-  L.pool_slots = half_mode(h) ? 4 * (2 * (L.P / 128) + 40) : 0;
+  L.pool_slots = (half_mode(h) || h->fp32_split) ? 4 * (2 * (L.P / 128) + 40) : 0;
   L.pool = take((size_t)B * std::max(S, L.pool_slots) * 32, 4);
   L.sc = take((size_t)B * 32, 4);
   if (half_mode(h)) {   // tensor-core CSAR tail: 64-channel hidden map and the gated concat [x_in^2*s_c | x_in*s_s]
@@ -494,7 +514,9 @@ namespace {
 int forward_dispatch(lpsr_handle* h, const float* x, float* y, int B, int H, int W, char* ws, cudaStream_t st, bool dry, int* nl,
                      LaunchProfile* prof = nullptr) {
   switch (h->cfg.precision) {
-    case LPSR_PREC_FP32: return forward_impl<float>(h, x, y, B, H, W, ws, st, dry, nl, prof);
+    case LPSR_PREC_FP32:
+      if (h->fp32_split) return forward_split_entry(h, x, y, B, H, W, ws, st, dry, nl, prof);
+      return forward_impl<float>(h, x, y, B, H, W, ws, st, dry, nl, prof);
     case LPSR_PREC_BF16: return forward_impl<__nv_bfloat16>(h, x, y, B, H, W, ws, st, dry, nl, prof);
     case LPSR_PREC_FP16: return forward_impl<__half>(h, x, y, B, H, W, ws, st, dry, nl, prof);
     default: return fail(h, LPSR_ERR_UNSUPPORTED, "precision mode %d not built", h->cfg.precision);
@@ -572,6 +594,8 @@ int lpsr_create(lpsr_handle** out, const lpsr_config* cfg) {
   h->cfg = *cfg;
   h->sm = prop.major * 10 + prop.minor;
   h->num_sms = prop.multiProcessorCount;
+  // fp32 mode = tensor cores with split (double-fp16) operands; LPSR_FP32_FFMA=1 (or LPSR_UMMA=0) keeps the CUDA-core FFMA path
+  h->fp32_split = cfg->precision == LPSR_PREC_FP32 && umma_enabled() && !getenv("LPSR_FP32_FFMA");
   build_live_table(h);
   *out = h;
   return LPSR_OK;
@@ -810,6 +834,8 @@ int lpsr_debug_read_tap(lpsr_handle* h, const char* name, float* dst, int64_t ds
     if (dst_numel != need) return fail(h, LPSR_ERR_INVALID_ARG, "tap '%s' has %lld elements, buffer has %lld", name, (long long)need, (long long)dst_numel);
     char* ws = static_cast<char*>(wsv);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (h->fp32_split && strncmp(t.name, "ae.", 3))   // trunk tensors of the fp32 mode are split (double-fp16) tensors
+      return tap_copy_split(h, ws + t.off, dst, B, t.C, Ht, Wt, st);
     if (t.ae_half)   // tensor-core AutoEncoder intermediates are fp16 in both 16-bit modes
       return tap_copy_impl<__half>(h, ws + t.off, dst, B, t.C, Ht, Wt, t.pitch, t.choff, t.unshuffled, st);
     switch (h->cfg.precision) {

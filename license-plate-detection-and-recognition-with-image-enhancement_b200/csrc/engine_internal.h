@@ -33,6 +33,7 @@ struct ConvW {
   float* w = nullptr;      // [ks*ks][cin][cout] fp32 (CUDA-core kernels)
   float* b = nullptr;      // [cout] fp32 (nullptr: no bias)
   UmmaWeights u;           // tensor-core packing (16-bit modes)
+  UmmaWeights us;          // tensor-core packing for split (double-fp16) operands: the fp32-accuracy mode (forward_split.cuh)
 };
 
 // Tensor-core CSAR tail: the channel branch x_in^2 * s_c (lpsr.py:133-135,182-184) reaches a few thousand with the shipped checkpoint
@@ -57,6 +58,8 @@ struct lpsr_handle {
   // packed layers
   lpsr::ConvW ae_in, ae_out, sfe1, sfe2, rdb[2][4], lff[2], csar_c1, csar_c2, csar_sa1, csar_sa2, csar_co, gff0, gff1, fin;
   lpsr::UmmaWeights fin_u;   // final conv with Cout padded 1 -> 16 for the tensor-core path
+  lpsr::UmmaWeights fin_us;  // the same for split operands
+  bool fp32_split = false;   // LPSR_PREC_FP32 runs its dense trunk layers on tensor cores with split operands (LPSR_FP32_FFMA=1: CUDA cores)
   lpsr::UmmaWeights sfe1_u;  // shallowF1 7x7 as 28 pixel-pair K-steps over an 8-channel padded input (tensor-core path)
   lpsr::UmmaWeights ae_out_u; // AutoEncoder conv_out 12 -> 3 on tensor cores: Cin padded to 16, Cout padded to 16 (zeros)
   // Tensor-core AutoEncoder (16-bit modes): every stage is ONE dense convolution on the half / quarter grid, the pixel
@@ -117,6 +120,9 @@ WsLayout ws_layout(const lpsr_handle* h, int B, int H, int W);
 template <typename T>
 int forward_impl(lpsr_handle* h, const float* x, float* y, int B, int H, int W, char* ws, cudaStream_t st, bool dry, int* n_launch,
                  LaunchProfile* prof);
+int forward_split_entry(lpsr_handle* h, const float* x, float* y, int B, int H, int W, char* ws, cudaStream_t st, bool dry, int* n_launch,
+                        LaunchProfile* prof);
+int tap_copy_split(lpsr_handle* h, const void* src, float* dst, int B, int C, int H, int W, cudaStream_t st);
 template <typename T>
 int op_conv_impl(lpsr_handle* h, const float* x, const float* w_oihw, const float* bias, float* y, int B, int Cin, int Cout, int ks,
                  int H, int W, int relu, cudaStream_t st);

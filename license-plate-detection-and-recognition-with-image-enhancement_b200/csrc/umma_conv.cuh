@@ -60,7 +60,9 @@ constexpr int kUmmaMaxBufs = 4;         // item buffers in the shared-memory rin
 
 struct UmmaParams {
   int n_ks;                         // K-slices of 16 channels (weights split into hi + lo terms: twice the activation K-slices)
-  int n_ks_real;                    // K-slices staged in shared memory; K-slice ks >= n_ks_real re-reads the tile of ks - n_ks_real
+  int n_ks_real;                    // K-slices staged in shared memory; K-slice ks >= n_ks_real re-reads the tile of (ks - n_ks_real) * wlo_step
+  float acc_scale;                  // split mode: accumulator scale 2^-s undoing the power-of-two scaling of the packed weights
+  int wlo_step;                     // 1; 2 in the split (hi | lo activation) mode, whose lo-weight K-slices re-read only the hi tiles
   // A operand = n_chunks TMA boxes per item: chunk c has chunk_ch[c] channels (16/32/64 -> swizzle 32/64/128 B) starting at
   // channel coordinate chunk_coff[c] of tensor map chunk_map[c], and lives at byte offset chunk_smem[c] of the item buffer
   int n_chunks;
@@ -359,6 +361,37 @@ __device__ __forceinline__ void store_chunk16(T* __restrict__ out, int pitch, in
                : "memory");
 }
 
+// Split (double-fp16) tensors -- the fp32-accuracy mode on tensor cores.  A real channel is carried as hi + lo, two 16-bit values with
+// hi = rn16(v), lo = rn16(v - hi) (22 significant bits in fp16), stored per 16-channel chunk as [16 hi | 16 lo]: a tensor of C real
+// channels is an NHWC 16-bit tensor of 2C channels, its chunks alternate hi and lo, and every convolution multiplies
+// A_hi * W_hi + A_lo * W_hi + A_hi * W_lo (fp32 accumulation in TMEM; the dropped lo * lo term is 2^-22 relative).
+// One 64-byte store per accumulator row and real 16-channel chunk.  pitch / off are in 16-bit elements of the split tensor.
+template <typename T, bool RELU = false>
+__device__ __forceinline__ void store_chunk16_split(T* __restrict__ out, int pitch, int off, int pix, const float (&vin)[16]) {
+  static_assert(!IsBf16<T>::value, "split tensors are fp16 pairs");
+  if (pix < 0) return;
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float a = vin[2 * i], b = vin[2 * i + 1];
+    if constexpr (RELU) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+    hi[i] = pack2<T, false>(a, b);
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hi[i]));
+    lo[i] = pack2<T, false>(a - f.x, b - f.y);
+  }
+  T* dst = out + (size_t)pix * pitch + off;
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]),
+               "r"(hi[6]), "r"(hi[7]) : "memory");
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 16), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(lo[4]), "r"(lo[5]),
+               "r"(lo[6]), "r"(lo[7]) : "memory");
+}
+// SP selects the tensor representation of an epilogue store of real channels [cc, cc + 16) (off = the tensor's channel offset in ELEMENTS)
+template <typename T, bool RELU, bool SP>
+__device__ __forceinline__ void store_out16(T* __restrict__ out, int pitch, int off, int cc, int pix, const float (&v)[16]) {
+  if constexpr (SP) store_chunk16_split<T, RELU>(out, pitch, off + 2 * cc, pix, v);
+  else store_chunk16<T, RELU>(out, pitch, off + cc, pix, v);
+}
+
 // half a chunk (8 channels, 16 bytes) per accumulator row: the column-split epilogue (two warps share a 32-byte pixel chunk)
 template <typename T, bool RELU = false>
 __device__ __forceinline__ void store_chunk8(T* __restrict__ out, int pitch, int off, int pix, const float (&v)[8]) {
@@ -392,7 +425,7 @@ struct UmmaTmaps { CUtensorMap m[kUmmaMaxKChunks]; };   // one tiled map per K-c
 // NS = 2 (per-tap 3x3, Cout = 32): the weights are carried as hi + lo concatenated along GEMM-N (columns [0, NOUT) hi, [NOUT, 2 NOUT) lo).
 // An M = 128 MMA costs max(N/2, 32 + N/4) clk, so N = 64 instead of 32 is 48 instead of 45 clk: weights at 22 significant bits for ~7 % of
 // tensor time; the epilogue adds the two column blocks.
-template <typename T, int NOUT, int MODE, int EPI, typename TOUT = T, int CS = 1, int NS = 1>
+template <typename T, int NOUT, int MODE, int EPI, typename TOUT = T, int CS = 1, int NS = 1, bool SP = false>
 __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __grid_constant__ UmmaParams p, const __grid_constant__ UmmaTmaps tm) {
   static_assert(sizeof(T) == 2, "16-bit operands");
   constexpr int kThreadsAll = umma_threads(CS);
@@ -406,6 +439,7 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
   constexpr int HF = FOLD5 ? 2 : (FOLD ? 1 : 0);               // rows of a tile lost on each side to the dx fold
   static_assert(!LFF || NOUT == 16, "fused layer: growth rate 16");
   constexpr bool K3 = (MODE != kConv1x1);
+  static_assert(!SP || (CS == 1 && NS == 1 && !IsBf16<T>::value), "split tensors: fp16 pairs, plain epilogue layout");
   static_assert(NS == 1 || (NS == 2 && MODE == kConv3x3Taps && NOUT == 32 && CS == 1), "N-split weights: per-tap 3x3, Cout = 32");
   constexpr int NMMA = LFF ? kLffCols : (FOLD5 ? 5 * NOUT : (FOLD ? 3 * NOUT : NOUT * NS));   // TMEM columns per tile (and weight rows per K core-matrix)
   constexpr int KSZ = (MODE == kConv5x5Taps) ? 5 : 3;          // taps per kernel row (per-tap / folded modes)
@@ -457,7 +491,8 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
   // fused layer: the additions of its two epilogue passes run on the tensor core (its pipe has slack, the epilogue warps do not): a
   // "ones" operand times {hi(bias), lo(bias)} starts the accumulator at the biases (b3 in the dx = 1 block, lff's in columns 48..79),
   // and x (chunk 0 of the staged block, centre tap) times a 32x32 identity adds the residual exactly.
-  uint8_t* ones_s = a2_all + (size_t)G * 4096;                 // [2 planes][128 rows][8]: k = 0, 1 are 1.0
+  constexpr uint32_t kA2Bytes = SP ? 8192u : 4096u;            // g3 operand per group: [2 planes][128 rows][8] (split: hi, then lo)
+  uint8_t* ones_s = a2_all + (size_t)G * kA2Bytes;             // [2 planes][128 rows][8]: k = 0, 1 are 1.0
   uint8_t* lffb_s = ones_s + 2 * 128 * 16;                     // [2][80][8]
   uint8_t* lffid_s = lffb_s + 2 * kLffCols * 16;               // [4][32][8]
 
@@ -518,7 +553,7 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
         for (int kk = 0; kk < (p.chunk_ch[c] >> 4); ++kk, ++ks)
           steps[ks] = make_uint4((p.chunk_smem[c] >> 4) + 2u * (uint32_t)kk, rb16, umma_desc_hi_swizzled(rb16 << 4), (uint32_t)p.pitch * rb16);
       }
-      for (; ks < p.n_ks; ++ks) steps[ks] = steps[ks - p.n_ks_real];   // lo-weight K-slices: same activation tiles
+      for (; ks < p.n_ks; ++ks) steps[ks] = steps[(ks - p.n_ks_real) * p.wlo_step];   // lo-weight K-slices: same activation tiles (split: the hi tiles)
     }
   }
   ptx::fence_proxy_async();      // weights were written with st.shared: make them visible to the tensor core proxy
@@ -578,7 +613,7 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
     constexpr uint32_t idesc = umma_idesc_f16(IsBf16<T>::value, NMMA);
     constexpr uint32_t idesc48 = umma_idesc_f16(IsBf16<T>::value, 48), idesc32 = umma_idesc_f16(IsBf16<T>::value, kLffN);
     const uint32_t w2_lo = umma_desc_lo(ptx::smem_u32(w_smem) + w_main_bytes, (uint32_t)kLffN * 16);
-    const uint32_t a2_lo = umma_desc_lo(ptx::smem_u32(a2_all) + (uint32_t)mg * 4096u, 2048u);
+    const uint32_t a2_lo = umma_desc_lo(ptx::smem_u32(a2_all) + (uint32_t)mg * kA2Bytes, 2048u);
     const uint32_t ones_lo = umma_desc_lo(ptx::smem_u32(ones_s), 2048u), lffb_lo = umma_desc_lo(ptx::smem_u32(lffb_s), (uint32_t)kLffCols * 16),
                    lffid_lo = umma_desc_lo(ptx::smem_u32(lffid_s), 32u * 16);
     uint32_t a2_par = 0;
@@ -621,10 +656,12 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
               const uint4 e = steps[ks];
               const uint32_t a0 = (buf16 + e.x + slot * e.y) | (1u << 16);
               if constexpr (LFF) {
-                if (ks < 2)   // + x: channels 16 ks .. 16 ks + 15 of the block input (centre tap) times the identity -> lff columns
-                  ptx::tc_mma_f16_lohi(d + 48, a0 + e.w, e.z, lffid_lo + (uint32_t)(ks * 2 * 32), kUmmaDescHi, idesc32, 1u);
-                // lo terms of lff's weights over this K-slice (stored in the lff columns of the dy = 0 weight block), centre-row operand
-                ptx::tc_mma_f16_lohi(d + 48, a0 + e.w, e.z, b_lo + 48u, kUmmaDescHi, idesc32, 1u);
+                // + x: channels 16 r .. 16 r + 15 of the block input (centre tap) times the identity -> lff columns (split: hi and lo chunks)
+                if (ks < (SP ? 4 : 2))
+                  ptx::tc_mma_f16_lohi(d + 48, a0 + e.w, e.z, lffid_lo + (uint32_t)((SP ? (ks >> 1) : ks) * 2 * 32), kUmmaDescHi, idesc32, 1u);
+                // lo terms of lff's weights over this K-slice (stored in the lff columns of the dy = 0 weight block), centre-row operand;
+                // split mode: the lo-weight K-slices at the end of the K extent carry them instead
+                if constexpr (!SP) ptx::tc_mma_f16_lohi(d + 48, a0 + e.w, e.z, b_lo + 48u, kUmmaDescHi, idesc32, 1u);
               }
 #pragma unroll
               for (int t = 0; t < NTAP; ++t) {
@@ -654,6 +691,8 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
             if (!no_mma) {
               ptx::tc_mma_f16_lohi(tmem_base + acc * NMMA + 48, a2_lo, kUmmaDescHi, w2_lo, kUmmaDescHi, idesc32, 1u);
               ptx::tc_mma_f16_lohi(tmem_base + acc * NMMA + 48, a2_lo, kUmmaDescHi, w2_lo + 2u * kLffN, kUmmaDescHi, idesc32, 1u);   // lo terms
+              if constexpr (SP)   // g3's lo operand times the hi weights
+                ptx::tc_mma_f16_lohi(tmem_base + acc * NMMA + 48, a2_lo + (4096u >> 4), kUmmaDescHi, w2_lo, kUmmaDescHi, idesc32, 1u);
             }
             ptx::tc_commit(tfull2_bar(acc));
           }
@@ -686,6 +725,7 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
     const int out_pitch = p.out_pitch, out_off = p.out_off, res_pitch = p.res_pitch, res_off = p.res_off;
     const int total_px32 = (int)p.total_px;
     const bool skip_store = (p.debug & 2) != 0;
+    [[maybe_unused]] const float acc_scale = p.acc_scale;
     const int adv_y = K3 ? tstride / pitch : 0, adv_x = K3 ? tstride - adv_y * pitch : 0;   // one tile further along the strip
     const int advg_y = K3 ? (G * tstride) / pitch : 0, advg_x = K3 ? G * tstride - advg_y * pitch : 0;   // G tiles further (the group's next tile)
     float bias_r[NB];
@@ -748,7 +788,7 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
         }
         // operands that do not depend on the accumulator are requested before waiting for it
         uint4 rsd_raw[NRES];                                    // raw 16-bit residual: converted only after the accumulator arrived
-        if constexpr ((EPI == kEpiResidual && NOUT <= 32 && !LFF) || (EPI == kEpiReluResidual && NOUT <= 48)) {
+        if constexpr (!SP && ((EPI == kEpiResidual && NOUT <= 32 && !LFF) || (EPI == kEpiReluResidual && NOUT <= 48))) {
           if (pix >= 0) {
 #pragma unroll
             for (int i = 0; i < NRES; ++i) rsd_raw[i] = *reinterpret_cast<const uint4*>(res + (size_t)pix * res_pitch + res_off + i * 8);
@@ -970,6 +1010,9 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
           }
           if constexpr (LFF) {
             // biases and the residual were accumulated by the tensor core
+          } else if constexpr (NOUT <= 32 && SP) {
+#pragma unroll
+            for (int c = 0; c < CH; ++c) v[c] = fmaf(v[c], acc_scale, bias_r[cc + c]);
           } else if constexpr (NOUT <= 32) {
 #pragma unroll
             for (int c = 0; c < CH; ++c) v[c] += bias_r[cc + c];
@@ -983,11 +1026,22 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
           if constexpr (LFF) {
             // ---- stage 1: g3 = relu(conv + bias) becomes the K = 16 operand of lff's last slice (planes of 8 channels, row = 16 B)
             {
-              uint8_t* a2 = a2_all + (size_t)grp * 4096;
-              *reinterpret_cast<uint4*>(a2 + row * 16) =
-                  make_uint4(pack2<T, true>(v[0], v[1]), pack2<T, true>(v[2], v[3]), pack2<T, true>(v[4], v[5]), pack2<T, true>(v[6], v[7]));
-              *reinterpret_cast<uint4*>(a2 + 2048 + row * 16) =
-                  make_uint4(pack2<T, true>(v[8], v[9]), pack2<T, true>(v[10], v[11]), pack2<T, true>(v[12], v[13]), pack2<T, true>(v[14], v[15]));
+              uint8_t* a2 = a2_all + (size_t)grp * kA2Bytes;
+              uint32_t hi[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) hi[i] = pack2<T, true>(v[2 * i], v[2 * i + 1]);
+              *reinterpret_cast<uint4*>(a2 + row * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(a2 + 2048 + row * 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+              if constexpr (SP) {   // g3's lo operand: relu(v) - hi
+                uint32_t lo[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hi[i]));
+                  lo[i] = pack2<T, false>(fmaxf(v[2 * i], 0.f) - f.x, fmaxf(v[2 * i + 1], 0.f) - f.y);
+                }
+                *reinterpret_cast<uint4*>(a2 + 4096 + row * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                *reinterpret_cast<uint4*>(a2 + 6144 + row * 16) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+              }
             }
             ptx::fence_proxy_async();                           // generic-proxy stores -> visible to the tensor core
             __syncwarp();
@@ -1007,7 +1061,7 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
               float oc[CH];
 #pragma unroll
               for (int c = 0; c < CH; ++c) oc[c] = o[hh * CH + c];
-              store_chunk16<T>(out, out_pitch, out_off + hh * CH, pix32, oc);
+              store_out16<T, false, SP>(out, out_pitch, out_off, hh * CH, pix32, oc);
             }
           } else if constexpr (EPI == kEpiFinalSigmoid) {
             // final conv (Cout = 1, padded to 16): channel 0 only, fp32; lanes are consecutive pixels -> coalesced 4-byte stores
@@ -1063,7 +1117,23 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
                 }
               }
             }
-            if constexpr (EPI == kEpiResidual) {
+            if constexpr (EPI == kEpiResidual && SP) {
+              if (valid) {   // residual as a split tensor: [16 hi | 16 lo] per chunk
+                const uint4* rp = reinterpret_cast<const uint4*>(res + (size_t)pix * res_pitch + res_off + 2 * cc);
+                const uint4 h0 = rp[0], h1 = rp[1], l0 = rp[2], l1 = rp[3];
+                const __half2* hh2[2] = {reinterpret_cast<const __half2*>(&h0), reinterpret_cast<const __half2*>(&h1)};
+                const __half2* ll2[2] = {reinterpret_cast<const __half2*>(&l0), reinterpret_cast<const __half2*>(&l1)};
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float2 a = __half22float2(hh2[q][i]), b = __half22float2(ll2[q][i]);
+                    v[q * 8 + 2 * i] += a.x + b.x;
+                    v[q * 8 + 2 * i + 1] += a.y + b.y;
+                  }
+              }
+            }
+            if constexpr (EPI == kEpiResidual && !SP) {
               if (valid) {
                 float r[CH];
                 if constexpr (NOUT > 32) {
@@ -1085,7 +1155,7 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
               if (!(lane & 1)) p.pool[((size_t)(item * k_tiles + m) * 4 + wq) * NOUT + cc + ((lane >> 1) & 15)] = tot;
             }
             // all 32 lanes take part in the staged, coalesced store (rows without a pixel are skipped inside)
-            if (!LPSR_DBG(32)) store_chunk16<T, EPI == kEpiRelu>(out, out_pitch, out_off + cc, pix32, v);
+            if (!LPSR_DBG(32)) store_out16<T, EPI == kEpiRelu, SP>(out, out_pitch, out_off, cc, pix32, v);
             else if (v[0] == 123.456f) out[0] = from_f32<T>(v[1] + v[5] + v[9] + v[13]);
           }
         }
@@ -1169,9 +1239,11 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
   const size_t xch_bytes = fold ? (size_t)kEpiGroups * 2 * 4 * 2 * (fold5 ? 3 : 1) * N * 4 : 0;
   p.halo = halo;
   p.n_ks = w.cin / 16;                                       // 7x7: 28 pixel-pair steps (UmmaWeights::cin = 448 pseudo channels)
-  p.n_ks_real = w.wsplit ? p.n_ks / 2 : p.n_ks;
+  p.n_ks_real = w.split ? w.n_real : (w.wsplit ? p.n_ks / 2 : p.n_ks);
+  p.wlo_step = w.split ? 2 : 1;
+  p.acc_scale = w.split ? w.acc_scale : 1.f;
   if (p.n_ks > kUmmaMaxSteps) return "too many K-steps";
-  if (w.wsplit && (lff || c7)) return "hi + lo weights are not supported by this mode";
+  if (w.wsplit && !w.split && (lff || c7)) return "hi + lo weights are not supported by this mode";
   if (w.nsplit && (w.ks != 3 || fold || lff || w.wsplit || N != 32)) return "N-split weights: per-tap 3x3 with Cout = 32 only";
   if (!c7 && cp.n_chunks != p.n_ks_real) return "chunk table does not match Cin/16";
   if (!fp32_out && (cp.out_pitch % 16 || cp.out_off % 16 || reinterpret_cast<uintptr_t>(cp.out) % 32)) return "output pitch/offset not 32-byte aligned (256-bit stores)";
@@ -1233,7 +1305,7 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
 #endif
   }
   const size_t w_bytes = ((size_t)ntap * w.cin * NMMA * 2 + (lff ? 4 * kLffN * 16 : 0) + 127) & ~(size_t)127;
-  const size_t a2_bytes = lff ? (size_t)kEpiGroups * 4096 + 2 * 128 * 16 + 2 * kLffCols * 16 + 4 * 32 * 16   // g3 operands, ones, biases, identity
+  const size_t a2_bytes = lff ? (size_t)kEpiGroups * (w.split ? 8192 : 4096) + 2 * 128 * 16 + 2 * kLffCols * 16 + 4 * 32 * 16   // g3 operands, ones, biases, identity
                               : (N > 32 ? (size_t)N * 4 : 0);                                                   // wide layers: bias vector
   const size_t fixed = w_bytes + (2 * kUmmaMaxBufs + 6 * kEpiGroups + 2) * 8 + xch_bytes + a2_bytes + 640 /*steps, slot_base*/ + 1024 /*alignment slack*/ + 256;
   const size_t smem_cap = 227 * 1024 - fixed;
@@ -1353,16 +1425,16 @@ inline bool umma_column_split() {   // LPSR_EPI_SPLIT=0: one epilogue warp per l
   return v == 1;
 }
 
-template <typename T, int N, int MODE, int EPI, typename TOUT = T, int CS = 1, int NS = 1>
+template <typename T, int N, int MODE, int EPI, typename TOUT = T, int CS = 1, int NS = 1, bool SP = false>
 inline const char* umma_launch_inst(const UmmaPlan& plan, cudaStream_t st) {
   static bool configured[kMaxDevices] = {};
   bool* flag = func_configured_flag(configured);
   if (!flag || !*flag) {
-    cudaError_t e = cudaFuncSetAttribute(umma_conv_kernel<T, N, MODE, EPI, TOUT, CS, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(umma_conv_kernel<T, N, MODE, EPI, TOUT, CS, NS, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return cudaGetErrorString(e);
     if (flag) *flag = true;
   }
-  cudaError_t e = launch_pdl(umma_conv_kernel<T, N, MODE, EPI, TOUT, CS, NS>, dim3(plan.grid), dim3(umma_threads(CS)), plan.smem_bytes, st, plan.p, plan.tm);
+  cudaError_t e = launch_pdl(umma_conv_kernel<T, N, MODE, EPI, TOUT, CS, NS, SP>, dim3(plan.grid), dim3(umma_threads(CS)), plan.smem_bytes, st, plan.p, plan.tm);
   if (e == cudaSuccess) e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
@@ -1399,8 +1471,34 @@ inline const char* umma_launch_epi(const UmmaPlan& plan, cudaStream_t st, bool n
   return "epilogue mode not instantiated for this shape";
 }
 
+// split (double-fp16) tensors: the dense trunk layers of the fp32-accuracy mode
+template <typename T>
+inline const char* umma_plan_launch_split(const UmmaPlan& plan, const UmmaWeights& w, cudaStream_t st) {
+  if constexpr (IsBf16<T>::value) {
+    return "split tensors are fp16 pairs";
+  } else {
+    const UmmaParams& p = plan.p;
+    const bool plain = p.mode == kEpiPlain;
+    if (w.fused_lff) return "the fused layer + lff kernel is not used with split tensors (its weights would not fit shared memory)";
+    if (w.ks == 3 && w.cout == 16) {
+      if (p.mode == kEpiFinalSigmoid) return umma_launch_inst<T, 16, kConv3x3Fold, kEpiFinalSigmoid, T, 1, 1, true>(plan, st);
+      if (plain && p.relu && !p.res) return umma_launch_inst<T, 16, kConv3x3Fold, kEpiRelu, T, 1, 1, true>(plan, st);
+    }
+    if (w.ks == 3 && w.cout == 32) {
+      if (p.mode == kEpiPool) return umma_launch_inst<T, 32, kConv3x3Taps, kEpiPool, T, 1, 1, true>(plan, st);
+      if (plain && p.res && !p.relu) return umma_launch_inst<T, 32, kConv3x3Taps, kEpiResidual, T, 1, 1, true>(plan, st);
+      if (plain && p.relu && !p.res) return umma_launch_inst<T, 32, kConv3x3Taps, kEpiRelu, T, 1, 1, true>(plan, st);
+      if (plain && !p.relu && !p.res) return umma_launch_inst<T, 32, kConv3x3Taps, kEpiPlain, T, 1, 1, true>(plan, st);
+    }
+    if (w.ks == 1 && w.cout == 32 && plain && !p.relu && !p.res) return umma_launch_inst<T, 32, kConv1x1, kEpiPlain, T, 1, 1, true>(plan, st);
+    if (w.ks == 1 && w.cout == 32 && plain && !p.relu && p.res) return umma_launch_inst<T, 32, kConv1x1, kEpiResidual, T, 1, 1, true>(plan, st);
+    return "split tensors: shape/epilogue not instantiated";
+  }
+}
+
 template <typename T, typename TOUT = T>
 inline const char* umma_plan_launch(const UmmaPlan& plan, const UmmaWeights& w, cudaStream_t st) {
+  if (w.split) return umma_plan_launch_split<T>(plan, w, st);
   const int mode = plan.p.mode;
   const bool plain = (mode == kEpiPlain && !plan.p.res);
   if (w.ks == 7) return w.cout == 32 ? umma_launch_epi<T, 32, kConv7x7>(plan, st) : "unsupported Cout";

@@ -19,6 +19,11 @@ struct UmmaWeights {
   uint16_t* w = nullptr;   // 16-bit (bf16 or fp16): 1x1 [cin/8][cout][8]; 3x3 [dy][cin/8][dx*cout + co][8] (dx folded into N)
   float* bias = nullptr;   // [cout] (zeros if the conv has no bias)
   bool fused_lff = false;  // kConv3x3FoldLff: w = [dy][cin/8][48 folded + 32 lff (dy = 1: hi, dy = 0: lo)][8] then lff's g3 slice [2 hi, 2 lo][32][8]; bias = [16] + [32]
+  bool split = false;      // split (double-fp16) activations: K rows = per real 16-channel chunk [W_hi for the hi chunk, W_hi for the lo chunk], then the
+                           // lo terms of the weights once per real chunk (re-reading the hi tiles); n_real = K-slices staged in shared memory
+  int n_real = 0;
+  float acc_scale = 1.f;   // split packing: weights are stored times 2^s (so that their lo terms stay normal fp16 numbers); the epilogue
+                           // multiplies the accumulator by acc_scale = 2^-s before the bias
   bool nsplit = false;     // per-tap 3x3: weights carried as hi + lo along N: packed rows [0, cout) hi, [cout, 2 cout) lo; cout stays the real one
   bool wsplit = false;     // weights carried as hi + lo (two 16-bit terms): cin is DOUBLED, K-slices [cin/2, cin) hold the lo terms and
                            // re-read the activations of K-slices [0, cin/2) (no second copy in shared memory)
@@ -200,8 +205,97 @@ bool umma_pack_weights_nsplit(UmmaWeights& u, const float* pw, const float* bias
   return ok;
 }
 
+// Split mode (see store_chunk16_split in umma_conv.cuh).  pw: fp32 [taps][cin][cout] over the REAL channels; the packed K extent is
+// 3 * cin: [hi chunk g: hi(W_g)] [lo chunk g: hi(W_g)] for every real 16-channel chunk g, then [lo(W_g)] for every g.
+inline std::vector<float> split_weight_rows(const float* pw, int taps, int cin, int cout) {
+  std::vector<float> p3((size_t)taps * 3 * cin * cout);
+  for (int t = 0; t < taps; ++t)
+    for (int ci = 0; ci < cin; ++ci) {
+      const int g = ci / 16, j = ci % 16;
+      for (int co = 0; co < cout; ++co) {
+        const float w = pw[((size_t)t * cin + ci) * cout + co];
+        const float hi = bits16_to_f32(f32_to_bits16(w, true), true);
+        p3[((size_t)t * 3 * cin + g * 32 + j) * cout + co] = hi;
+        p3[((size_t)t * 3 * cin + g * 32 + 16 + j) * cout + co] = hi;
+        p3[((size_t)t * 3 * cin + 2 * cin + ci) * cout + co] = w - hi;
+      }
+    }
+  return p3;
+}
+// 2^s with max |w| * 2^s in [2^12, 2^13): far below the fp16 maximum, and the lo term of a weight 2^-10 times smaller than the largest is
+// still a normal fp16 number (without the scaling the lo terms of this network's weights, ~1e-5, are subnormal: 3e-8 absolute = 2^-19 relative)
+inline float split_weight_scale(const float* pw, size_t n) {
+  float m = 0.f;
+  for (size_t i = 0; i < n; ++i) m = std::max(m, std::fabs(pw[i]));
+  if (!(m > 0.f) || !std::isfinite(m)) return 1.f;
+  int e;
+  std::frexp(m, &e);                 // m = f * 2^e, f in [0.5, 1)
+  return std::ldexp(1.f, 13 - e);
+}
+template <typename PutU16, typename PutF32>
+bool umma_pack_weights_split(UmmaWeights& u, const float* pw_in, const float* bias, int ks, int cin, int cout, PutU16 put16, PutF32 put32) {
+  const size_t n = (size_t)ks * ks * cin * cout;
+  const float sc = split_weight_scale(pw_in, n);
+  std::vector<float> pws(pw_in, pw_in + n);
+  for (auto& v : pws) v *= sc;
+  const float* pw = pws.data();
+  u.acc_scale = 1.f / sc;
+  const std::vector<float> p3 = split_weight_rows(pw, ks * ks, cin, cout);
+  const bool ok = umma_pack_weights(u, p3.data(), bias, ks, 3 * cin, cout, true, put16, put32);
+  u.wsplit = true;
+  u.split = true;
+  u.n_real = 2 * cin / 16;
+  return ok;
+}
+
 // Last dense layer of an RDB (3x3, cin -> 16, ReLU) fused with the block's local feature fusion (1x1 over cin + 16 channels -> 32,
 // alpha already folded in, lpsr.py:52-61).  w3: fp32 [9][cin][16]; wl: fp32 [cin + 16][32].
+// Split mode of the fused layer: K rows as in split_weight_rows (hi weights for hi and lo chunks, then the lo weights); lff's columns sit in
+// the dy = 1 block for every K row; the g3 slice keeps its [2 hi, 2 lo][32][8] layout (the kernel multiplies g3_hi * hi, g3_hi * lo, g3_lo * hi).
+template <typename PutU16, typename PutF32>
+bool umma_pack_fused_lff_split(UmmaWeights& u, const float* w3, const float* b3, const float* wl, const float* bl, int cin, PutU16 put16, PutF32 put32) {
+  const int K = 3 * cin, cg = K / 8, nf = 80;
+  std::vector<uint16_t> v((size_t)3 * cg * nf * 8 + 4 * 32 * 8, 0);
+  auto cvt = [&](float f) { return f32_to_f16_bits(f); };
+  auto hi_of = [&](float f) { return bits16_to_f32(f32_to_f16_bits(f), true); };
+  for (int k = 0; k < K; ++k) {
+    int ci;
+    bool lo;
+    if (k < 2 * cin) { ci = (k / 32) * 16 + k % 16; lo = false; } else { ci = k - 2 * cin; lo = true; }
+    const int g = k / 8, j = k % 8;
+    for (int dy = 0; dy < 3; ++dy) {
+      for (int dx = 0; dx < 3; ++dx)
+        for (int n = 0; n < 16; ++n) {
+          const float w = w3[((size_t)(dy * 3 + dx) * cin + ci) * 16 + n];
+          v[(((size_t)dy * cg + g) * nf + dx * 16 + n) * 8 + j] = cvt(lo ? w - hi_of(w) : w);
+        }
+      if (dy == 1)
+        for (int n = 0; n < 32; ++n) {
+          const float w = wl[(size_t)ci * 32 + n];
+          v[(((size_t)dy * cg + g) * nf + 48 + n) * 8 + j] = cvt(lo ? w - hi_of(w) : w);
+        }
+    }
+  }
+  const size_t base2 = (size_t)3 * cg * nf * 8;
+  for (int g = 0; g < 2; ++g)
+    for (int n = 0; n < 32; ++n)
+      for (int j = 0; j < 8; ++j) {
+        const float w = wl[(size_t)(cin + g * 8 + j) * 32 + n];
+        v[base2 + ((size_t)g * 32 + n) * 8 + j] = cvt(w);
+        v[base2 + 2 * 32 * 8 + ((size_t)g * 32 + n) * 8 + j] = cvt(w - hi_of(w));
+      }
+  std::vector<float> b(48, 0.f);
+  for (int n = 0; n < 16; ++n) b[n] = b3[n];
+  for (int n = 0; n < 32; ++n) b[16 + n] = bl[n];
+  u.w = put16(v);
+  u.bias = put32(b);
+  u.ks = 3; u.cin = K; u.cout = 16;
+  u.fused_lff = true;
+  u.wsplit = true; u.split = true; u.n_real = 2 * cin / 16;
+  u.packed = (u.w != nullptr && u.bias != nullptr);
+  return u.packed;
+}
+
 template <typename PutU16, typename PutF32>
 bool umma_pack_fused_lff(UmmaWeights& u, const float* w3, const float* b3, const float* wl, const float* bl, int cin, bool fp16, PutU16 put16,
                          PutF32 put32) {
