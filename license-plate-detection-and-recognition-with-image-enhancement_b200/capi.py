@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liblpsr_b200.so")
+# LPSR_B200_LIB: another build of the same library (A/B measurements of kernel variants); default: the in-tree build
+LIB_PATH = os.environ.get("LPSR_B200_LIB") or os.path.join(HERE, "liblpsr_b200.so")
 ABI_VERSION = 1
 
 PREC = {"fp32": 0, "bf16": 1, "fp16": 2}

@@ -453,7 +453,10 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
   // MMA warps issue in the same phase (tensor pipe saturated for ~850 clk) and then all wait for their epilogues (pipe idle): the pipe is
   // 39 % busy although a tile's own MMAs take 270 clk.  Only together with the column-split epilogue (CS = 2), which is otherwise the next
   // limiter at ~620 clk per tile.
-  constexpr int NACC = (MODE == kConv3x3Fold && CS == 2 && 2 * G * NMMA <= 512) ? 2 : 1;
+  #ifndef LPSR_UMMA_NACC_FOLD
+#define LPSR_UMMA_NACC_FOLD 0
+#endif
+  constexpr int NACC = (MODE == kConv3x3Fold && (CS == 2 || LPSR_UMMA_NACC_FOLD) && 2 * G * NMMA <= 512) ? 2 : 1;
   constexpr int GA = G * NACC;                                  // accumulators in TMEM
   constexpr uint32_t kTmemCols = (GA * NMMA <= 32) ? 32 : (GA * NMMA <= 64) ? 64 : (GA * NMMA <= 128) ? 128 : (GA * NMMA <= 256) ? 256 : 512;
   extern __shared__ __align__(1024) uint8_t smem_raw[];

@@ -1,4 +1,4 @@
-"""Write profiles/r1_ncu_traffic.json from the raw-page CSV of an `ncu --set full` capture covering every tensor-core launch of
+"""Write profiles/r2_ncu_traffic.json from the raw-page CSV of an `ncu --set full` capture covering every tensor-core launch of
 ONE 16-bit forward in launch order (tools/ncu_forward.py, `-k regex:"umma|csar_tail" --launch-skip 25 --launch-count 25`).
 Usage: python tools/ncu_traffic.py raw.csv B H W"""
 import csv, json, os, sys
@@ -23,5 +23,5 @@ out = {"batch": B, "pixels_per_crop": H * W, "source": os.path.basename(raw),
        "umma_dram_bytes_per_forward": sum(l["dram"] for l in launches),
        "tail_dram_bytes_per_forward": sum(l["dram"] for l, n in zip(launches, names) if n.endswith(".tail")),
        "launches": [dict(l, layer=n) for l, n in zip(launches, names)]}
-json.dump(out, open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r1_ncu_traffic.json"), "w"), indent=1)
+json.dump(out, open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r2_ncu_traffic.json"), "w"), indent=1)
 print(json.dumps({k: v for k, v in out.items() if k != "launches"}))
