@@ -414,7 +414,10 @@ __device__ __forceinline__ void store_chunk8(T* __restrict__ out, int pitch, int
 //       | kConv5x5Fold (Cout = 16: the five dx taps folded into N = 80, 5 MMAs per K-slice instead of 25; the epilogue forms
 //         out[q] = sum_dx D[q + dx - 2, dx] with shuffles by 1 and 2 rows; tiles overlap by 4 rows (stride 124))
 enum { kConv1x1 = 0, kConv3x3Taps = 1, kConv3x3Fold = 2, kConv7x7 = 3, kConv5x5Taps = 4, kConv3x3FoldLff = 5, kConv5x5Fold = 6 };
-constexpr int kLffN = 32, kLffCols = 48 + kLffN;   // fused layer: TMEM columns per accumulator = 3*16 folded + 32 lff
+// fused layer: TMEM columns per accumulator = 3*16 folded + 32 lff (hi weights) + 32 lff (lo weights); the dy = 1 weight block carries all 112
+// columns, the dy = 0 / dy = 2 blocks only the 48 folded ones (an MMA has a floor of ~46 clk for N <= 64 whatever it does --
+// profiles/r2_umma_variants_microbench.txt -- so the lo terms ride in the dy = 1 MMA (N = 112: 56 clk) instead of a separate N = 32 MMA)
+constexpr int kLffN = 32, kLffCols = 48 + 2 * kLffN, kLffWCols = kLffCols + 48 + 48;
 
 struct UmmaTmaps { CUtensorMap m[kUmmaMaxKChunks]; };   // one tiled map per K-chunk (its tensor, its box width)
 
@@ -431,13 +434,13 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
   constexpr int kThreadsAll = umma_threads(CS);
   constexpr int kEpiWarps = 4 * kEpiGroups * CS;               // warps [0, kEpiWarps): epilogue; then G MMA warps; then the TMA producer
   constexpr int kMmaWarp0 = kEpiWarps, kLoaderWarp = kEpiWarps + kEpiGroups;
-  static_assert(CS == 1 || (CS == 2 && NOUT == 16 && (MODE == kConv3x3FoldLff || (MODE == kConv3x3Fold && EPI == kEpiRelu))),
+  static_assert(CS == 1 || (CS == 2 && NOUT == 16 && MODE == kConv3x3Fold && EPI == kEpiRelu),
                 "column split: the folded Cout = 16 layers");
   constexpr bool LFF = (MODE == kConv3x3FoldLff);
   constexpr bool FOLD = (MODE == kConv3x3Fold) || LFF;
   constexpr bool FOLD5 = (MODE == kConv5x5Fold);
   constexpr int HF = FOLD5 ? 2 : (FOLD ? 1 : 0);               // rows of a tile lost on each side to the dx fold
-  static_assert(!LFF || NOUT == 16, "fused layer: growth rate 16");
+  static_assert(!LFF || (NOUT == 16 && !SP && CS == 1), "fused layer: growth rate 16, plain 16-bit tensors");
   constexpr bool K3 = (MODE != kConv1x1);
   static_assert(!SP || (CS == 1 && NS == 1 && !IsBf16<T>::value), "split tensors: fp16 pairs, plain epilogue layout");
   static_assert(NS == 1 || (NS == 2 && MODE == kConv3x3Taps && NOUT == 32 && CS == 1), "N-split weights: per-tap 3x3, Cout = 32");
@@ -465,8 +468,8 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int CG = p.n_ks * 2;                                  // 8-channel groups of the whole K extent
-  const uint32_t w_main_bytes = (uint32_t)NTAP * CG * NMMA * 16;
-  const uint32_t w_bytes = w_main_bytes + (LFF ? 4u * kLffN * 16u : 0u);   // fused: + lff's g3 slice, hi and lo [2 + 2][32][8]
+  const uint32_t w_main_bytes = LFF ? (uint32_t)CG * kLffWCols * 16 : (uint32_t)NTAP * CG * NMMA * 16;
+  const uint32_t w_bytes = w_main_bytes + (LFF ? 4u * kLffN * 16u : 0u);   // fused: + lff's g3 slice [2][32 hi | 32 lo][8]
   const uint32_t buf_bytes = p.buf_bytes;                      // multiple of 1024
   uint8_t* a_smem = smem;                                      // item buffers first (1024-aligned)
   uint8_t* w_smem = smem + (size_t)p.n_bufs * buf_bytes;
@@ -492,12 +495,11 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
   // FADDs waiting on L2 latency (ncu: long-scoreboard stalls on every bias add of the N = 128 shallowF1 kernel)
   float* bias_s = reinterpret_cast<float*>(a2_all);            // same place as the fused layer's operands (that layer has N = 16)
   // fused layer: the additions of its two epilogue passes run on the tensor core (its pipe has slack, the epilogue warps do not): a
-  // "ones" operand times {hi(bias), lo(bias)} starts the accumulator at the biases (b3 in the dx = 1 block, lff's in columns 48..79),
-  // and x (chunk 0 of the staged block, centre tap) times a 32x32 identity adds the residual exactly.
+  // "ones" operand times {hi(bias), lo(bias)} starts the accumulator at the biases (b3 in the dx = 1 block, lff's in columns 48..79);
+  // the residual x is part of lff's weights (1 + w on the diagonal of the block-input channels, hi + lo: exact to 22 bits).
   constexpr uint32_t kA2Bytes = SP ? 8192u : 4096u;            // g3 operand per group: [2 planes][128 rows][8] (split: hi, then lo)
   uint8_t* ones_s = a2_all + (size_t)G * kA2Bytes;             // [2 planes][128 rows][8]: k = 0, 1 are 1.0
-  uint8_t* lffb_s = ones_s + 2 * 128 * 16;                     // [2][80][8]
-  uint8_t* lffid_s = lffb_s + 2 * kLffCols * 16;               // [4][32][8]
+  uint8_t* lffb_s = ones_s + 2 * 128 * 16;                     // [2][112][8]
 
   // ---- one-time setup ------------------------------------------------------------------------------
   {
@@ -515,15 +517,13 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
     for (uint32_t i = threadIdx.x; i < 2 * kLffCols * 8; i += kThreadsAll) {
       const uint32_t k = i & 7, col = (i >> 3) % kLffCols, plane = (i >> 3) / kLffCols;
       float v = 0.f;
-      if (plane == 0 && k < 2 && ((col >= 16 && col < 32) || col >= 48)) {
+      if (plane == 0 && k < 2 && ((col >= 16 && col < 32) || (col >= 48 && col < 48 + kLffN))) {
         const float bv = __ldg(p.bias + (col < 32 ? col - 16 : col - 32));   // bias = [b3 (16) | lff bias (32)]
         const float hi = to_f32<T>(from_f32<T>(bv));
         v = k == 0 ? hi : bv - hi;
       }
       bb[i] = from_f32<T>(v);
     }
-    T* idm = reinterpret_cast<T*>(lffid_s);
-    for (uint32_t i = threadIdx.x; i < 4 * 32 * 8; i += kThreadsAll) idm[i] = from_f32<T>(((i >> 8) * 8 + (i & 7)) == ((i >> 3) & 31) ? 1.f : 0.f);
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < R; ++s) {
@@ -614,11 +614,14 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
     const int mg = warp - kMmaWarp0;
     const bool leader = ptx::elect_one();
     constexpr uint32_t idesc = umma_idesc_f16(IsBf16<T>::value, NMMA);
-    constexpr uint32_t idesc48 = umma_idesc_f16(IsBf16<T>::value, 48), idesc32 = umma_idesc_f16(IsBf16<T>::value, kLffN);
-    const uint32_t w2_lo = umma_desc_lo(ptx::smem_u32(w_smem) + w_main_bytes, (uint32_t)kLffN * 16);
+    constexpr uint32_t idesc48 = umma_idesc_f16(IsBf16<T>::value, 48), idesc64 = umma_idesc_f16(IsBf16<T>::value, 2 * kLffN);
+    const uint32_t w2_lo = umma_desc_lo(ptx::smem_u32(w_smem) + w_main_bytes, 2u * kLffN * 16);
     const uint32_t a2_lo = umma_desc_lo(ptx::smem_u32(a2_all) + (uint32_t)mg * kA2Bytes, 2048u);
-    const uint32_t ones_lo = umma_desc_lo(ptx::smem_u32(ones_s), 2048u), lffb_lo = umma_desc_lo(ptx::smem_u32(lffb_s), (uint32_t)kLffCols * 16),
-                   lffid_lo = umma_desc_lo(ptx::smem_u32(lffid_s), 32u * 16);
+    const uint32_t ones_lo = umma_desc_lo(ptx::smem_u32(ones_s), 2048u), lffb_lo = umma_desc_lo(ptx::smem_u32(lffb_s), (uint32_t)kLffCols * 16);
+    // fused layer: weight blocks [dy = 1: CG x 112 | dy = 0: CG x 48 | dy = 2: CG x 48] rows of 16 bytes
+    const uint32_t wl1_lo = umma_desc_lo(ptx::smem_u32(w_smem), (uint32_t)kLffCols * 16),
+                   wl0_lo = umma_desc_lo(ptx::smem_u32(w_smem) + (uint32_t)CG * kLffCols * 16, 48u * 16),
+                   wl2_lo = umma_desc_lo(ptx::smem_u32(w_smem) + (uint32_t)CG * (kLffCols + 48) * 16, 48u * 16);
     uint32_t a2_par = 0;
     const uint32_t w_lo = umma_desc_lo(ptx::smem_u32(w_smem), (uint32_t)NMMA * 16);
     const uint32_t cgn = (uint32_t)(CG * NMMA);               // weights: 16-byte units between taps
@@ -659,21 +662,15 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
               const uint4 e = steps[ks];
               const uint32_t a0 = (buf16 + e.x + slot * e.y) | (1u << 16);
               if constexpr (LFF) {
-                // + x: channels 16 r .. 16 r + 15 of the block input (centre tap) times the identity -> lff columns (split: hi and lo chunks)
-                if (ks < (SP ? 4 : 2))
-                  ptx::tc_mma_f16_lohi(d + 48, a0 + e.w, e.z, lffid_lo + (uint32_t)((SP ? (ks >> 1) : ks) * 2 * 32), kUmmaDescHi, idesc32, 1u);
-                // lo terms of lff's weights over this K-slice (stored in the lff columns of the dy = 0 weight block), centre-row operand;
-                // split mode: the lo-weight K-slices at the end of the K extent carry them instead
-                if constexpr (!SP) ptx::tc_mma_f16_lohi(d + 48, a0 + e.w, e.z, b_lo + 48u, kUmmaDescHi, idesc32, 1u);
-              }
+                // dy = 1: 48 folded columns + lff over this K-slice (hi and lo weights) in one N = 112 MMA; dy = 0, 2: the folded columns
+                const uint32_t k2 = 2u * (uint32_t)ks;
+                ptx::tc_mma_f16_lohi(d, a0 + e.w, e.z, wl1_lo + k2 * kLffCols, kUmmaDescHi, idesc, 1u);
+                ptx::tc_mma_f16_lohi(d, a0, e.z, wl0_lo + k2 * 48u, kUmmaDescHi, idesc48, 1u);
+                ptx::tc_mma_f16_lohi(d, a0 + 2u * e.w, e.z, wl2_lo + k2 * 48u, kUmmaDescHi, idesc48, 1u);
+              } else {
 #pragma unroll
-              for (int t = 0; t < NTAP; ++t) {
-                // tap -> start shift in 16-byte units: folded: dy rows (dx lives in N); per-tap: dy rows + dx pixels
-                if constexpr (LFF) {
-                  // dy = 1 goes first: its 80-column MMA (48 folded + 32 lff) initialises the whole accumulator
-                  const uint32_t dyv = t == 0 ? 1u : (t == 1 ? 0u : 2u);
-                  ptx::tc_mma_f16_lohi(d, a0 + dyv * e.w, e.z, b_lo + dyv * cgn, kUmmaDescHi, t == 0 ? idesc : idesc48, 1u);
-                } else {
+                for (int t = 0; t < NTAP; ++t) {
+                  // tap -> start shift in 16-byte units: folded: dy rows (dx lives in N); per-tap: dy rows + dx pixels
                   const uint32_t shift = (FOLD || FOLD5) ? (uint32_t)t * e.w : (uint32_t)(t / KSZ) * e.w + (uint32_t)(t % KSZ) * e.y;
                   ptx::tc_mma_f16_lohi(d, a0 + shift, e.z, b_lo + (uint32_t)t * cgn, kUmmaDescHi, idesc, (uint32_t)(ks | t));
                 }
@@ -692,10 +689,8 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
           ptx::tc_fence_after();
           if (leader) {
             if (!no_mma) {
-              ptx::tc_mma_f16_lohi(tmem_base + acc * NMMA + 48, a2_lo, kUmmaDescHi, w2_lo, kUmmaDescHi, idesc32, 1u);
-              ptx::tc_mma_f16_lohi(tmem_base + acc * NMMA + 48, a2_lo, kUmmaDescHi, w2_lo + 2u * kLffN, kUmmaDescHi, idesc32, 1u);   // lo terms
-              if constexpr (SP)   // g3's lo operand times the hi weights
-                ptx::tc_mma_f16_lohi(tmem_base + acc * NMMA + 48, a2_lo + (4096u >> 4), kUmmaDescHi, w2_lo, kUmmaDescHi, idesc32, 1u);
+              // lff's g3 slice, hi | lo weights along N: one N = 64 MMA into columns 48..111
+              ptx::tc_mma_f16_lohi(tmem_base + acc * NMMA + 48, a2_lo, kUmmaDescHi, w2_lo, kUmmaDescHi, idesc64, 1u);
             }
             ptx::tc_commit(tfull2_bar(acc));
           }
@@ -1052,13 +1047,18 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
             // ---- stage 2: columns 48..79 = x + lff(cat[x, g0..g3]) + bias -> block output
             ptx::mbar_wait(tfull2_bar(grp), tile_par);
             ptx::tc_fence_after();
-            float o[kLffN];
+            float o[kLffN], ol[kLffN];                          // products with the hi and with the lo weights
 #pragma unroll
-            for (int hh = 0; hh < kLffN / CH; ++hh) ptx::tc_ld16_nowait(taddr + 48 + hh * CH, o + hh * CH);
+            for (int hh = 0; hh < kLffN / CH; ++hh) {
+              ptx::tc_ld16_nowait(taddr + 48 + hh * CH, o + hh * CH);
+              ptx::tc_ld16_nowait(taddr + 48 + kLffN + hh * CH, ol + hh * CH);
+            }
             ptx::tc_wait_ld();
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(tempty_bar(accI));
+#pragma unroll
+            for (int c = 0; c < kLffN; ++c) o[c] += ol[c];
 #pragma unroll
             for (int hh = 0; hh < kLffN / CH; ++hh) {
               float oc[CH];
@@ -1307,7 +1307,7 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
     if (tr_on) { cudaMemsetAsync(trace, 0, 512 * 8 * sizeof(long long)); p.trace = trace; umma_trace_buffer() = trace; }
 #endif
   }
-  const size_t w_bytes = ((size_t)ntap * w.cin * NMMA * 2 + (lff ? 4 * kLffN * 16 : 0) + 127) & ~(size_t)127;
+  const size_t w_bytes = ((lff ? (size_t)(w.cin / 8) * kLffWCols * 16 + 4 * kLffN * 16 : (size_t)ntap * w.cin * NMMA * 2) + 127) & ~(size_t)127;
   const size_t a2_bytes = lff ? (size_t)kEpiGroups * (w.split ? 8192 : 4096) + 2 * 128 * 16 + 2 * kLffCols * 16 + 4 * 32 * 16   // g3 operands, ones, biases, identity
                               : (N > 32 ? (size_t)N * 4 : 0);                                                   // wide layers: bias vector
   const size_t fixed = w_bytes + (2 * kUmmaMaxBufs + 6 * kEpiGroups + 2) * 8 + xch_bytes + a2_bytes + 640 /*steps, slot_base*/ + 1024 /*alignment slack*/ + 256;
@@ -1515,8 +1515,7 @@ inline const char* umma_plan_launch(const UmmaPlan& plan, const UmmaWeights& w, 
   if (w.ks == 3) {
     if (w.fused_lff) {
       if (!(mode == kEpiPlain && plan.p.res)) return "fused dense layer + lff needs the residual";
-      return umma_column_split() ? umma_launch_inst<T, 16, kConv3x3FoldLff, kEpiResidual, T, 2>(plan, st)
-                                 : umma_launch_inst<T, 16, kConv3x3FoldLff, kEpiResidual>(plan, st);
+      return umma_launch_inst<T, 16, kConv3x3FoldLff, kEpiResidual>(plan, st);
     }
     if (w.cout == 16) return umma_launch_epi<T, 16, kConv3x3Fold>(plan, st);
     if (w.cout == 32) return umma_launch_epi<T, 32, kConv3x3Taps>(plan, st, w.nsplit);

@@ -18,7 +18,7 @@ struct UmmaWeights {
   int ks = 0, cin = 0, cout = 0;
   uint16_t* w = nullptr;   // 16-bit (bf16 or fp16): 1x1 [cin/8][cout][8]; 3x3 [dy][cin/8][dx*cout + co][8] (dx folded into N)
   float* bias = nullptr;   // [cout] (zeros if the conv has no bias)
-  bool fused_lff = false;  // kConv3x3FoldLff: w = [dy][cin/8][48 folded + 32 lff (dy = 1: hi, dy = 0: lo)][8] then lff's g3 slice [2 hi, 2 lo][32][8]; bias = [16] + [32]
+  bool fused_lff = false;  // kConv3x3FoldLff: w = [cin/8][48 folded + 32 lff hi + 32 lff lo][8] (dy = 1), [cin/8][48][8] (dy = 0), [cin/8][48][8] (dy = 2), then lff's g3 slice [2][32 hi | 32 lo][8]; bias = [16] + [32]
   bool split = false;      // split (double-fp16) activations: K rows = per real 16-channel chunk [W_hi for the hi chunk, W_hi for the lo chunk], then the
                            // lo terms of the weights once per real chunk (re-reading the hi tiles); n_real = K-slices staged in shared memory
   int n_real = 0;
@@ -250,79 +250,41 @@ bool umma_pack_weights_split(UmmaWeights& u, const float* pw_in, const float* bi
 
 // Last dense layer of an RDB (3x3, cin -> 16, ReLU) fused with the block's local feature fusion (1x1 over cin + 16 channels -> 32,
 // alpha already folded in, lpsr.py:52-61).  w3: fp32 [9][cin][16]; wl: fp32 [cin + 16][32].
-// Split mode of the fused layer: K rows as in split_weight_rows (hi weights for hi and lo chunks, then the lo weights); lff's columns sit in
-// the dy = 1 block for every K row; the g3 slice keeps its [2 hi, 2 lo][32][8] layout (the kernel multiplies g3_hi * hi, g3_hi * lo, g3_lo * hi).
 template <typename PutU16, typename PutF32>
-bool umma_pack_fused_lff_split(UmmaWeights& u, const float* w3, const float* b3, const float* wl, const float* bl, int cin, PutU16 put16, PutF32 put32) {
-  const int K = 3 * cin, cg = K / 8, nf = 80;
-  std::vector<uint16_t> v((size_t)3 * cg * nf * 8 + 4 * 32 * 8, 0);
-  auto cvt = [&](float f) { return f32_to_f16_bits(f); };
-  auto hi_of = [&](float f) { return bits16_to_f32(f32_to_f16_bits(f), true); };
-  for (int k = 0; k < K; ++k) {
-    int ci;
-    bool lo;
-    if (k < 2 * cin) { ci = (k / 32) * 16 + k % 16; lo = false; } else { ci = k - 2 * cin; lo = true; }
-    const int g = k / 8, j = k % 8;
-    for (int dy = 0; dy < 3; ++dy) {
+bool umma_pack_fused_lff(UmmaWeights& u, const float* w3, const float* b3, const float* wl, const float* bl, int cin, bool fp16, PutU16 put16,
+                         PutF32 put32) {
+  const int cg = cin / 8;
+  constexpr int kW1 = 112, kW0 = 48;   // rows of the dy = 1 block (48 folded + 32 lff hi + 32 lff lo) and of the dy = 0 / dy = 2 blocks
+  // lff's weights are carried as hi + lo (its rounding error is one of the largest single contributions to the output error with the shipped
+  // checkpoint, tools/parity_report.py): hi and lo are two 32-column blocks of the dy = 1 MMA (N = 112) and the epilogue adds the two products.
+  // The block's residual `x + alpha * lff(...)` (lpsr.py:61) is part of these weights: 1 is added on the diagonal of the block-input channels
+  // (ci < 32), and hi + lo carries 1 + w to 22 bits, so x passes through exactly and no identity MMA / epilogue add is needed.
+  std::vector<uint16_t> v((size_t)cg * (kW1 + 2 * kW0) * 8 + 2 * 64 * 8, 0);
+  auto cvt = [&](float f) { return fp16 ? f32_to_f16_bits(f) : f32_to_bf16_bits(f); };
+  auto lo16 = [&](float f) { return cvt(f - bits16_to_f32(cvt(f), fp16)); };
+  const size_t base0 = (size_t)cg * kW1 * 8, base2 = base0 + (size_t)cg * kW0 * 8;
+  for (int g = 0; g < cg; ++g)
+    for (int j = 0; j < 8; ++j) {
+      const int ci = g * 8 + j;
       for (int dx = 0; dx < 3; ++dx)
         for (int n = 0; n < 16; ++n) {
-          const float w = w3[((size_t)(dy * 3 + dx) * cin + ci) * 16 + n];
-          v[(((size_t)dy * cg + g) * nf + dx * 16 + n) * 8 + j] = cvt(lo ? w - hi_of(w) : w);
+          v[((size_t)g * kW1 + dx * 16 + n) * 8 + j] = cvt(w3[((size_t)(1 * 3 + dx) * cin + ci) * 16 + n]);
+          v[base0 + ((size_t)g * kW0 + dx * 16 + n) * 8 + j] = cvt(w3[((size_t)(0 * 3 + dx) * cin + ci) * 16 + n]);
+          v[base2 + ((size_t)g * kW0 + dx * 16 + n) * 8 + j] = cvt(w3[((size_t)(2 * 3 + dx) * cin + ci) * 16 + n]);
         }
-      if (dy == 1)
-        for (int n = 0; n < 32; ++n) {
-          const float w = wl[(size_t)ci * 32 + n];
-          v[(((size_t)dy * cg + g) * nf + 48 + n) * 8 + j] = cvt(lo ? w - hi_of(w) : w);
-        }
+      for (int n = 0; n < 32; ++n) {
+        const float w = wl[(size_t)ci * 32 + n] + ((ci < 32 && ci == n) ? 1.f : 0.f);
+        v[((size_t)g * kW1 + 48 + n) * 8 + j] = cvt(w);
+        v[((size_t)g * kW1 + 80 + n) * 8 + j] = lo16(w);
+      }
     }
-  }
-  const size_t base2 = (size_t)3 * cg * nf * 8;
+  const size_t base3 = base2 + (size_t)cg * kW0 * 8;           // lff's g3 slice: [2 K core matrices][32 hi | 32 lo][8]
   for (int g = 0; g < 2; ++g)
     for (int n = 0; n < 32; ++n)
       for (int j = 0; j < 8; ++j) {
         const float w = wl[(size_t)(cin + g * 8 + j) * 32 + n];
-        v[base2 + ((size_t)g * 32 + n) * 8 + j] = cvt(w);
-        v[base2 + 2 * 32 * 8 + ((size_t)g * 32 + n) * 8 + j] = cvt(w - hi_of(w));
-      }
-  std::vector<float> b(48, 0.f);
-  for (int n = 0; n < 16; ++n) b[n] = b3[n];
-  for (int n = 0; n < 32; ++n) b[16 + n] = bl[n];
-  u.w = put16(v);
-  u.bias = put32(b);
-  u.ks = 3; u.cin = K; u.cout = 16;
-  u.fused_lff = true;
-  u.wsplit = true; u.split = true; u.n_real = 2 * cin / 16;
-  u.packed = (u.w != nullptr && u.bias != nullptr);
-  return u.packed;
-}
-
-template <typename PutU16, typename PutF32>
-bool umma_pack_fused_lff(UmmaWeights& u, const float* w3, const float* b3, const float* wl, const float* bl, int cin, bool fp16, PutU16 put16,
-                         PutF32 put32) {
-  const int cg = cin / 8, nf = 80;
-  // lff's weights are carried as hi + lo (its rounding error is one of the largest single contributions to the output error with the shipped
-  // checkpoint, tools/parity_report.py): the lo terms over the layer's own input channels sit in the otherwise unused lff columns of the
-  // dy = 0 block (no extra shared memory), the lo terms of the g3 slice follow the hi ones.
-  std::vector<uint16_t> v((size_t)3 * cg * nf * 8 + 4 * 32 * 8, 0);
-  auto cvt = [&](float f) { return fp16 ? f32_to_f16_bits(f) : f32_to_bf16_bits(f); };
-  auto lo16 = [&](float f) { return cvt(f - bits16_to_f32(cvt(f), fp16)); };
-  for (int dy = 0; dy < 3; ++dy)
-    for (int g = 0; g < cg; ++g)
-      for (int j = 0; j < 8; ++j) {
-        const int ci = g * 8 + j;
-        for (int dx = 0; dx < 3; ++dx)
-          for (int n = 0; n < 16; ++n) v[(((size_t)dy * cg + g) * nf + dx * 16 + n) * 8 + j] = cvt(w3[((size_t)(dy * 3 + dx) * cin + ci) * 16 + n]);
-        if (dy == 1)
-          for (int n = 0; n < 32; ++n) v[(((size_t)dy * cg + g) * nf + 48 + n) * 8 + j] = cvt(wl[(size_t)ci * 32 + n]);
-        if (dy == 0)
-          for (int n = 0; n < 32; ++n) v[(((size_t)dy * cg + g) * nf + 48 + n) * 8 + j] = lo16(wl[(size_t)ci * 32 + n]);
-      }
-  const size_t base2 = (size_t)3 * cg * nf * 8;
-  for (int g = 0; g < 2; ++g)
-    for (int n = 0; n < 32; ++n)
-      for (int j = 0; j < 8; ++j) {
-        v[base2 + ((size_t)g * 32 + n) * 8 + j] = cvt(wl[(size_t)(cin + g * 8 + j) * 32 + n]);
-        v[base2 + 2 * 32 * 8 + ((size_t)g * 32 + n) * 8 + j] = lo16(wl[(size_t)(cin + g * 8 + j) * 32 + n]);
+        v[base3 + ((size_t)g * 64 + n) * 8 + j] = cvt(w);
+        v[base3 + ((size_t)g * 64 + 32 + n) * 8 + j] = lo16(w);
       }
   std::vector<float> b(48, 0.f);
   for (int n = 0; n < 16; ++n) b[n] = b3[n];
