@@ -402,6 +402,15 @@ int pack_all(lpsr_handle* h) {
     ok &= umma_pack_weights_wsplit(h->csar_co.u, pw.data(), W(h, "rdn.csar.conv_out.bias").data(), 1, 2 * F, F, h->cfg.precision == LPSR_PREC_FP16,
                                    [&](const std::vector<uint16_t>& v) { return arena_put(h, v); }, [&](const std::vector<float>& v) { return arena_put(h, v); });
   }
+  h->csar_co_us_scaled = UmmaWeights{};
+  if (h->fp32_split) {   // split tensor-core tail: same channel-branch scaling as the 16-bit tail (exact: a power of two)
+    const std::vector<float>& w = W(h, "rdn.csar.conv_out.weight");   // [F][2F]
+    std::vector<float> pw((size_t)2 * F * F);
+    for (int co = 0; co < F; ++co)
+      for (int ci = 0; ci < 2 * F; ++ci) pw[(size_t)ci * F + co] = (ci < F ? kCsarChanScale : 1.f) * w[(size_t)co * 2 * F + ci];
+    ok &= umma_pack_weights_split(h->csar_co_us_scaled, pw.data(), W(h, "rdn.csar.conv_out.bias").data(), 1, 2 * F, F,
+                                  [&](const std::vector<uint16_t>& v) { return arena_put(h, v); }, [&](const std::vector<float>& v) { return arena_put(h, v); });
+  }
   h->ca_w1 = arena_put(h, W(h, "rdn.csar.ca.block.2.weight"));
   h->ca_b1 = arena_put(h, W(h, "rdn.csar.ca.block.2.bias"));
   h->ca_w2 = arena_put(h, W(h, "rdn.csar.ca.block.4.weight"));

@@ -11,6 +11,7 @@
 //                                  split tensors directly; its three per-pixel 1x1s are 2 % of the FLOPs)
 // The fused "last dense layer + lff" kernel is not used here: with 3x the K rows its weights alone would take 115 KB of shared memory.
 #pragma once
+#include "csar_tail_split_umma.cuh"
 #include "forward_impl.cuh"
 
 namespace lpsr {
@@ -105,12 +106,33 @@ inline int forward_split(lpsr_handle* h, const float* x, float* y, int B, int H,
     conv("csar.conv_in.2 + pool", h->csar_c2.us, conv_params(h->csar_c2, {S32(t)}, 16, xin, 64, 0, B, Hp, Wp, false), &pg);
     c.tag = tag_tail;
     float* sc = reinterpret_cast<float*>(ws + L.sc);
+    // the tail on tensor cores (csar_tail_split_umma.cuh) carries the channel branch as x_in^2 * s_c / kCsarChanScale (fp16 hi parts must not
+    // overflow); conv_out's channel-branch weight rows are multiplied by the same power of two at pack time.  LPSR_SPLIT_TAIL_FFMA=1: CUDA cores.
+    static const bool tail_tc = !getenv("LPSR_SPLIT_TAIL_FFMA");
+    const bool use_tc = tail_tc && h->csar_sa1.us.packed && h->csar_sa2.us.packed && h->csar_co_us_scaled.packed;
     c.begin("channel_gate");   // s_c once per crop from the pooled partial sums (lpsr.py:120-135)
     if (!c.dry && c.rc == LPSR_OK) {
       channel_gate_kernel<<<dim3(B), dim3(256), 0, st>>>((const float*)pool, pool_slots, L.P, (const float*)h->ca_w1, (const float*)h->ca_b1,
-                                                        (const float*)h->ca_w2, (const float*)h->ca_b2, sc, 1.f);
+                                                        (const float*)h->ca_w2, (const float*)h->ca_b2, sc, use_tc ? 1.f / kCsarChanScale : 1.f);
       cudaError_t e = cudaGetLastError();
       if (e != cudaSuccess) c.rc = fail(h, LPSR_ERR_CUDA, "channel_gate launch: %s", cudaGetErrorString(e));
+    }
+    if (use_tc) {
+      c.begin("csar_tail_split_umma");
+      if (!c.dry && c.rc == LPSR_OK) {
+        TailSplitParams p{};
+        p.x_in = xin;
+        p.res = xb; p.res_pitch = 64; p.res_off = 0;
+        p.out = out; p.out_pitch = 64; p.out_off = 0;
+        p.w3 = h->csar_sa1.us.w; p.b3 = h->csar_sa1.us.bias; p.s3 = h->csar_sa1.us.acc_scale;
+        p.w4 = h->csar_sa2.us.w; p.b4 = h->csar_sa2.us.bias; p.s4 = h->csar_sa2.us.acc_scale;
+        p.wo = h->csar_co_us_scaled.w; p.bo = h->csar_co_us_scaled.bias; p.so = h->csar_co_us_scaled.acc_scale;
+        p.s_c = sc;
+        p.total_px = (long long)B * L.P;
+        p.px_per_crop = L.P;
+        if (const char* msg = csar_tail_split_umma_launch(p, h->num_sms, st)) c.rc = fail(h, LPSR_ERR_CUDA, "csar_tail (split, tensor cores): %s", msg);
+      }
+      return;
     }
     c.begin("csar_tail_split");
     if (!c.dry && c.rc == LPSR_OK) {
