@@ -500,6 +500,22 @@ static __global__ void f32_to_split_inplace_kernel(float* __restrict__ buf, long
     store_vec<__half, 16>(o + 16, lo);
   }
 }
+// fp32 NHWC [n_px][3] (the AutoEncoder output) -> 16-byte pixels [hi(c0 c1 c2) | lo(c0 c1 c2) | 0 0] of fp16: the operand of the fp32-accuracy
+// mode's tensor-core shallowF1 (7x7 as pixel-pair K-steps, umma_conv.cuh kConv7x7)
+static __global__ void ae_to_pix8_split_kernel(const float* __restrict__ ae, __half* __restrict__ out, long long n_px) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_px; i += (long long)gridDim.x * blockDim.x) {
+    __half e[8];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = ae[i * 3 + c];
+      const __half hi = from_f32<__half>(v);
+      e[c] = hi;
+      e[3 + c] = from_f32<__half>(v - __half2float(hi));
+    }
+    e[6] = e[7] = from_f32<__half>(0.f);
+    *reinterpret_cast<uint4*>(out + i * 8) = *reinterpret_cast<const uint4*>(e);
+  }
+}
 // split NHWC (2C 16-bit channels per pixel) -> fp32 NCHW [B][C][H][W] (debug taps)
 static __global__ void split_nhwc_to_nchw_kernel(const __half* __restrict__ src, float* __restrict__ dst, int B, int C, int H, int W) {
   const long long total = (long long)B * C * H * W;

@@ -337,6 +337,37 @@ int pack_all(lpsr_handle* h) {
     ok &= umma_pack_weights(h->ae_out_u, p16.data(), nullptr, 3, 16, 16, h->cfg.precision == LPSR_PREC_FP16,
                             [&](const std::vector<uint16_t>& v) { return arena_put(h, v); }, [&](const std::vector<float>& v) { return arena_put(h, v); });
   }
+  h->sfe1_us = UmmaWeights{};
+  if (h->fp32_split && C == 3 && F == 32) {
+    // fp32-accuracy mode: the same pixel-pair K-steps, but a pixel's 8 slots are [hi(c0 c1 c2) | lo(c0 c1 c2) | 0 0] (ae_to_pix8_split_kernel), so
+    // one MMA per K-step covers A_hi W_hi + A_lo W_hi (rows 0..5 carry hi(W) twice) and a second pass over the same pixels with lo(W) in
+    // rows 0..2 adds A_hi W_lo: 56 K-steps.  Weights times a power of two so that the lo terms stay normal fp16 numbers (acc_scale undoes it).
+    const std::vector<float>& w = W(h, "rdn.shallowF1.weight");   // [F][C][7][7]
+    const float sc = split_weight_scale(w.data(), w.size());
+    std::vector<float> pw((size_t)896 * F, 0.f);
+    for (int dy = 0; dy < 7; ++dy)
+      for (int pr = 0; pr < 4; ++pr)
+        for (int half = 0; half < 2; ++half) {
+          const int dx = 2 * pr + half;
+          if (dx >= 7) continue;
+          for (int ci = 0; ci < C; ++ci)
+            for (int co = 0; co < F; ++co) {
+              const float wv = sc * w[(((size_t)co * C + ci) * 7 + dy) * 7 + dx];
+              const float hi = bits16_to_f32(f32_to_bits16(wv, true), true);
+              const size_t row = (size_t)((dy * 4 + pr) * 16 + half * 8);
+              pw[(row + ci) * F + co] = hi;              // x hi(activation)
+              pw[(row + 3 + ci) * F + co] = hi;          // x lo(activation)
+              pw[(448 + row + ci) * F + co] = wv - hi;   // lo(W) x hi(activation)
+            }
+        }
+    ok &= umma_pack_weights(h->sfe1_us, pw.data(), W(h, "rdn.shallowF1.bias").data(), 1, 896, F, true,
+                            [&](const std::vector<uint16_t>& v) { return arena_put(h, v); }, [&](const std::vector<float>& v) { return arena_put(h, v); });
+    h->sfe1_us.ks = 7;
+    h->sfe1_us.split = true;      // split output tensor, acc_scale in the epilogue
+    h->sfe1_us.n_real = 28;
+    h->sfe1_us.wlo_step = 1;
+    h->sfe1_us.acc_scale = 1.f / sc;
+  }
   h->ae_tc = false;
   if (half_mode(h) && umma_enabled() && C == 3 && h->sfe1_u.packed && !getenv("LPSR_AE_CUDA_CORES")) {
     ok &= pack_ae_tensor_core(h);

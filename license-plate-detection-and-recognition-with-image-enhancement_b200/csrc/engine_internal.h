@@ -59,6 +59,7 @@ struct lpsr_handle {
   lpsr::ConvW ae_in, ae_out, sfe1, sfe2, rdb[2][4], lff[2], csar_c1, csar_c2, csar_sa1, csar_sa2, csar_co, gff0, gff1, fin;
   lpsr::UmmaWeights fin_u;   // final conv with Cout padded 1 -> 16 for the tensor-core path
   lpsr::UmmaWeights fin_us;  // the same for split operands
+  lpsr::UmmaWeights sfe1_us;   // shallowF1 7x7 for the fp32-accuracy mode: 8-slot pixels [hi(3) | lo(3) | 0 0], hi + lo weights (56 K-steps)
   lpsr::UmmaWeights csar_co_us_scaled;   // conv_out for the split tensor-core tail: channel-branch rows x kCsarChanScale
   bool fp32_split = false;   // LPSR_PREC_FP32 runs its dense trunk layers on tensor cores with split operands (LPSR_FP32_FFMA=1: CUDA cores)
   lpsr::UmmaWeights sfe1_u;  // shallowF1 7x7 as 28 pixel-pair K-steps over an 8-channel padded input (tensor-core path)

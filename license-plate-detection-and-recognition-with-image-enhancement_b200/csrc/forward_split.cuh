@@ -64,13 +64,34 @@ inline int forward_split(lpsr_handle* h, const float* x, float* y, int B, int H,
   c.tag = "ae.conv_out";
   launch_direct<float, 3, 12, 3, false, false>(c, conv_params(h->ae_out, s, 12, 0, 12, ae, 3, 0, B, Hp, Wp, false));
   c.tag = "rdn.shallowF1";
-  launch_direct<float, 7, 3, 32, false, false>(c, conv_params(h->sfe1, ae, 3, 0, 3, sfe1_f, 32, 0, B, Hp, Wp, false));
-  c.begin("f32_to_split");
-  if (!c.dry && c.rc == LPSR_OK) {
-    const long long n_chunks = (long long)B * L.P * 2;
-    f32_to_split_inplace_kernel<<<(int)std::min<long long>((n_chunks + 255) / 256, (long long)h->num_sms * 16), 256, 0, st>>>(sfe1_f, n_chunks);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) c.rc = fail(h, LPSR_ERR_CUDA, "f32_to_split launch: %s", cudaGetErrorString(e));
+  static const bool sfe1_ffma = getenv("LPSR_SPLIT_SFE1_FFMA") != nullptr;
+  if (h->sfe1_us.packed && !sfe1_ffma) {
+    // 7x7 on tensor cores (umma_conv.cuh kConv7x7, hi + lo weights): the operand is the AutoEncoder output as 16-byte split pixels, staged in the
+    // region of x0 (written only afterwards, by shallowF2)
+    TH* ae8 = reinterpret_cast<TH*>(ws + L.x0);
+    c.begin("ae_to_pix8_split");
+    if (!c.dry && c.rc == LPSR_OK) {
+      const long long n_px = (long long)B * L.P;
+      ae_to_pix8_split_kernel<<<(int)std::min<long long>((n_px + 255) / 256, (long long)h->num_sms * 16), 256, 0, st>>>(ae, ae8, n_px);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) c.rc = fail(h, LPSR_ERR_CUDA, "ae_to_pix8_split launch: %s", cudaGetErrorString(e));
+    }
+    c.begin("umma_conv7x7_split");
+    if (!c.dry && c.rc == LPSR_OK) {
+      ConvW w7;
+      w7.ks = 7; w7.cin = 896; w7.cout = 32;
+      const char* msg = umma_conv_launch<TH>(h->sfe1_us, conv_params(w7, {Seg{ae8, 8, 0, 8}}, 8, sfe1, 64, 0, B, Hp, Wp, false), h->num_sms, c.st);
+      if (msg) c.rc = fail(h, LPSR_ERR_CUDA, "umma_conv 7x7 (split) launch: %s", msg);
+    }
+  } else {
+    launch_direct<float, 7, 3, 32, false, false>(c, conv_params(h->sfe1, ae, 3, 0, 3, sfe1_f, 32, 0, B, Hp, Wp, false));
+    c.begin("f32_to_split");
+    if (!c.dry && c.rc == LPSR_OK) {
+      const long long n_chunks = (long long)B * L.P * 2;
+      f32_to_split_inplace_kernel<<<(int)std::min<long long>((n_chunks + 255) / 256, (long long)h->num_sms * 16), 256, 0, st>>>(sfe1_f, n_chunks);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) c.rc = fail(h, LPSR_ERR_CUDA, "f32_to_split launch: %s", cudaGetErrorString(e));
+    }
   }
 
   // ---- trunk on tensor cores, split operands ---------------------------------------------------------------------------------------------

@@ -54,7 +54,7 @@ constexpr int kEpiGroups = LPSR_UMMA_EPI_GROUPS;   // epilogue groups == TMEM ti
 __host__ __device__ constexpr int umma_threads(int cs) { return (4 * kEpiGroups * cs + kEpiGroups + 1) * 32; }
 constexpr int kUmmaThreads = umma_threads(1);
 constexpr int kUmmaMaxKChunks = 8;      // TMA boxes (K-chunks of 16/32/64 channels) per item
-constexpr int kUmmaMaxSteps = 32;       // K-steps (MMAs per tap) per tile: Cin/16, or 28 pixel-pair steps of the 7x7 conv
+constexpr int kUmmaMaxSteps = 64;       // K-steps (MMAs per tap) per tile: Cin/16, or 28 (56 with hi + lo weights) pixel-pair steps of the 7x7 conv
 constexpr int kUmmaMaxK = 16;           // max M-tiles per item
 constexpr int kUmmaMaxBufs = 4;         // item buffers in the shared-memory ring
 
@@ -549,6 +549,7 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
       // step (dy, dx-pair): A start shifts by dy strip rows + 2*pair pixels; rows are 16-byte pixels (no swizzle, LBO = next pixel)
       for (int dy = 0; dy < 7; ++dy)
         for (int pr = 0; pr < 4; ++pr) steps[dy * 4 + pr] = make_uint4((uint32_t)(dy * p.pitch + 2 * pr), 1u, kUmmaDescHi, 0u);
+      for (int ks = 28; ks < p.n_ks; ++ks) steps[ks] = steps[(ks - p.n_ks_real) * p.wlo_step];   // lo-weight K-steps: the same pixel pairs
     } else if (lane == 0) {
       int ks = 0;
       for (int c = 0; c < p.n_chunks; ++c) {
@@ -1243,7 +1244,7 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
   p.halo = halo;
   p.n_ks = w.cin / 16;                                       // 7x7: 28 pixel-pair steps (UmmaWeights::cin = 448 pseudo channels)
   p.n_ks_real = w.split ? w.n_real : (w.wsplit ? p.n_ks / 2 : p.n_ks);
-  p.wlo_step = w.split ? 2 : 1;
+  p.wlo_step = w.wlo_step ? w.wlo_step : (w.split ? 2 : 1);
   p.acc_scale = w.split ? w.acc_scale : 1.f;
   if (p.n_ks > kUmmaMaxSteps) return "too many K-steps";
   if (w.wsplit && !w.split && (lff || c7)) return "hi + lo weights are not supported by this mode";
@@ -1310,7 +1311,7 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
   const size_t w_bytes = ((lff ? (size_t)(w.cin / 8) * kLffWCols * 16 + 4 * kLffN * 16 : (size_t)ntap * w.cin * NMMA * 2) + 127) & ~(size_t)127;
   const size_t a2_bytes = lff ? (size_t)kEpiGroups * (w.split ? 8192 : 4096) + 2 * 128 * 16 + 2 * kLffCols * 16 + 4 * 32 * 16   // g3 operands, ones, biases, identity
                               : (N > 32 ? (size_t)N * 4 : 0);                                                   // wide layers: bias vector
-  const size_t fixed = w_bytes + (2 * kUmmaMaxBufs + 6 * kEpiGroups + 2) * 8 + xch_bytes + a2_bytes + 640 /*steps, slot_base*/ + 1024 /*alignment slack*/ + 256;
+  const size_t fixed = w_bytes + (2 * kUmmaMaxBufs + 6 * kEpiGroups + 2) * 8 + xch_bytes + a2_bytes + (kUmmaMaxSteps * 16 + 128) /*steps, slot_base*/ + 1024 /*alignment slack*/ + 256;
   const size_t smem_cap = 227 * 1024 - fixed;
   auto item_buf_bytes = [&](size_t npx) {                      // every chunk is 1024-aligned inside the buffer
     size_t b = 0;
@@ -1385,7 +1386,7 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
   if (bufs < 2) return "tile does not fit in shared memory";
   if (bufs > kUmmaMaxBufs) bufs = kUmmaMaxBufs;
   p.n_bufs = bufs;
-  plan.smem_bytes = (size_t)bufs * off + w_bytes + (2 * bufs + 6 * kEpiGroups + 2) * 8 + xch_bytes + a2_bytes + 640 + 1024 + 64;
+  plan.smem_bytes = (size_t)bufs * off + w_bytes + (2 * bufs + 6 * kEpiGroups + 2) * 8 + xch_bytes + a2_bytes + (kUmmaMaxSteps * 16 + 128) + 1024 + 64;
   plan.grid = std::min(p.n_items, num_sms);
   // ---- tensor maps, one per K-chunk
   for (int c = 0; c < p.n_chunks; ++c)
@@ -1493,6 +1494,7 @@ inline const char* umma_plan_launch_split(const UmmaPlan& plan, const UmmaWeight
       if (plain && p.relu && !p.res) return umma_launch_inst<T, 32, kConv3x3Taps, kEpiRelu, T, 1, 1, true>(plan, st);
       if (plain && !p.relu && !p.res) return umma_launch_inst<T, 32, kConv3x3Taps, kEpiPlain, T, 1, 1, true>(plan, st);
     }
+    if (w.ks == 7 && w.cout == 32 && plain && !p.relu && !p.res) return umma_launch_inst<T, 32, kConv7x7, kEpiPlain, T, 1, 1, true>(plan, st);
     if (w.ks == 1 && w.cout == 32 && plain && !p.relu && !p.res) return umma_launch_inst<T, 32, kConv1x1, kEpiPlain, T, 1, 1, true>(plan, st);
     if (w.ks == 1 && w.cout == 32 && plain && !p.relu && p.res) return umma_launch_inst<T, 32, kConv1x1, kEpiResidual, T, 1, 1, true>(plan, st);
     return "split tensors: shape/epilogue not instantiated";

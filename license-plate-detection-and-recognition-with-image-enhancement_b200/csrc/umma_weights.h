@@ -18,6 +18,7 @@ struct UmmaWeights {
   int ks = 0, cin = 0, cout = 0;
   uint16_t* w = nullptr;   // 16-bit (bf16 or fp16): 1x1 [cin/8][cout][8]; 3x3 [dy][cin/8][dx*cout + co][8] (dx folded into N)
   float* bias = nullptr;   // [cout] (zeros if the conv has no bias)
+  int wlo_step = 0;        // 0: default (1; 2 for split tensors); otherwise the activation K-step stride of the lo-weight K-steps
   bool fused_lff = false;  // kConv3x3FoldLff: w = [cin/8][48 folded + 32 lff hi + 32 lff lo][8] (dy = 1), [cin/8][48][8] (dy = 0), [cin/8][48][8] (dy = 2), then lff's g3 slice [2][32 hi | 32 lo][8]; bias = [16] + [32]
   bool split = false;      // split (double-fp16) activations: K rows = per real 16-channel chunk [W_hi for the hi chunk, W_hi for the lo chunk], then the
                            // lo terms of the weights once per real chunk (re-reading the hi tiles); n_real = K-slices staged in shared memory
