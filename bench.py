@@ -73,8 +73,42 @@ class ClockSampler:
         self.idx = gpu_index
         self.proc = None
         self.lines = []
+        self.nvml = None
+        self.samples = []          # (sm MHz, max sm MHz, power W, reason bitmask) through NVML: every 10 ms, the first one immediately
+        self._stop = threading.Event()
+
+    def _nvml_loop(self, pynvml, handle):
+        while True:
+            try:
+                self.samples.append((float(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)),
+                                     float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM)),
+                                     pynvml.nvmlDeviceGetPowerUsage(handle) / 1000.0,
+                                     int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(handle))))
+            except Exception:
+                pass
+            if self._stop.wait(0.01):
+                return
 
     def start(self):
+        # NVML in-process (the same counters nvidia-smi prints) so that even a 30 ms timed region (strong scaling at 8 GPUs) is sampled;
+        # nvidia-smi -lms as the fallback
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES remaps ordinals: resolve by PCI bus id of the torch device
+            try:
+                bus = torch.cuda.get_device_properties(self.idx).pci_bus_id
+                dom = torch.cuda.get_device_properties(self.idx).pci_domain_id
+                dev = torch.cuda.get_device_properties(self.idx).pci_device_id
+                handle = pynvml.nvmlDeviceGetHandleByPciBusId(f"{dom:08x}:{bus:02x}:{dev:02x}.0".encode())
+            except Exception:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            self.nvml = pynvml
+            self.t = threading.Thread(target=self._nvml_loop, args=(pynvml, handle), daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -88,6 +122,19 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop.set()
+            self.t.join(timeout=1)
+            n = self.nvml
+            bits = {"hw_slowdown": getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                    "hw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                    "sw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                    "sw_power_cap": getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            sm = [s[0] for s in self.samples]
+            reasons = sorted(k for k, b in bits.items() if any(s[3] & b for s in self.samples))
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max((s[1] for s in self.samples), default=None),
+                    "power_w_max": max((s[2] for s in self.samples), default=None), "samples": len(sm), "reasons": reasons,
+                    "source": "NVML, 10 ms interval during the timed region"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -110,7 +157,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 100"}
 
 
 def ncu_traffic():
