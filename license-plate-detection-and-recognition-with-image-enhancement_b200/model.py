@@ -235,13 +235,16 @@ class LPSR(nn.Module):
             ws = self._workspace(h, dev, B, H, W)
             cur = torch.cuda.current_stream(dev)
             # the scratch is shared by every forward of this shape: a forward on a different stream than the previous one waits for it
+            # (not while `cur` is being captured into a CUDA graph: a capturing stream cannot wait on work outside its graph -- the caller orders
+            # the capture after earlier forwards, as torch.cuda.graph does by synchronising the device first)
             used = self._ws_streams.setdefault((dev, B, H, W, self.precision), [])
-            if used and used[-1] != cur:
-                cur.wait_stream(used[-1])
-            if cur not in used:
-                used.append(cur)
-            elif used[-1] != cur:
-                used.remove(cur); used.append(cur)
+            if not torch.cuda.is_current_stream_capturing():
+                if used and used[-1] != cur:
+                    cur.wait_stream(used[-1])
+                if cur not in used:
+                    used.append(cur)
+                elif used[-1] != cur:
+                    used.remove(cur); used.append(cur)
             capi.check(lib.lpsr_forward(h, xin.data_ptr(), y.data_ptr(), B, H, W, self._aligned_ptr(ws),
                                         ws.numel() - (self._aligned_ptr(ws) - ws.data_ptr()), cur.cuda_stream), h, "lpsr_forward")
         return y
