@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(kTailSpThreads, 1) csar_tail_split_umma_kernel
     ptx::fence_mbar_init();
   }
   if (warp == 4 * G) {
-    ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 256);
+    ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
     ptx::tmem_relinquish();
   }
   ptx::fence_proxy_async();
@@ -120,14 +120,18 @@ __global__ void __launch_bounds__(kTailSpThreads, 1) csar_tail_split_umma_kernel
           if (!ptx::mbar_test_wait(bar(s, phase * 2), par_s[s])) continue;   // a1_full / a2_ready / a3_ready
           ptx::tc_fence_after();
           const uint32_t slot16 = ptx::smem_u32(slots + (size_t)s * kSlot) >> 4;
-          const uint32_t d = tmem_base + (uint32_t)(s * 64);     // 64 columns per slot: H, then S in [0,32) and O in [32,64)
+          // 128 columns per slot: hi x hi products in [0,64) (H, then S in [0,32) and O in [32,64)), the lo terms A_lo W_hi + A_hi W_lo in the same
+          // layout 64 columns further: the tensor core truncates every accumulation step, so the small terms get their own accumulator
+          // (umma_conv.cuh, NACCW) and the epilogue adds the two blocks
+          const uint32_t d = tmem_base + (uint32_t)(s * 128);
           if (phase == 0) {
             // K rows of W3 (umma_pack_weights_split, 2 real chunks): [hiW0 | hiW0 | hiW1 | hiW1 | loW0 | loW1] against the x_in tile's
             // 32-byte column blocks [hi0 | lo0 | hi1 | lo1] of its 128-byte (swizzled) rows
 #pragma unroll
             for (int ks = 0; ks < 6; ++ks) {
               const uint32_t as = ks < 4 ? (uint32_t)ks : (uint32_t)(ks - 4) * 2u;
-              ptx::tc_mma_f16_lohi(d, (slot16 + 2u * as) | (1u << 16), a1_hi, w3_lo + (uint32_t)(ks * 2 * 64), kUmmaDescHi, idesc64, ks ? 1u : 0u);
+              const bool lo_term = ks >= 4 || (ks & 1);
+              ptx::tc_mma_f16_lohi(d + (lo_term ? 64u : 0u), (slot16 + 2u * as) | (1u << 16), a1_hi, w3_lo + (uint32_t)(ks * 2 * 64), kUmmaDescHi, idesc64, ks > 1 ? 1u : 0u);
             }
           } else {
             // planar split operand [cg][128 rows][16 B], K-slices [hi0 | lo0 | hi1 | lo1 | hi2 | lo2 | hi3 | lo3]; weight rows as above, 4 real chunks
@@ -137,7 +141,8 @@ __global__ void __launch_bounds__(kTailSpThreads, 1) csar_tail_split_umma_kernel
 #pragma unroll
             for (int ks = 0; ks < 12; ++ks) {
               const uint32_t as = ks < 8 ? (uint32_t)ks : (uint32_t)(ks - 8) * 2u;
-              ptx::tc_mma_f16_lohi(dd, (a16 + as * 2u * 128u) | (128u << 16), kUmmaDescHi, w_lo + (uint32_t)(ks * 2 * 32), kUmmaDescHi, idesc32, ks ? 1u : 0u);
+              const bool lo_term = ks >= 8 || (ks & 1);
+              ptx::tc_mma_f16_lohi(dd + (lo_term ? 64u : 0u), (a16 + as * 2u * 128u) | (128u << 16), kUmmaDescHi, w_lo + (uint32_t)(ks * 2 * 32), kUmmaDescHi, idesc32, ks > 1 ? 1u : 0u);
             }
           }
           ptx::tc_commit(bar(s, phase * 2 + 1));                         // h_full / s_full / o_full
@@ -154,7 +159,7 @@ __global__ void __launch_bounds__(kTailSpThreads, 1) csar_tail_split_umma_kernel
     const int g = warp >> 2, wq = warp & 3, row = wq * 32 + lane;
     uint8_t* slot = slots + (size_t)g * kSlot;
     uint8_t* a2 = slot + kA1;
-    const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(g * 64);
+    const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(g * 128);
     const T* res = static_cast<const T*>(p.res);
     T* out = static_cast<T*>(p.out);
     const float s3 = p.s3, s4 = p.s4, so = p.so;
@@ -188,8 +193,12 @@ __global__ void __launch_bounds__(kTailSpThreads, 1) csar_tail_split_umma_kernel
       ptx::tc_fence_after();
 #pragma unroll
       for (int c0 = 0; c0 < 64; c0 += 16) {
-        float v[16];
-        ptx::tc_ld16(taddr + c0, v);
+        float v[16], vl[16];
+        ptx::tc_ld16_nowait(taddr + c0, v);
+        ptx::tc_ld16_nowait(taddr + 64 + c0, vl);
+        ptx::tc_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] += vl[c];
 #pragma unroll
         for (int c = 0; c < 16; c += 4) {
           const float4 b = *reinterpret_cast<const float4*>(b3_s + c0 + c);
@@ -219,7 +228,14 @@ __global__ void __launch_bounds__(kTailSpThreads, 1) csar_tail_split_umma_kernel
           const float2 a = __half22float2(xh[i]), b = __half22float2(xh[8 + i]);
           x[2 * i] = a.x + b.x; x[2 * i + 1] = a.y + b.y;
         }
-        ptx::tc_ld16(taddr + q * 16, v);
+        {
+          float vl[16];
+          ptx::tc_ld16_nowait(taddr + q * 16, v);
+          ptx::tc_ld16_nowait(taddr + 64 + q * 16, vl);
+          ptx::tc_wait_ld();
+#pragma unroll
+          for (int c = 0; c < 16; ++c) v[c] += vl[c];
+        }
 #pragma unroll
         for (int c = 0; c < 16; c += 4) {
           const float4 b = *reinterpret_cast<const float4*>(b4_s + q * 16 + c);
@@ -244,10 +260,14 @@ __global__ void __launch_bounds__(kTailSpThreads, 1) csar_tail_split_umma_kernel
       // ---- phase 3: out = acc * so + bo + x -> split tensor
       ptx::mbar_wait(bar(g, 5), par);
       ptx::tc_fence_after();
-      float o[32];
+      float o[32], ol[32];
       ptx::tc_ld16_nowait(taddr + 32, o);
       ptx::tc_ld16_nowait(taddr + 48, o + 16);
+      ptx::tc_ld16_nowait(taddr + 96, ol);
+      ptx::tc_ld16_nowait(taddr + 112, ol + 16);
       ptx::tc_wait_ld();
+#pragma unroll
+      for (int c = 0; c < 32; ++c) o[c] += ol[c];
       ptx::tc_fence_before();                                             // accumulators are in registers: free the slot
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar(g, 6));
@@ -268,7 +288,7 @@ __global__ void __launch_bounds__(kTailSpThreads, 1) csar_tail_split_umma_kernel
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 4 * G) ptx::tmem_dealloc(tmem_base, 256);
+  if (warp == 4 * G) ptx::tmem_dealloc(tmem_base, 512);
 }
 
 inline const char* csar_tail_split_umma_launch(const TailSplitParams& pin, int num_sms, cudaStream_t st) {

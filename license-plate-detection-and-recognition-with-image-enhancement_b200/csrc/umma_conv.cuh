@@ -459,9 +459,15 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
   #ifndef LPSR_UMMA_NACC_FOLD
 #define LPSR_UMMA_NACC_FOLD 0
 #endif
-  constexpr int NACC = (MODE == kConv3x3Fold && (CS == 2 || LPSR_UMMA_NACC_FOLD) && 2 * G * NMMA <= 512) ? 2 : 1;
+  // Split operands: the hi x hi products and the (2^-11 smaller) lo terms A_lo W_hi + A_hi W_lo accumulate in SEPARATE TMEM column blocks and are
+  // added once in the epilogue.  The tensor core truncates every fp32 accumulation step; with all three terms in one accumulator the 3 K/16 steps
+  // per output left a relative error of ~1.4e-6 per layer (tools/parity_stages.py), which this network amplifies 30-60x; the main block now takes
+  // K/16 steps and the lo block's truncation errors are 2^-11 smaller.
+  constexpr int NACCW = SP ? 2 * NMMA : NMMA;                  // TMEM columns per accumulator
+  constexpr int NACC = (MODE == kConv3x3Fold && (CS == 2 || LPSR_UMMA_NACC_FOLD) && !SP && 2 * G * NMMA <= 512) ? 2 : 1;
   constexpr int GA = G * NACC;                                  // accumulators in TMEM
-  constexpr uint32_t kTmemCols = (GA * NMMA <= 32) ? 32 : (GA * NMMA <= 64) ? 64 : (GA * NMMA <= 128) ? 128 : (GA * NMMA <= 256) ? 256 : 512;
+  constexpr uint32_t kTmemCols = (GA * NACCW <= 32) ? 32 : (GA * NACCW <= 64) ? 64 : (GA * NACCW <= 128) ? 128 : (GA * NACCW <= 256) ? 256 : 512;
+  static_assert(GA * NACCW <= 512, "TMEM accumulators");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // TMA swizzle atoms need 1024-byte aligned destinations: align the carve-up by hand
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -628,6 +634,8 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
     const uint32_t cgn = (uint32_t)(CG * NMMA);               // weights: 16-byte units between taps
     const uint32_t a_smem16 = ptx::smem_u32(a_smem) >> 4, buf16_sz = buf_bytes >> 4;
     const int n_ks = p.n_ks, k_tiles = p.k;
+    [[maybe_unused]] const int n_ks_real = p.n_ks_real;
+    [[maybe_unused]] const bool wlo2 = p.wlo_step == 2;
     const uint32_t tstride = (uint32_t)p.tstride;
     const bool no_mma = (p.debug & 1) != 0;
     __syncwarp();
@@ -654,8 +662,9 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
         ptx::tc_fence_after();
         LPSR_TRACE(leader, ii * k_tiles + m, 1, clock64());
         if (leader) {
-          const uint32_t d = tmem_base + acc * NMMA;
+          const uint32_t d = tmem_base + acc * NACCW;
           uint32_t b_lo = w_lo;
+          [[maybe_unused]] uint32_t lo_started = 0;               // split operands: the lo-term accumulator block has been initialised
           if (!no_mma) {
             if constexpr (LFF) ptx::tc_mma_f16_lohi(d, ones_lo, kUmmaDescHi, lffb_lo, kUmmaDescHi, idesc, 0u);   // accumulator := biases
 #pragma unroll 1
@@ -668,6 +677,16 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
                 ptx::tc_mma_f16_lohi(d, a0 + e.w, e.z, wl1_lo + k2 * kLffCols, kUmmaDescHi, idesc, 1u);
                 ptx::tc_mma_f16_lohi(d, a0, e.z, wl0_lo + k2 * 48u, kUmmaDescHi, idesc48, 1u);
                 ptx::tc_mma_f16_lohi(d, a0 + 2u * e.w, e.z, wl2_lo + k2 * 48u, kUmmaDescHi, idesc48, 1u);
+              } else if constexpr (SP) {
+                // lo term: a lo-weight K-slice (ks >= n_ks_real) or the lo chunk of a split activation tensor (odd K-slices; wlo_step == 2)
+                const bool lo_term = ks >= n_ks_real || (wlo2 && (ks & 1));
+                const uint32_t dd = lo_term ? d + NMMA : d;
+#pragma unroll
+                for (int t = 0; t < NTAP; ++t) {
+                  const uint32_t shift = (FOLD || FOLD5) ? (uint32_t)t * e.w : (uint32_t)(t / KSZ) * e.w + (uint32_t)(t % KSZ) * e.y;
+                  ptx::tc_mma_f16_lohi(dd, a0 + shift, e.z, b_lo + (uint32_t)t * cgn, kUmmaDescHi, idesc, lo_term ? (lo_started | (uint32_t)t) : (uint32_t)(ks | t));
+                }
+                if (lo_term) lo_started = 1u;
               } else {
 #pragma unroll
                 for (int t = 0; t < NTAP; ++t) {
@@ -691,7 +710,7 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
           if (leader) {
             if (!no_mma) {
               // lff's g3 slice, hi | lo weights along N: one N = 64 MMA into columns 48..111
-              ptx::tc_mma_f16_lohi(tmem_base + acc * NMMA + 48, a2_lo, kUmmaDescHi, w2_lo, kUmmaDescHi, idesc64, 1u);
+              ptx::tc_mma_f16_lohi(tmem_base + acc * NACCW + 48, a2_lo, kUmmaDescHi, w2_lo, kUmmaDescHi, idesc64, 1u);
             }
             ptx::tc_commit(tfull2_bar(acc));
           }
@@ -717,7 +736,7 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
     T* out = static_cast<T*>(p.out);
     const T* res = static_cast<const T*>(p.res);
     float* xg = xchg + (size_t)grp * (2 * 4 * 2 * XROW * NOUT);
-    const uint32_t taddr0 = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(grp * NMMA);
+    const uint32_t taddr0 = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(grp * NACCW);
     // everything the per-tile path needs lives in registers
     const int pitch = p.pitch, tstride = p.tstride, k_tiles = p.k, Himg = p.H, Wimg = p.W, halo = p.halo, TWs = p.TW;
     const int ips = p.items_per_strip, per_crop = p.n_strips * p.items_per_strip, crop_px = p.H * p.W;
@@ -795,7 +814,7 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
         }
         LPSR_TRACE(wq == 0 && lane == 0, ii * k_tiles + m, 3, clock64());
         const int accI = grp + G * (int)esel;                   // this tile's accumulator
-        const uint32_t taddr = taddr0 + esel * (uint32_t)(G * NMMA);
+        const uint32_t taddr = taddr0 + esel * (uint32_t)(G * NACCW);
         ptx::mbar_wait(tfull_bar(accI), (full_bits >> esel) & 1u);
         full_bits ^= 1u << esel;
         esel ^= (uint32_t)(NACC - 1);
@@ -872,7 +891,8 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
           }
         } else {
         constexpr bool PRELOAD = !FOLD && !FOLD5;
-        constexpr int PB = NS == 2 ? 16 : (NOUT <= 64 ? NOUT : 64);   // N-split: block by block, the lo block is added right after its load
+        constexpr bool DUAL = (NS == 2) || SP;                        // a second column block (lo weights along N / split lo terms) is added to the first
+        constexpr int PB = DUAL ? 16 : (NOUT <= 64 ? NOUT : 64);      // dual: block by block, the lo block is added right after its load
         static_assert(NOUT % PB == 0, "block size");
         [[maybe_unused]] float vall[PRELOAD ? PB : 1];
 #pragma unroll
@@ -882,10 +902,10 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
             if (cc % PB == 0) {
 #pragma unroll
               for (int c2 = 0; c2 < PB; c2 += CH) ptx::tc_ld16_nowait(taddr + cc + c2, vall + c2);
-              [[maybe_unused]] float vlo[NS == 2 ? PB : 1];
-              if constexpr (NS == 2) ptx::tc_ld16_nowait(taddr + NOUT + cc, vlo);
+              [[maybe_unused]] float vlo[DUAL ? PB : 1];
+              if constexpr (DUAL) ptx::tc_ld16_nowait(taddr + NOUT + cc, vlo);
               ptx::tc_wait_ld();
-              if constexpr (NS == 2) {
+              if constexpr (DUAL) {
 #pragma unroll
                 for (int c = 0; c < PB; ++c) vall[c] += vlo[c];
               }
@@ -962,6 +982,15 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
             if (!LPSR_DBG(64)) ptx::tc_ld16_nowait(taddr + cc, lf);
             ptx::tc_ld16_nowait(taddr + NOUT + cc, v);
             if (!LPSR_DBG(64)) ptx::tc_ld16_nowait(taddr + 2 * NOUT + cc, rg);
+            if constexpr (SP) {   // + the lo-term accumulator block (same three dx sub-blocks, NMMA columns further)
+              float lf2[CH], v2[CH], rg2[CH];
+              ptx::tc_ld16_nowait(taddr + NMMA + cc, lf2);
+              ptx::tc_ld16_nowait(taddr + NMMA + NOUT + cc, v2);
+              ptx::tc_ld16_nowait(taddr + NMMA + 2 * NOUT + cc, rg2);
+              ptx::tc_wait_ld();
+#pragma unroll
+              for (int c = 0; c < CH; ++c) { lf[c] += lf2[c]; v[c] += v2[c]; rg[c] += rg2[c]; }
+            }
             ptx::tc_wait_ld();
             if (cc + CH >= NOUT && !LFF) {
               ptx::tc_fence_before();
@@ -1252,7 +1281,7 @@ inline const char* umma_plan(UmmaPlan& plan, const UmmaWeights& w, const ConvPar
   if (!c7 && cp.n_chunks != p.n_ks_real) return "chunk table does not match Cin/16";
   if (!fp32_out && (cp.out_pitch % 16 || cp.out_off % 16 || reinterpret_cast<uintptr_t>(cp.out) % 32)) return "output pitch/offset not 32-byte aligned (256-bit stores)";
   if (cp.res && (cp.res_pitch % 8 || cp.res_off % 8)) return "residual pitch/offset not 16-byte aligned";
-  if (kEpiGroups * NMMA > 512) return "N too large for the TMEM accumulators";
+  if (kEpiGroups * NMMA * (w.split ? 2 : 1) > 512) return "N too large for the TMEM accumulators";
   // ---- K-chunks: merge runs of 16-channel slices that are contiguous in the SAME tensor into TMA boxes of 64 / 32 / 16 ch
   const void* chunk_base[kUmmaMaxKChunks];
   int chunk_pitch[kUmmaMaxKChunks];
