@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(kThreads) ae_unshuffle_in_kernel(const float* 
                                                                    int inH, int inW) {
   const int Ho = H >> 1, Wo = W >> 1;
   const long long total = (long long)B * Ho * Wo;
-  const bool vec = (inW % 2 == 0);                               // float2 alignment of every (even-x) pixel pair
+  const bool vec = (inW % 2 == 0) && (reinterpret_cast<uintptr_t>(x) % 8 == 0);   // float2 alignment of every (even-x) pixel pair (a sliced tensor may start on an odd float)
   for (long long pix = blockIdx.x * (long long)kThreads + threadIdx.x; pix < total; pix += (long long)gridDim.x * kThreads) {
     const int xo = (int)(pix % Wo), yo = (int)((pix / Wo) % Ho), n = (int)(pix / ((long long)Wo * Ho));
     uint4 q[2];

@@ -944,7 +944,7 @@ int lpsr_preprocess_resize(lpsr_handle* h, const uint8_t* crops, const int64_t* 
   // weight can be non-zero, so processing all H rows gives the same values (the vertical bounds index the unshifted rows)
   const size_t tab_bytes = tab.size() * sizeof(int), desc_bytes = desc.size() * sizeof(ResampleCrop);
   const size_t need_dev = align_up(tab_bytes, 256) + align_up(desc_bytes, 256) + (size_t)tmp_total;
-  if (h->pre_ev) CUDA_TRY(h, cudaEventSynchronize(h->pre_ev));            // the previous call's table upload has left the staging buffer
+  if (h->pre_ev) CUDA_TRY(h, cudaEventSynchronize(h->pre_ev));            // the previous call's kernel is done with the staging buffer, the tables and the scratch
   else CUDA_TRY(h, cudaEventCreateWithFlags(&h->pre_ev, cudaEventDisableTiming));
   if (h->pre_host_cap < tab_bytes + desc_bytes) {
     if (h->pre_host) cudaFreeHost(h->pre_host);
@@ -968,9 +968,11 @@ int lpsr_preprocess_resize(lpsr_handle* h, const uint8_t* crops, const int64_t* 
   uint8_t* d_tmp = reinterpret_cast<uint8_t*>(dp + align_up(tab_bytes, 256) + align_up(desc_bytes, 256));
   CUDA_TRY(h, cudaMemcpyAsync(d_tab, hp, tab_bytes, cudaMemcpyHostToDevice, st));
   CUDA_TRY(h, cudaMemcpyAsync(d_desc, hp + tab_bytes, desc_bytes, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(h, cudaEventRecord(h->pre_ev, st));
   preprocess_resize_kernel<<<B, 256, 0, st>>>(crops, d_desc, d_tab, d_tmp, x_out, out_h, out_w);
   CUDA_TRY(h, cudaGetLastError());
+  // recorded AFTER the kernel: the next call (on any stream) waits until this one has finished reading the tables, the descriptors and
+  // the scratch before it overwrites them, not only until the staging buffer was copied
+  CUDA_TRY(h, cudaEventRecord(h->pre_ev, st));
   return LPSR_OK;
 }
 
