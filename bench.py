@@ -593,7 +593,7 @@ def run_ours(args):
         per_kernel[kind][1] += names.count(name)
     # the dominant kernel family: the tcgen05 implicit-GEMM convolutions (umma_conv_kernel instantiations + the fused RDB chain);
     # the CSAR tail kernel (also tcgen05, HBM bound) is reported separately under roofline_csar
-    is_conv = lambda n_: n_.split(":")[1].startswith(("umma_conv", "rdb_chain"))
+    is_conv = lambda n_: n_.split(":")[1].startswith(("umma_conv", "rowconv", "rdb_chain"))
     is_tail = lambda n_: ".tail:" in n_
     conv_ms = sum(t for n_, t in fam_ms.items() if is_conv(n_))
     conv_tags = {n_.split(":")[0] for n_ in names if is_conv(n_)}

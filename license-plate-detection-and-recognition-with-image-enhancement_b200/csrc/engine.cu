@@ -142,6 +142,12 @@ bool pack_conv(lpsr_handle* h, ConvW& cw, const std::string& prefix, int cin, in
                            h->cfg.precision == LPSR_PREC_FP16, [&](const std::vector<uint16_t>& v) { return arena_put(h, v); },
                            [&](const std::vector<float>& v) { return arena_put(h, v); }))
       return false;
+    // row-streaming kernel (rowconv.cuh): every 3x3 layer with 16 or 32 output channels that keeps single-rounded weights
+    cw.rw = RowWeights{};
+    if (ks == 3 && (cout == 16 || cout == 32) && cin <= 16 * kMaxChunks &&
+        !rowconv_pack_weights(cw.rw, pw.data(), bias ? pb.data() : nullptr, cin, cout, h->cfg.precision == LPSR_PREC_FP16,
+                              [&](const std::vector<uint16_t>& v) { return arena_put(h, v); }, [&](const std::vector<float>& v) { return arena_put(h, v); }))
+      return false;
   }
   cw.us = UmmaWeights{};
   if (h->fp32_split && umma_supported(ks, cin, cout) && 3 * cin / 16 <= kUmmaMaxSteps &&
@@ -418,6 +424,7 @@ int pack_all(lpsr_handle* h) {
     };
     ok &= repack(h->csar_c1, "rdn.csar.conv_in.0");
     ok &= repack(h->csar_c2, "rdn.csar.conv_in.2");
+    h->csar_c1.rw.packed = h->csar_c2.rw.packed = false;   // hi + lo weights: these two stay on the per-tap kernel
   }
   ok &= pack_conv(h, h->csar_sa1, "rdn.csar.sa.block.0", F, 2 * F, 1, true);    // tensor-core CSAR tail (16-bit modes)
   ok &= pack_conv(h, h->csar_sa2, "rdn.csar.sa.block.2", 2 * F, F, 1, true);
@@ -483,6 +490,9 @@ int pack_all(lpsr_handle* h) {
     quantize_conv_sum_preserving(pw, 9, F, 16, h->cfg.precision == LPSR_PREC_FP16);
     ok &= umma_pack_weights(h->fin_u, pw.data(), pb.data(), 3, F, 16, h->cfg.precision == LPSR_PREC_FP16,
                             [&](const std::vector<uint16_t>& v) { return arena_put(h, v); }, [&](const std::vector<float>& v) { return arena_put(h, v); });
+    h->fin_rw = RowWeights{};
+    ok &= rowconv_pack_weights(h->fin_rw, pw.data(), pb.data(), F, 16, h->cfg.precision == LPSR_PREC_FP16,
+                               [&](const std::vector<uint16_t>& v) { return arena_put(h, v); }, [&](const std::vector<float>& v) { return arena_put(h, v); });
   }
   h->fin_us = UmmaWeights{};
   if (h->fp32_split) {   // final conv for split operands: Cout padded 1 -> 16 with zero filters

@@ -12,6 +12,7 @@
 #include "../../include/lpsr_b200.h"
 #include "common.cuh"
 #include "umma_weights.h"
+#include "rowconv_weights.h"
 
 namespace lpsr {
 
@@ -33,6 +34,7 @@ struct ConvW {
   float* w = nullptr;      // [ks*ks][cin][cout] fp32 (CUDA-core kernels)
   float* b = nullptr;      // [cout] fp32 (nullptr: no bias)
   UmmaWeights u;           // tensor-core packing (16-bit modes)
+  RowWeights rw;           // row-streaming 3x3 kernel (rowconv.cuh), 16-bit modes
   UmmaWeights us;          // tensor-core packing for split (double-fp16) operands: the fp32-accuracy mode (forward_split.cuh)
 };
 
@@ -58,6 +60,7 @@ struct lpsr_handle {
   // packed layers
   lpsr::ConvW ae_in, ae_out, sfe1, sfe2, rdb[2][4], lff[2], csar_c1, csar_c2, csar_sa1, csar_sa2, csar_co, gff0, gff1, fin;
   lpsr::UmmaWeights fin_u;   // final conv with Cout padded 1 -> 16 for the tensor-core path
+  lpsr::RowWeights fin_rw;   // the same for the row-streaming kernel (rowconv.cuh)
   lpsr::UmmaWeights fin_us;  // the same for split operands
   lpsr::UmmaWeights sfe1_us;   // shallowF1 7x7 for the fp32-accuracy mode: 8-slot pixels [hi(3) | lo(3) | 0 0], hi + lo weights (56 K-steps)
   lpsr::UmmaWeights csar_co_us_scaled;   // conv_out for the split tensor-core tail: channel-branch rows x kCsarChanScale

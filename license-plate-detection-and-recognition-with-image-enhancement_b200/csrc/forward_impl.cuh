@@ -7,6 +7,7 @@
 #include "cuda_core_kernels.cuh"
 #include "engine_internal.h"
 #include "umma_conv.cuh"
+#include "rowconv.cuh"
 #include "csar_tail_umma.cuh"
 
 namespace lpsr {
@@ -77,6 +78,18 @@ template <typename T>
 void dense_conv(Ctx& c, const ConvW& w, ConvParams p) {
   if constexpr (sizeof(T) == 2) {
     if (w.u.packed) {
+      if (w.rw.packed && w.ks == 3 && rowconv_enabled() && !(p.relu && p.res)) {
+        RowPlan rp;
+        if (!rowconv_plan(rp, w.rw, p, c.h->num_sms, !IsBf16<T>::value)) {   // shapes it does not cover fall through to umma_conv
+          c.begin("rowconv");
+          if (c.dry || c.rc != LPSR_OK) return;
+          bool handled = false;
+          const char* msg = rowconv_launch<T>(w.rw, p, c.h->num_sms, c.st, &handled);
+          if (msg) c.rc = fail(c.h, LPSR_ERR_CUDA, "rowconv launch (cin=%d cout=%d): %s", w.cin, w.cout, msg);
+          if (handled || msg) return;
+          c.launches--;
+        }
+      }
       c.begin("umma_conv");
       if (c.dry || c.rc != LPSR_OK) return;
       const char* msg = umma_conv_launch<T>(w.u, p, c.h->num_sms, c.st);
@@ -421,16 +434,24 @@ int forward_impl(lpsr_handle* h, const float* x, float* y, int B, int H, int W, 
   c.tag = "final_conv";
   bool fin_done = false;
   if constexpr (sizeof(T) == 2) {
-    if (h->fin_u.packed) {   // tensor cores: Cout padded to 16, folded taps, epilogue keeps channel 0 -> sigmoid -> fp32
-      c.begin("umma_conv_final");
+    if (h->fin_u.packed) {   // tensor cores: Cout padded to 16, epilogue keeps channel 0 -> sigmoid -> fp32
+      ConvW fw;
+      fw.ks = 3; fw.cin = 32; fw.cout = 16;
+      const ConvParams fp = conv_params(fw, g, 32, 0, 16, y, 1, 0, B, Hp, Wp, false);
+      RowPlan rp;
+      const bool row = h->fin_rw.packed && rowconv_enabled() && !rowconv_plan(rp, h->fin_rw, fp, h->num_sms, !IsBf16<T>::value, true);
+      c.begin(row ? "rowconv_final" : "umma_conv_final");
       fin_done = true;
       if (!c.dry && c.rc == LPSR_OK) {
-        ConvW fw;
-        fw.ks = 3; fw.cin = 32; fw.cout = 16;
-        UmmaGate fg{};
-        fg.final_sigmoid = 1;
-        const char* msg = umma_conv_launch<T>(h->fin_u, conv_params(fw, g, 32, 0, 16, y, 1, 0, B, Hp, Wp, false), h->num_sms, c.st, &fg);
-        if (msg) c.rc = fail(h, LPSR_ERR_CUDA, "umma_conv final launch: %s", msg);
+        const char* msg = nullptr;
+        bool handled = false;
+        if (row) msg = rowconv_launch<T>(h->fin_rw, fp, h->num_sms, c.st, &handled, true);
+        if (!handled && !msg) {
+          UmmaGate fg{};
+          fg.final_sigmoid = 1;
+          msg = umma_conv_launch<T>(h->fin_u, fp, h->num_sms, c.st, &fg);
+        }
+        if (msg) c.rc = fail(h, LPSR_ERR_CUDA, "final conv launch: %s", msg);
       }
     }
   }
@@ -456,7 +477,7 @@ int op_conv_impl(lpsr_handle* h, const float* x, const float* w_oihw, const floa
       for (int t = 0; t < ks * ks; ++t) pw[((size_t)t * Cin + ci) * Cout + co] = wh[((size_t)co * Cin + ci) * ks * ks + t];
   // private scratch: [packed weights | bias | umma weights | in NHWC | out NHWC]
   void* scratch = nullptr;
-  const size_t wbytes = align_up(pw.size() * 4, 256) + align_up(Cout * 4, 256) + align_up(pw.size() * 2 + 4096, 256) + 256;
+  const size_t wbytes = align_up(pw.size() * 4, 256) + align_up(Cout * 4, 256) + align_up(pw.size() * 2 + 4096, 256) + align_up(pw.size() * 2 * 7 / 3 + 4096, 256) + 1024;
   const size_t total = wbytes + align_up(npix * Cin * sizeof(T), 256) + align_up(npix * Cout * sizeof(T), 256);
   CUDA_TRY(h, cudaMalloc(&scratch, total));
   char* sp = static_cast<char*>(scratch);
@@ -473,6 +494,10 @@ int op_conv_impl(lpsr_handle* h, const float* x, const float* w_oihw, const floa
   cw.b = bias ? static_cast<float*>(put(bh.data(), Cout * 4)) : nullptr;
   if (sizeof(T) == 2 && umma_supported(ks, Cin, Cout)) {
     bool ok = umma_pack_weights(cw.u, pw.data(), bias ? bh.data() : nullptr, ks, Cin, Cout, h->cfg.precision == LPSR_PREC_FP16,
+                                [&](const std::vector<uint16_t>& v) { return static_cast<uint16_t*>(put(v.data(), v.size() * 2)); },
+                                [&](const std::vector<float>& v) { return static_cast<float*>(put(v.data(), v.size() * 4)); });
+    if (ok && ks == 3 && (Cout == 16 || Cout == 32))
+      ok = rowconv_pack_weights(cw.rw, pw.data(), bias ? bh.data() : nullptr, Cin, Cout, h->cfg.precision == LPSR_PREC_FP16,
                                 [&](const std::vector<uint16_t>& v) { return static_cast<uint16_t*>(put(v.data(), v.size() * 2)); },
                                 [&](const std::vector<float>& v) { return static_cast<float*>(put(v.data(), v.size() * 4)); });
     if (!ok || off > wbytes) { cudaFree(scratch); return fail(h, LPSR_ERR_CUDA, "op_conv: umma weight packing failed"); }

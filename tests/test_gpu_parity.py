@@ -125,6 +125,9 @@ CONV_SHAPES = [  # (ks, Cin, Cout, B, H, W, relu) -- every GEMM shape of SURVEY 
     (3, 32, 16, 2, 32, 192, True), (3, 48, 16, 1, 64, 192, True), (3, 64, 16, 1, 20, 36, True), (3, 80, 16, 2, 16, 200, True),
     (3, 32, 32, 1, 64, 192, False), (3, 32, 32, 3, 4, 4, True), (3, 32, 32, 1, 128, 384, False), (3, 32, 32, 1, 36, 196, False),
     (1, 96, 32, 2, 32, 192, False), (1, 128, 32, 1, 64, 192, False), (1, 32, 64, 1, 24, 40, True), (1, 64, 32, 5, 4, 4, False),
+    # row-streaming kernel (rowconv.cuh): crop groups with a partial last group, work ranges cut inside a crop, narrow and 255-wide rows
+    (3, 32, 16, 7, 64, 192, True), (3, 80, 16, 5, 64, 192, True), (3, 32, 32, 7, 64, 192, False), (3, 48, 16, 40, 8, 24, True),
+    (3, 32, 16, 2, 12, 255, True), (3, 64, 16, 160, 4, 4, True),
 ]
 
 
