@@ -476,6 +476,11 @@ inline const char* rowconv_plan(RowPlan& plan, const RowWeights& w, const ConvPa
     }
   }
   const long long total_u = (long long)p.n_groups * (cp.H / 4);
+  // small batches stay on the tile kernels of umma_conv.cuh: a CTA here walks its rows one after the other (~1 us per row), so with fewer than ~16
+  // rows per SM the launch is latency bound (measured: B = 1 at 32 x 192, 250 us per forward against 190 us; B = 3: 210 against 76 us per plate)
+  const char* mu = getenv("LPSR_ROWCONV_MIN_UNITS");            // read per call: the tests force the kernel on small shapes with 0
+  const int min_units = mu ? atoi(mu) : 4;
+  if (total_u < (long long)min_units * num_sms) return "too little work for the row-streaming kernel";
   plan.grid = (int)std::min<long long>(num_sms, total_u);
   plan.threads = (kRowEpiWarp0 + 4 * p.NT) * 32;
   plan.smem_bytes = 1024 + (size_t)p.n_stages * p.stage_bytes + ((w.bytes + 127) & ~127u) + misc;

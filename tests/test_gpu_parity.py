@@ -131,6 +131,26 @@ CONV_SHAPES = [  # (ks, Cin, Cout, B, H, W, relu) -- every GEMM shape of SURVEY 
 ]
 
 
+@pytest.fixture
+def force_rowconv(monkeypatch):
+    """The row-streaming 3x3 kernel (csrc/rowconv.cuh) is only dispatched when a launch has >= 4 work units per SM; the library reads this
+    switch on every launch, so 0 sends every eligible shape (3x3, Cout 16 / 32, H % 4 == 0, W <= 255) of these small tests through it."""
+    monkeypatch.setenv("LPSR_ROWCONV_MIN_UNITS", "0")
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+@pytest.mark.parametrize("ks,cin,cout,B,H,W,relu", [s for s in CONV_SHAPES if s[0] == 3])
+def test_op_conv2d_row_streaming_kernel(models, force_rowconv, prec, ks, cin, cout, B, H, W, relu):
+    test_op_conv2d_matches_torch_cpu(models, prec, ks, cin, cout, B, H, W, relu)
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+@pytest.mark.parametrize("case", golden_cases())
+def test_half_modes_golden_row_streaming_kernel(case, prec, shipped_weights, models, force_rowconv):
+    """The golden cases again with the RDB dense layers, shallowF2, gff.1 (+ residual) and the final conv (+ sigmoid) on the row-streaming kernel."""
+    test_half_modes_match_reference_golden(case, prec, shipped_weights, models)
+
+
 @pytest.mark.parametrize("prec", ["fp32", "bf16", "fp16"])
 @pytest.mark.parametrize("ks,cin,cout,B,H,W,relu", CONV_SHAPES)
 def test_op_conv2d_matches_torch_cpu(models, prec, ks, cin, cout, B, H, W, relu):
@@ -226,9 +246,18 @@ def test_fp32_batch256_matches_torch_port(shipped_weights, models):
     assert float((y[idx] - ref).abs().max()) <= FP32_TOL
 
 
-def test_batch_composition_independence_full_size(models):
+@pytest.mark.parametrize("min_units", ["0", "1000000000", None])
+def test_batch_composition_independence_full_size(models, monkeypatch, min_units):
     """Size-independent property at BASELINE's full batch (1024): a crop's output does not depend on what else is in the
-    batch, so tiling a base set of 8 crops 128x must reproduce the B=8 result."""
+    batch, so tiling a base set of 8 crops 128x must reproduce the B=8 result -- bit for bit as long as both batch sizes run the same
+    kernels.  The 3x3 layers have two implementations (tile kernels of umma_conv.cuh for small launches, the row-streaming kernel of
+    rowconv.cuh from 4 work units per SM on), whose accumulation orders differ: LPSR_ROWCONV_MIN_UNITS pins one of them for every batch size
+    (0: always row-streaming, where a crop also changes its lane position inside its crop group between the two batches; huge: never);
+    with the default dispatch the two batch sizes agree to rounding."""
+    if min_units is None:
+        monkeypatch.delenv("LPSR_ROWCONV_MIN_UNITS", raising=False)
+    else:
+        monkeypatch.setenv("LPSR_ROWCONV_MIN_UNITS", min_units)
     base = torch.rand(8, 3, 64, 192, generator=torch.Generator().manual_seed(9)).to(DEV)
     for prec in ("fp16", "bf16", "fp32"):
         m = models[prec]
@@ -236,18 +265,27 @@ def test_batch_composition_independence_full_size(models):
         yb = m(base.repeat(128, 1, 1, 1))
         assert yb.shape == (1024, 1, 64, 192)
         d = (yb.view(128, 8, 1, 64, 192) - y8.unsqueeze(0)).abs().max()
-        assert float(d) == 0.0        # bit-identical: tiling, pooling slices and accumulation order do not depend on B
+        if min_units is None and prec != "fp32":
+            # two accumulation orders of the same 16-bit operands, amplified by the trained trunk like any other rounding: each of them is
+            # within the mode's tolerance of the reference (asserted above for fp16; bf16 is the documented wider mode)
+            assert float(d) <= (HALF_TOL if prec == "fp16" else 1e-1), (prec, float(d))
+        else:
+            assert float(d) == 0.0    # bit-identical: tiling, crop grouping, pooling slices and accumulation order do not depend on B
         assert torch.isfinite(yb).all() and float(yb.min()) > 0 and float(yb.max()) < 1   # sigmoid range
 
 
 @pytest.mark.parametrize("batch", [5, 130, 520])     # 1, 2 and 4 pipelined chunks inside lpsr_forward_host
-def test_forward_host_equals_forward(models, batch):
+def test_forward_host_equals_forward(models, batch, monkeypatch):
+    monkeypatch.setenv("LPSR_ROWCONV_MIN_UNITS", "0")   # one implementation of the 3x3 layers whatever the chunk size (see above)
     x = torch.rand(batch, 3, 32, 96, generator=torch.Generator().manual_seed(4))
     for prec in ("fp32", "fp16", "bf16"):
         m = models[prec]
         y_dev = m(x.to(DEV)).cpu()
         y_host = m.forward_host(x.pin_memory())
         assert torch.equal(y_dev, y_host)            # chunking must not change a single bit (crops are independent)
+    monkeypatch.delenv("LPSR_ROWCONV_MIN_UNITS")
+    m = models["fp16"]
+    assert float((m(x.to(DEV)).cpu() - m.forward_host(x.pin_memory())).abs().max()) <= HALF_TOL   # default dispatch: chunks may pick the other kernel
 
 
 def test_call_site_semantics(models):
