@@ -24,7 +24,7 @@ print(f"{'kernel':34s} {'us':>8s} {'readMB':>8s} {'writeMB':>8s} {'planes':>7s} 
 print("# tensor-pipe metric:", TP)
 for r in rows[2:]:
     name = r[idx['Kernel Name']]
-    m = re.search(r'umma_conv_kernel<(.*?)>', name) or re.search(r'(csar_tail_umma_kernel)', name)
+    m = re.search(r'umma_conv_kernel<(.*?)>', name) or re.search(r'(rowconv_kernel<.*?>)', name) or re.search(r'(csar_tail_umma_kernel)', name)
     short = m.group(1).replace('__nv_bfloat16', 'bf16').replace('(int)', '').replace('__half', 'f16') if m else name[:32]
     d, w, t = val(r, 'dram__bytes_read.sum'), val(r, 'dram__bytes_write.sum'), val(r, 'gpu__time_duration.sum')
     tot += t

@@ -1,5 +1,5 @@
 """Write profiles/r2_ncu_traffic.json from the raw-page CSV of an `ncu --set full` capture covering every tensor-core launch of
-ONE 16-bit forward in launch order (tools/ncu_forward.py, `-k regex:"umma|csar_tail" --launch-skip 25 --launch-count 25`).
+ONE 16-bit forward in launch order (tools/ncu_forward.py, `-k regex:"umma|csar_tail|rowconv" --launch-skip 25 --launch-count 25`).
 Usage: python tools/ncu_traffic.py raw.csv B H W"""
 import csv, json, os, sys
 raw, B, H, W = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
