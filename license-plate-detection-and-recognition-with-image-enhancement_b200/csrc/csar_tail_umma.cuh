@@ -18,7 +18,11 @@
 namespace lpsr {
 
 constexpr int kTailGroups = 6;   // tile slots in flight (4 x 128 TMEM columns); one tile's three-phase chain is latency bound
-constexpr int kTailMmaWarps = 2;   // MMA issuers (slots s % 2): one thread issuing 15 MMAs per tile at ~70 clk each was the bottleneck
+#ifndef LPSR_TAIL_MMA_WARPS
+#define LPSR_TAIL_MMA_WARPS 3
+#endif
+constexpr int kTailMmaWarps = LPSR_TAIL_MMA_WARPS;   // MMA issuers (slots s % kTailMmaWarps): one thread issuing 19 MMAs + 3 commits per tile was the bottleneck (tcgen05.mma blocks the issuing thread,
+                                                     // a commit costs it ~250-300 clk: 2 -> 3 issuers 610 -> 547 us per application at B = 1024, 6 issuers (66 registers, spills) 616)
 constexpr int kTailThreads = (4 * kTailGroups + kTailMmaWarps + 1) * 32;
 
 struct TailUmmaParams {

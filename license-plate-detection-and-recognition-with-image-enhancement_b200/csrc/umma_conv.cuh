@@ -638,7 +638,9 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
     [[maybe_unused]] const bool wlo2 = p.wlo_step == 2;
     const uint32_t tstride = (uint32_t)p.tstride;
     const bool no_mma = (p.debug & 1) != 0;
-    __syncwarp();
+    // The whole issue loop runs in ONE thread (no warp-wide control flow around an elected lane, no __syncwarp per tile): tcgen05.mma blocks the
+    // issuing thread while the pipe's short queue is full, so everything else this thread does per tile adds to its MMAs' time
+    if (leader) {
     uint32_t asel = 0;                                        // which of this warp's NACC accumulators the next tile uses
     uint32_t acc_bits = 3u;                                   // parities to wait for on their tmem_empty barriers (bit per accumulator)
     int turn = 0;
@@ -701,7 +703,6 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
           ptx::tc_commit(tfull_bar(acc));                     // this tile's accumulator is complete
           LPSR_TRACE(true, ii * k_tiles + m, 2, clock64());
         }
-        __syncwarp();
         if constexpr (LFF) {
           // second stage: the epilogue group has written g3 (K = 16) to shared memory; add lff's g3 slice to columns 48..79
           ptx::mbar_wait(a2full_bar(acc), a2_par);
@@ -714,14 +715,13 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
             }
             ptx::tc_commit(tfull2_bar(acc));
           }
-          __syncwarp();
         }
         acc_bits ^= 1u << asel;
         asel ^= (uint32_t)(NACC - 1);
       }
       if (leader) ptx::tc_commit(empty_bar(buf));             // this warp's MMAs on the item buffer have retired (count G)
-      __syncwarp();
       if (++buf == R) { buf = 0; buf_par ^= 1u; }
+    }
     }
   } else {
     // =================================== epilogue groups ============================================
