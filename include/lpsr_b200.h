@@ -152,6 +152,23 @@ int lpsr_op_conv2d(lpsr_handle* h, const float* x_nchw, const float* w_oihw, con
                    float* y_nchw, int32_t B, int32_t Cin, int32_t Cout, int32_t ksize,
                    int32_t H, int32_t W, int32_t relu, void* cuda_stream);
 
+
+/* -- detection post-processing around the path ---------------------------------- */
+/* replaces: `non_max_suppression(pred, conf_thres, iou_thres, classes, agnostic, multi_label, max_det=...)` of
+ * yolov5/utils/general.py:677-760 as called per plate by my_models/detection.py:44-54, for a whole batch of images in one launch.
+ *   pred_dev      : device fp32 [B,N,5+nc] (cx, cy, w, h, objectness, class scores) -- the YOLOv5 head's output; not modified
+ *   classes_host  : optional class filter (host int32[n_classes], NULL = none)
+ *   out_dev       : device fp32 [B,max_det,6] rows (x1, y1, x2, y2, conf, cls), image b's first out_count_dev[b] rows are valid,
+ *                   in the reference's order (descending confidence; equal confidences in candidate order)
+ *   out_count_dev : device int32 [B]; -1 = the image had more than max_candidates detections before NMS (nothing is truncated
+ *                   silently: call again with a larger max_candidates, a multiple of 64, at most 8192)
+ * Bit-identical to the reference on CPU (same float32 operations in the same order).  Asynchronous on `cuda_stream`. */
+size_t lpsr_op_yolo_nms_workspace_bytes(int32_t B, int32_t max_candidates, int32_t max_det, int32_t n_classes);
+int lpsr_op_yolo_nms(lpsr_handle* h, const float* pred_dev, int32_t B, int32_t N, int32_t nc, float conf_thres, float iou_thres,
+                     const int32_t* classes_host, int32_t n_classes, int32_t agnostic, int32_t multi_label, int32_t max_det,
+                     int32_t max_candidates, float* out_dev, int32_t* out_count_dev, void* workspace, size_t workspace_bytes,
+                     void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,6 +20,7 @@ EXPORTS = [
     "lpsr_live_tensor_numel", "lpsr_output_shape", "lpsr_workspace_bytes", "lpsr_forward", "lpsr_forward_profiled", "lpsr_forward_host",
     "lpsr_forward_launch_count", "lpsr_debug_read_tap", "lpsr_debug_umma_trace", "lpsr_last_error", "lpsr_abi_version", "lpsr_device_sm",
     "lpsr_op_pixel_unshuffle2", "lpsr_op_pixel_shuffle2", "lpsr_op_conv2d", "lpsr_preprocess_resize",
+    "lpsr_op_yolo_nms_workspace_bytes", "lpsr_op_yolo_nms",
 ]
 
 
@@ -76,6 +77,9 @@ def load_library() -> C.CDLL:
     lib.lpsr_op_pixel_unshuffle2.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     lib.lpsr_op_pixel_shuffle2.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     lib.lpsr_op_conv2d.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
+    lib.lpsr_op_yolo_nms_workspace_bytes.argtypes = [i32, i32, i32, i32]
+    lib.lpsr_op_yolo_nms_workspace_bytes.restype = C.c_size_t
+    lib.lpsr_op_yolo_nms.argtypes = [vp, vp, i32, i32, i32, C.c_float, C.c_float, vp, i32, i32, i32, i32, i32, vp, vp, vp, C.c_size_t, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int:   # default

@@ -16,6 +16,7 @@
 #include "cuda_core_kernels.cuh"
 #include "engine_internal.h"
 #include "preprocess.cuh"
+#include "nms.cuh"
 #include "umma_conv.cuh"
 
 using namespace lpsr;
@@ -910,6 +911,55 @@ int lpsr_debug_umma_trace(long long* dst_host) {
   long long* t = umma_trace_buffer();
   if (!t || !dst_host) return LPSR_ERR_INVALID_ARG;
   return cudaMemcpy(dst_host, t, 512 * 8 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? LPSR_OK : LPSR_ERR_CUDA;
+}
+
+size_t lpsr_op_yolo_nms_workspace_bytes(int32_t B, int32_t max_candidates, int32_t max_det, int32_t n_classes) {
+  if (B < 0 || max_candidates < 64 || max_candidates % 64 || max_candidates > kNmsMaxCap || max_det < 1 || n_classes < 0) return 0;
+  return nms_workspace_bytes(B, max_candidates, max_det, n_classes);
+}
+
+int lpsr_op_yolo_nms(lpsr_handle* h, const float* pred, int32_t B, int32_t N, int32_t nc, float conf_thres, float iou_thres,
+                     const int32_t* classes_host, int32_t n_classes, int32_t agnostic, int32_t multi_label, int32_t max_det,
+                     int32_t max_candidates, float* out, int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B < 0 || N < 0 || nc < 1 || max_det < 1 || n_classes < 0) return fail(h, LPSR_ERR_INVALID_ARG, "yolo_nms: bad shape");
+  if (!(conf_thres >= 0.f && conf_thres <= 1.f) || !(iou_thres >= 0.f && iou_thres <= 1.f))      // general.py:689-690
+    return fail(h, LPSR_ERR_INVALID_ARG, "yolo_nms: thresholds must be in [0, 1]");
+  if (max_candidates < 64 || max_candidates % 64 || max_candidates > kNmsMaxCap)
+    return fail(h, LPSR_ERR_INVALID_ARG, "yolo_nms: max_candidates must be a multiple of 64 in [64, %d]", kNmsMaxCap);
+  if (B == 0) return LPSR_OK;
+  if (!pred || !out || !out_count || !workspace || (n_classes && !classes_host)) return fail(h, LPSR_ERR_INVALID_ARG, "yolo_nms: null argument");
+  const size_t need = lpsr_op_yolo_nms_workspace_bytes(B, max_candidates, max_det, n_classes);
+  char* ws = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);
+  if (workspace_bytes < need) return fail(h, LPSR_ERR_INVALID_ARG, "yolo_nms: workspace of %zu bytes, %zu needed", workspace_bytes, need);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  NmsParams p{};
+  p.pred = pred; p.B = B; p.N = N; p.nc = nc;
+  p.conf_thres = conf_thres; p.iou_thres = iou_thres;
+  p.classes = nullptr; p.n_classes = n_classes;
+  if (n_classes) {
+    CUDA_TRY(h, cudaMemcpyAsync(ws, classes_host, (size_t)n_classes * 4, cudaMemcpyHostToDevice, st));
+    p.classes = reinterpret_cast<const int*>(ws);
+  }
+  ws += align_up((size_t)n_classes * 4, 256);
+  p.agnostic = agnostic ? 1 : 0; p.multi_label = multi_label ? 1 : 0; p.max_det = max_det;
+  p.cap = max_candidates;
+  const size_t cap = (size_t)max_candidates;
+  // per-image slices, array by array
+  p.det = reinterpret_cast<float*>(ws);                            ws += align_up((size_t)B * cap * 6 * 4, 256);
+  p.order = reinterpret_cast<int*>(ws);                            ws += align_up((size_t)B * cap * 4, 256);
+  p.keep = reinterpret_cast<int*>(ws);                             ws += align_up((size_t)B * max_det * 4, 256);
+  p.mask = reinterpret_cast<unsigned long long*>(ws);
+  p.out = out; p.out_count = out_count;
+  const size_t smem = cap * 5 * sizeof(float);
+  static bool configured[kMaxDevices] = {};
+  bool* flag = func_configured_flag(configured);
+  if (!flag || !*flag) {
+    CUDA_TRY(h, cudaFuncSetAttribute(yolo_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kNmsMaxCap * 5 * sizeof(float))));
+    if (flag) *flag = true;
+  }
+  yolo_nms_kernel<<<B, kNmsThreads, smem, st>>>(p);
+  CUDA_TRY(h, cudaGetLastError());
+  return LPSR_OK;
 }
 
 int lpsr_preprocess_resize(lpsr_handle* h, const uint8_t* crops, const int64_t* offsets, const int32_t* heights, const int32_t* widths,

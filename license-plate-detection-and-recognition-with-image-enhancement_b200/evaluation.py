@@ -12,8 +12,11 @@ Here:
   * ``sort_license_plate_detections`` mirrors my_utils/utils.py:7-72 (reading order of character boxes: rows by centre-y gaps, then left to right),
     ``detections_to_text`` the string assembly of eval.py:49-53;
   * ``super_resolve_batch`` is the SR path of eval.py:115-120 for ALL images at once (one pre-processing launch, one forward, one uint8 copy);
-  * ``evaluate`` produces the reference's report numbers.  The OCR model itself (YOLOv5 ``weights/char.pt`` + NMS) is NOT part
-    of this repository: the caller passes ``ocr(image_bgr) -> str`` (or ``-> detections``), e.g. a wrapper of the reference's ``Detection``.
+  * ``evaluate`` produces the reference's report numbers.  The OCR network itself (YOLOv5 ``weights/char.pt``) is NOT part
+    of this repository: the caller passes ``ocr(image_bgr) -> str`` (or ``-> detections``), e.g. a wrapper of the reference's ``Detection``;
+  * ``detections_from_predictions`` / ``texts_from_predictions`` are the half of row n4 that is: everything ``Detection.char_detection_yolo``
+    does AFTER the network (my_models/detection.py:44-71) -- ``non_max_suppression`` on the GPU for all plates at once
+    (``lpsr_b200.non_max_suppression``, bit-identical to yolov5/utils/general.py:677-760), the detection rows, the reading-order text.
 """
 from __future__ import annotations
 
@@ -24,7 +27,7 @@ from typing import Callable, Dict, List, Sequence, Tuple, Union
 import numpy as np
 import torch
 
-from .ops import preprocess_for_sr_batch
+from .ops import non_max_suppression, preprocess_for_sr_batch
 
 Detection = Tuple[str, float, Tuple[float, float, float, float]]     # (class name, confidence, (x1, y1, x2, y2)): Detection.detect's rows
 
@@ -84,6 +87,25 @@ def sort_license_plate_detections(detections: Sequence[Detection]) -> List[Detec
 def detections_to_text(detections: Sequence[Detection]) -> str:
     """eval.py:49-53: class names of the sorted detections, upper-cased and concatenated."""
     return "".join(str(d[0]).upper() for d in sort_license_plate_detections(detections))
+
+
+def detections_from_predictions(prediction: torch.Tensor, names: Sequence[str], conf_thres: float, iou_thres: float, classes=None,
+                                agnostic_nms: bool = True, max_det: int = 1000) -> List[List[Detection]]:
+    """``Detection.char_detection_yolo`` from the network output on (my_models/detection.py:44-71, ``bb_scale=False``) for a whole batch:
+    ``prediction`` = the YOLOv5 head's output ``model(img)[0]``, CUDA float32 [B, N, 5 + nc].  One NMS launch, one device-to-host copy;
+    rows are ``(names[int(cls)], conf, (x1, y1, x2, y2))`` in the reference's order (the reference keeps ``str(conf)``; the float is kept here)."""
+    dets = non_max_suppression(prediction, conf_thres=conf_thres, iou_thres=iou_thres, classes=classes, agnostic=agnostic_nms,
+                               multi_label=True, max_det=max_det)
+    out: List[List[Detection]] = []
+    for d in dets:
+        rows = d.cpu().tolist()
+        out.append([(names[int(r[5])], r[4], (r[0], r[1], r[2], r[3])) for r in rows])
+    return out
+
+
+def texts_from_predictions(prediction: torch.Tensor, names: Sequence[str], conf_thres: float, iou_thres: float, **kw) -> List[str]:
+    """Plate strings of a batch of OCR predictions: ``detections_from_predictions`` + the reading-order assembly of eval.py:49-53."""
+    return [detections_to_text(d) for d in detections_from_predictions(prediction, names, conf_thres, iou_thres, **kw)]
 
 
 def super_resolve_batch(model, images_bgr: Sequence[np.ndarray], target_size: Tuple[int, int] = (192, 32)) -> List[np.ndarray]:

@@ -1,6 +1,7 @@
 """Operator-level entry points of the C ABI (unit parity tests): device fp32 NCHW in / out, same kernels the forward uses."""
 from __future__ import annotations
 
+import numpy as np
 import torch
 
 from . import capi
@@ -96,3 +97,50 @@ def enhance_plates(model, plates, target_size=(192, 32)):
     # numpy's float32 * 255 followed by astype(uint8) truncates toward zero; the sigmoid output is in (0, 1) so no wrap-around
     u8 = (y * 255.0).to(torch.uint8).permute(0, 2, 3, 1).contiguous().cpu().numpy()
     return [u8[i] for i in range(u8.shape[0])]
+
+
+def non_max_suppression(prediction: torch.Tensor, conf_thres: float = 0.25, iou_thres: float = 0.45, classes=None, agnostic: bool = False,
+                        multi_label: bool = False, max_det: int = 300, max_candidates: int = 2048):
+    """The reference's ``non_max_suppression`` (yolov5/utils/general.py:677-760; call site my_models/detection.py:44-54) for a whole batch
+    of images in one CUDA launch: ``prediction`` is the YOLOv5 head's output, a CUDA float32 tensor [B, N, 5 + nc]; returns a list of B CUDA
+    tensors [n, 6] (x1, y1, x2, y2, conf, cls), bit-identical to the reference on CPU (same order of the kept boxes).  Same argument names
+    and checks as the reference; the input tensor is NOT modified (the reference zeroes the objectness of out-of-range boxes in place).
+    ``max_candidates`` bounds the detections per image BEFORE suppression the workspace holds (doubled automatically up to 8192)."""
+    if not (0 <= conf_thres <= 1):
+        raise ValueError(f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0")
+    if not (0 <= iou_thres <= 1):
+        raise ValueError(f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0")
+    if prediction.dim() != 3 or prediction.shape[2] < 6:
+        raise ValueError("prediction must be [B, N, 5 + nc]")
+    if not prediction.is_cuda or prediction.dtype != torch.float32:
+        raise ValueError("prediction must be a CUDA float32 tensor (there is no CPU path)")
+    B, N, row = prediction.shape
+    if B == 0:
+        return []
+    pred = prediction.contiguous()
+    lib = capi.load_library()
+    dev = pred.device
+    cls = np.ascontiguousarray(np.asarray(classes if classes is not None else [], dtype=np.int32))
+    cap = max(64, (int(max_candidates) + 63) // 64 * 64)
+    with torch.cuda.device(dev):
+        while True:
+            out = torch.empty(B, max_det, 6, dtype=torch.float32, device=dev)
+            cnt = torch.empty(B, dtype=torch.int32, device=dev)
+            nbytes = lib.lpsr_op_yolo_nms_workspace_bytes(B, cap, int(max_det), int(cls.size))
+            if nbytes == 0:
+                raise ValueError("bad max_candidates / max_det")
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            capi.check(lib.lpsr_op_yolo_nms(None, pred.data_ptr(), B, N, row - 5, float(conf_thres), float(iou_thres),
+                                            cls.ctypes.data if cls.size else None, int(cls.size), 1 if agnostic else 0, 1 if multi_label else 0,
+                                            int(max_det), cap, out.data_ptr(), cnt.data_ptr(), ws.data_ptr(), nbytes, _stream(pred)),
+                       None, "lpsr_op_yolo_nms")
+            counts = cnt.cpu().tolist()                        # the one synchronisation: the reference returns ragged tensors
+            if min(counts) >= 0:
+                break
+            if cap >= 8192:
+                raise RuntimeError(f"more than {cap} detections before suppression in one image: raise conf_thres (the reference cuts at 30000 "
+                                   "by an unstable argsort; this path reports instead of truncating)")
+            if cap >= (int(max_candidates) + 63) // 64 * 64 and int(max_candidates) < 2048:
+                raise RuntimeError(f"more than max_candidates = {max_candidates} detections before suppression in one image")
+            cap = min(8192, cap * 2)
+    return [out[b, :counts[b]] for b in range(B)]
