@@ -597,6 +597,8 @@ def run_ours(args):
     is_tail = lambda n_: ".tail:" in n_
     conv_ms = sum(t for n_, t in fam_ms.items() if is_conv(n_))
     conv_tags = {n_.split(":")[0] for n_ in names if is_conv(n_)}
+    if any(n_.endswith(":rowconv_chain") for n_ in names):
+        conv_tags.add("final_conv")      # gff.1 and the final conv are one launch (csrc/rowchain.cuh), tagged rdn.gff1
     # SURVEY 8(d) numerator: DENSE-conv FLOPs only (depthwise and linear arithmetic excluded); the AutoEncoder's pointwise 1x1s
     # are the dense part of its DConvs
     dense_mac = dict(UMMA_MAC_PER_PIXEL)

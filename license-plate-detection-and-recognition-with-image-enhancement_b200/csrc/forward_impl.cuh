@@ -8,6 +8,7 @@
 #include "engine_internal.h"
 #include "umma_conv.cuh"
 #include "rowconv.cuh"
+#include "rowchain.cuh"
 #include "csar_tail_umma.cuh"
 
 namespace lpsr {
@@ -429,12 +430,27 @@ int forward_impl(lpsr_handle* h, const float* x, float* y, int B, int H, int W, 
   }
   // gff.1 3x3 + global residual sfe1 (lpsr.py:211,224)
   c.tag = "rdn.gff1";
-  dense_conv<T>(c, h->gff1, conv_params(h->gff1, g0, 32, 0, 16, g, 32, 0, B, Hp, Wp, false, sfe1, 32, 0));
-  // ---- final conv + sigmoid, NCHW fp32 out (lpsr.py:273-274) -----------------------------------------------
-  c.tag = "final_conv";
   bool fin_done = false;
   if constexpr (sizeof(T) == 2) {
-    if (h->fin_u.packed) {   // tensor cores: Cout padded to 16, epilogue keeps channel 0 -> sigmoid -> fp32
+    // gff.1 -> final conv + sigmoid chained in ONE row-streaming kernel (rowchain.cuh): the 32-channel tensor between them stays in shared memory
+    if (h->gff1.rw.packed && h->fin_rw.packed) {
+      bool handled = false;
+      const char* msg = rowchain_launch<T>(h->gff1.rw, h->fin_rw, g0, 32, 0, sfe1, 32, 0, y, B, Hp, Wp, h->num_sms, c.st, &handled, /*dry=*/true);
+      if (handled && !msg) {
+        c.begin("rowconv_chain");
+        fin_done = true;
+        if (!c.dry && c.rc == LPSR_OK) {
+          msg = rowchain_launch<T>(h->gff1.rw, h->fin_rw, g0, 32, 0, sfe1, 32, 0, y, B, Hp, Wp, h->num_sms, c.st, &handled);
+          if (msg) c.rc = fail(h, LPSR_ERR_CUDA, "rowchain gff.1 + final launch: %s", msg);
+        }
+      }
+    }
+  }
+  if (!fin_done) dense_conv<T>(c, h->gff1, conv_params(h->gff1, g0, 32, 0, 16, g, 32, 0, B, Hp, Wp, false, sfe1, 32, 0));
+  // ---- final conv + sigmoid, NCHW fp32 out (lpsr.py:273-274) -----------------------------------------------
+  c.tag = "final_conv";
+  if constexpr (sizeof(T) == 2) {
+    if (h->fin_u.packed && !fin_done) {   // tensor cores: Cout padded to 16, epilogue keeps channel 0 -> sigmoid -> fp32
       ConvW fw;
       fw.ks = 3; fw.cin = 32; fw.cout = 16;
       const ConvParams fp = conv_params(fw, g, 32, 0, 16, y, 1, 0, B, Hp, Wp, false);

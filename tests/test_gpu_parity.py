@@ -151,6 +151,23 @@ def test_half_modes_golden_row_streaming_kernel(case, prec, shipped_weights, mod
     test_half_modes_match_reference_golden(case, prec, shipped_weights, models)
 
 
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+@pytest.mark.parametrize("B,H,W", [(5, 32, 192), (3, 64, 192), (2, 16, 40), (7, 8, 247)])
+def test_chained_gff1_final_is_bit_identical_to_separate_launches(models, monkeypatch, prec, B, H, W):
+    """csrc/rowchain.cuh (an opt-in experiment): gff.1 (+ residual) and the final conv (+ sigmoid) as one kernel, the tensor between them kept in shared memory in the
+    16-bit type the separate launch would have stored -- so the result must not differ in a single bit from the two row-streaming launches."""
+    monkeypatch.setenv("LPSR_ROWCONV_MIN_UNITS", "0")
+    monkeypatch.setenv("LPSR_ROWCHAIN", "1")              # off by default: measured slower than the two launches (rowchain.cuh)
+    x = torch.rand(B, 3, H, W, generator=torch.Generator().manual_seed(B * 100 + W)).to(DEV)
+    m = models[prec]
+    n_chain = m.launch_count(B, H, W)
+    y_chain = m(x).clone()
+    monkeypatch.setenv("LPSR_ROWCHAIN", "0")
+    assert m.launch_count(B, H, W) == n_chain + 1
+    y_sep = m(x)
+    assert torch.equal(y_chain, y_sep)
+
+
 @pytest.mark.parametrize("prec", ["fp32", "bf16", "fp16"])
 @pytest.mark.parametrize("ks,cin,cout,B,H,W,relu", CONV_SHAPES)
 def test_op_conv2d_matches_torch_cpu(models, prec, ks, cin, cout, B, H, W, relu):
