@@ -207,7 +207,8 @@ __global__ void __launch_bounds__(rowconv_max_threads(COUT), 1) rowconv_kernel(c
       const int n_sub = p.n_sub;
       const int ring = (NS / n_sub) * n_sub;
       const bool no_mma = (p.debug & 1) != 0;
-      constexpr uint32_t idesc1 = umma_idesc_f16(kBf16, COUT), idesc2 = umma_idesc_f16(kBf16, 2 * COUT), idesc4 = umma_idesc_f16(kBf16, 4 * COUT);
+      constexpr uint32_t idesc1 = umma_idesc_f16(kBf16, COUT), idesc2 = umma_idesc_f16(kBf16, 2 * COUT), idesc3 = umma_idesc_f16(kBf16, 3 * COUT),
+                         idesc4 = umma_idesc_f16(kBf16, 4 * COUT);
       const uint32_t trow = (uint32_t)(kRowLead + 128 * t - 1);
       const uint32_t dtile = tmem_base + (uint32_t)(t * 4 * COUT);
       int entry = 0;
@@ -223,8 +224,10 @@ __global__ void __launch_bounds__(rowconv_max_threads(COUT), 1) rowconv_kernel(c
         for (int yin = ylo; yin <= yhi; ++yin, ++sidx) {
           // output rows of this band the input row contributes to
           const int ra = max(yin - 1, ya), rb = min(yin + 1, yb - 1), nr = rb - ra + 1;
-          const bool full = (nr == 3);
-          const uint32_t idesc = full ? idesc4 : (nr == 2 ? idesc2 : idesc1);
+          // three rows whose slots do not wrap around the ring (slot(ra) <= 1) take an N = 3 * Cout window like the partial ones: the fourth slot is
+          // not touched, so its previous row may still be draining (one more row of slack), and N = 96 costs 56 instead of 64 clk
+          const bool full = (ra & 3) + nr > 4;                  // only a three-row window can wrap (band ends sit on multiples of 4)
+          const uint32_t idesc = full ? idesc4 : (nr == 3 ? idesc3 : (nr == 2 ? idesc2 : idesc1));
           const uint32_t d = dtile + (full ? 0u : (uint32_t)((ra & 3) * COUT));
           // first weight block of the window: full ring -> slot 0 gets the block of ((0 - slot(yin-1)) mod 4); partial -> the block of row ra
           const uint32_t blk = full ? (uint32_t)((4 - ((yin - 1) & 3)) & 3) : (uint32_t)(1 - yin + ra);
