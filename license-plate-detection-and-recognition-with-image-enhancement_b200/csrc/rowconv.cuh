@@ -7,11 +7,12 @@
 //     P8 = W + >= 1 zero columns, a multiple of 8).  The lane <-> pixel map is the same for every row of a crop group, so output row r of
 //     tile t always lives in the same TMEM lanes.
 //   * One input row y is staged by TMA ([ch][P8 px][1 row][G crops] box per K-chunk; the zero columns between crops and beyond the
-//     image are the TMA's out-of-bounds fill) and consumed ONCE: for every K-slice and dx tap one MMA with N = 4 * Cout whose weight
-//     blocks [ky=2 | ky=1 | ky=0 | zero] add the row's contributions to output rows y-1, y, y+1 (and nothing to the fourth slot).  The
-//     accumulators of a tile form a ring of 4 slots of Cout columns (slot = output row % 4); the rotation of the weight blocks against the
-//     slots is a different START ADDRESS into a 7-block copy [ky2 ky1 ky0 0 ky2 ky1 ky0] of the weights, so no MMA is ever split at the
-//     ring's wrap-around.  dx is a row shift of the A descriptor's start address (same trick as umma_conv.cuh).
+//     image are the TMA's out-of-bounds fill) and consumed ONCE: for every K-slice and dx tap one MMA whose weight blocks
+//     [ky=2 | ky=1 | ky=0] add the row's contributions to output rows y-1, y, y+1.  The accumulators of a tile form a ring of 4 slots of
+//     Cout columns (slot = output row % 4).  Where the three slots are adjacent the MMA has N = 3 * Cout; where they wrap around the ring it
+//     has N = 4 * Cout with a zero block for the fourth slot, and the rotation of the blocks against the slots is a different START ADDRESS
+//     into a 7-block copy [ky2 ky1 ky0 0 ky2 ky1 ky0] of the weights -- no MMA is ever split at the wrap-around (an N = 64 MMA costs the
+//     same 48 clk as N = 48).  dx is a row shift of the A descriptor's start address (same trick as umma_conv.cuh).
 //   * 3 * Cin/16 MMAs per tile and row instead of 9 * Cin/16 (Cout = 32) -- and, for Cout = 16, the same 3 * Cin/16 as the dx fold but with
 //     an epilogue of ~40 instead of ~286 instructions: after input row y + 1 the slot of output row y is complete; an epilogue warp loads
 //     it, RESETS it to the bias vector (tcgen05.st: the next occupant starts at its bias, no add in the epilogue) and hands it back.
