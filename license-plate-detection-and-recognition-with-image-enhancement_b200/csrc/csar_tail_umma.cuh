@@ -215,7 +215,6 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
     uint8_t* a2 = slot + 2 * kA1;
     uint8_t* a3 = a2;                                            // s_full (MMA2 complete) precedes the first write of the gated map
     const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(g * 64);
-    const T* xin = static_cast<const T*>(p.x_in);
     T* out = static_cast<T*>(p.out);
     uint32_t par = 0;
     for (int t = g; t < n_my; t += G, par ^= 1u) {

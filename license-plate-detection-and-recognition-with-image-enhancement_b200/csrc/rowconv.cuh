@@ -262,6 +262,7 @@ __global__ void __launch_bounds__(rowconv_max_threads(COUT), 1) rowconv_kernel(c
         g0 += yb - ya;
         u += ub - ua;
       }
+#undef ROW_TRACE
     }
   } else if (warp >= kRowEpiWarp0 && et < NT) {
     // =================================== epilogue warps ==============================================

@@ -1109,10 +1109,10 @@ __global__ void __launch_bounds__(umma_threads(CS), 1) umma_conv_kernel(const __
             }
           } else if constexpr (EPI == kEpiUp2Store) {
             static_assert(EPI != kEpiUp2Store || NOUT == 128 || NOUT == 64, "four pixels of 32 or 16 channels per row");
-            constexpr int CS = NOUT / 4;                          // channels per sub-pixel
-            const int up = valid ? ((nn * 2 * Himg + 2 * yy + cc / (2 * CS)) * 2 * Wimg + 2 * xx + (cc / CS) % 2) : -1;
-            if (p.relu) store_chunk16<TOUT, true>(reinterpret_cast<TOUT*>(out), out_pitch, out_off + cc % CS, up, v);
-            else store_chunk16<TOUT>(reinterpret_cast<TOUT*>(out), out_pitch, out_off + cc % CS, up, v);
+            constexpr int CSUB = NOUT / 4;                        // channels per sub-pixel
+            const int up = valid ? ((nn * 2 * Himg + 2 * yy + cc / (2 * CSUB)) * 2 * Wimg + 2 * xx + (cc / CSUB) % 2) : -1;
+            if (p.relu) store_chunk16<TOUT, true>(reinterpret_cast<TOUT*>(out), out_pitch, out_off + cc % CSUB, up, v);
+            else store_chunk16<TOUT>(reinterpret_cast<TOUT*>(out), out_pitch, out_off + cc % CSUB, up, v);
           } else if constexpr (EPI == kEpiGate) {
             // CSAR gates (1x1, NOUT = 32): spatial branch x_in * sigmoid(.), channel branch x_in^2 * s_c
             float g1[CH];
