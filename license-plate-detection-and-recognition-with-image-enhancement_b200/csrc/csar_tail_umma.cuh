@@ -9,8 +9,8 @@
 //     -> smem A3 -> MMA3 -> TMEM -> epilogue (+bias, +x) -> coalesced store.
 // HBM traffic is the algorithmic 96 elements/pixel (read x_in, read x, write out) plus a second (L2-hot) read of x_in for
 // the gates; the three-launch version it replaces moves 352 elements/pixel.
-// Warp roles: G groups x 4 epilogue warps (group g owns tile slot g: its smem operands and 128 TMEM columns), one MMA warp,
-// one TMA producer warp.  The MMA warp walks the G slots phase by phase (MMA1 for all slots, MMA2, MMA3), so while one
+// Warp roles: G groups x 4 epilogue warps (group g owns tile slot g: its smem operands and 64 TMEM columns), kTailMmaWarps issuing
+// threads (slots s % kTailMmaWarps), one TMA producer thread.  The MMA warp walks the G slots phase by phase (MMA1 for all slots, MMA2, MMA3), so while one
 // group is in an epilogue phase the tensor core works for the others.
 #pragma once
 #include "umma_conv.cuh"
@@ -62,10 +62,14 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
   uint8_t* bo_s = b4_s + kB4;
   uint8_t* id_s = bo_s + kB4;                                  // [4][32][8]: identity
   uint64_t* bars = reinterpret_cast<uint64_t*>(id_s + kIdent);
-  // per slot: 0 a1_full, 1 h_full, 2 a2_ready, 3 s_full, 4 a3_ready, 5 o_full, 6 slot_free
+  // per slot: 0 a1_full (x_in tile landed), 1 h_full, 2 a2_ready, 3 s_full, 4 a3_ready, 5 o_full, 6 slot_free (accumulators read: TMEM and the
+  // planar operand may be reused), 7 xin_free (the gates have read the x_in tile), 8 res_full (residual tile landed), 9 res_free (conv_out's MMAs,
+  // the last readers of the residual tile, have retired).  The two input tiles are reloaded as soon as THEY are free -- x_in while the tile's third
+  // GEMM still runs -- instead of after the whole tile: the TMA latency (~1.5 k clk) leaves the tile's dependent chain.
+  constexpr int kBars = 10;
   const uint32_t bar0 = ptx::smem_u32(bars);
-  auto bar = [&](int slot, int which) { return bar0 + 8u * (uint32_t)(slot * 7 + which); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7 * G);
+  auto bar = [&](int slot, int which) { return bar0 + 8u * (uint32_t)(slot * kBars + which); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kBars * G);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (uint32_t i = threadIdx.x; i < kW3 / 16; i += kTailThreads) reinterpret_cast<uint4*>(w3_s)[i] = __ldg(reinterpret_cast<const uint4*>(p.w3) + i);
@@ -112,6 +116,9 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
       ptx::mbar_init(bar(s, 4), 4);   // one arrival per epilogue warp
       ptx::mbar_init(bar(s, 5), 1);
       ptx::mbar_init(bar(s, 6), 4);   // one arrival per epilogue warp
+      ptx::mbar_init(bar(s, 7), 4);   // one arrival per epilogue warp
+      ptx::mbar_init(bar(s, 8), 1);
+      ptx::mbar_init(bar(s, 9), 1);   // epilogue warp 0 of the group, once it has seen o_full
     }
     ptx::fence_mbar_init();
   }
@@ -132,13 +139,33 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
     if (ptx::elect_one()) {
       ptx::prefetch_tmap(&tm.m);
       ptx::prefetch_tmap(&tm.r);
-      for (int t = 0; t < n_my; ++t) {
-        const int s = t % G;
-        ptx::mbar_wait(bar(s, 6), (((uint32_t)(t / G)) & 1u) ^ 1u);        // slot free
-        ptx::mbar_arrive_expect_tx(bar(s, 0), 2 * kA1);
-        const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
-        ptx::tma_load_2d(ptx::smem_u32(slots + (size_t)s * kSlot), &tm.m, bar(s, 0), 0, (int)(tile * 128));
-        ptx::tma_load_2d(ptx::smem_u32(slots + (size_t)s * kSlot + kA1), &tm.r, bar(s, 0), p.res_off, (int)(tile * 128));
+      // two independent sequences (x_in tiles, residual tiles), each in tile order, polled so that neither blocks the other
+      int tx = 0, tr = 0;
+      uint32_t idle = 0;
+      while (tx < n_my || tr < n_my) {
+        bool progressed = false;
+        if (tx < n_my) {
+          const int s = tx % G;
+          if (ptx::mbar_test_wait(bar(s, 7), (((uint32_t)(tx / G)) & 1u) ^ 1u)) {        // the previous tile's gates have read the x_in tile
+            ptx::mbar_arrive_expect_tx(bar(s, 0), kA1);
+            const long long tile = (long long)blockIdx.x + (long long)tx * gridDim.x;
+            ptx::tma_load_2d(ptx::smem_u32(slots + (size_t)s * kSlot), &tm.m, bar(s, 0), 0, (int)(tile * 128));
+            ++tx;
+            progressed = true;
+          }
+        }
+        if (tr < n_my) {
+          const int s = tr % G;
+          if (ptx::mbar_test_wait(bar(s, 9), (((uint32_t)(tr / G)) & 1u) ^ 1u)) {        // the previous tile's conv_out MMAs have retired
+            ptx::mbar_arrive_expect_tx(bar(s, 8), kA1);
+            const long long tile = (long long)blockIdx.x + (long long)tr * gridDim.x;
+            ptx::tma_load_2d(ptx::smem_u32(slots + (size_t)s * kSlot + kA1), &tm.r, bar(s, 8), p.res_off, (int)(tile * 128));
+            ++tr;
+            progressed = true;
+          }
+        }
+        if (progressed) idle = 0;
+        else if (++idle > (1u << 27)) __trap();
       }
     }
   } else if (warp >= 4 * G) {
@@ -172,6 +199,8 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
           if (s % kTailMmaWarps != mw || tile_s[s] >= n_my) continue;
           const int phase = phase_s[s];
           if (!ptx::mbar_test_wait(bar(s, phase * 2), par_s[s])) continue;   // a1_full / a2_ready / a3_ready
+          if (phase == 0 && !ptx::mbar_test_wait(bar(s, 6), par_s[s] ^ 1u)) continue;   // the slot's previous tile has been read out of TMEM
+          if (phase == 2 && !ptx::mbar_test_wait(bar(s, 8), par_s[s])) continue;        // residual tile landed
           ptx::tc_fence_after();
           const uint32_t slot16 = ptx::smem_u32(slots + (size_t)s * kSlot) >> 4;
           const uint32_t d = tmem_base + (uint32_t)(s * 64);     // 64 columns per slot: H, then S in [0,32) and O in [32,64)
@@ -255,6 +284,8 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
       uint4 xraw[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) xraw[j] = *reinterpret_cast<const uint4*>(slot + row * 64 + ((j ^ ((row >> 1) & 3)) << 4));
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar(g, 7));                         // x_in tile read (its MMAs retired before h_full): the producer may reload it
 #pragma unroll
       for (int c0 = 0; c0 < 32; c0 += 16) {
         float v[16], ga[16];
@@ -293,6 +324,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) csar_tail_umma_kernel(const _
       // ---- phase 3: out = acc (bias and residual already accumulated by the tensor core)
       ptx::mbar_wait(bar(g, 5), par);
       ptx::tc_fence_after();
+      if (wq == 0 && lane == 0) ptx::mbar_arrive(bar(g, 9));              // conv_out's MMAs (the residual tile's last readers) have retired
       const int pix32 = valid ? (int)pix : -1;
       ptx::tc_ld16_nowait(taddr + 32, blk);
       ptx::tc_ld16_nowait(taddr + 48, blk + 16);
@@ -325,7 +357,7 @@ inline const char* csar_tail_umma_launch(const TailUmmaParams& pin, bool fp16, i
   if (const char* msg = umma_make_tmap(&tm.r, p.res, fp16, p.res_pitch, 32, false, 0, 0, 0, 128, 0, p.total_px)) return msg;
   constexpr size_t kSlot = 2 * 128 * 64 + 128 * 128;
   const size_t smem = 1024 + kTailGroups * kSlot + 32 * 64 * 2 + 3 * 64 * 32 * 2 + (2 * 128 + 2 * 64 + 2 * 32 + 2 * 32 + 4 * 32) * 16 +
-                      (7 * kTailGroups + 2) * 8 + 64;
+                      (10 * kTailGroups + 2) * 8 + 64;
   static bool configured[kMaxDevices] = {};
   bool* flag = func_configured_flag(configured);
   if (!flag || !*flag) {
