@@ -117,6 +117,8 @@ def non_max_suppression(prediction: torch.Tensor, conf_thres: float = 0.25, iou_
     B, N, row = prediction.shape
     if B == 0:
         return []
+    if N == 0:
+        return [prediction.new_zeros((0, 6)) for _ in range(B)]
     pred = prediction.contiguous()
     lib = capi.load_library()
     dev = pred.device

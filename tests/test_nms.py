@@ -110,6 +110,7 @@ def test_gpu_nms_rejects_bad_arguments_and_overflow():
     with pytest.raises(RuntimeError):                     # 600 x 4 candidates > capacity 1024: reported, never truncated silently
         lpsr_b200.non_max_suppression(many, conf_thres=0.1, multi_label=True, max_candidates=1024)
     assert lpsr_b200.non_max_suppression(torch.zeros(0, 10, 9, device="cuda")) == []
+    assert [tuple(t.shape) for t in lpsr_b200.non_max_suppression(torch.zeros(2, 0, 9, device="cuda"))] == [(0, 6), (0, 6)]
 
 
 @pytest.mark.gpu
