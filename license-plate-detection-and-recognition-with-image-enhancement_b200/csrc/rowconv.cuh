@@ -42,6 +42,7 @@ struct RowParams {
   uint32_t stage_bytes;                   // bytes of one ring entry
   int n_stages;                           // ring entries
   int G, P8, NT;                          // crops per group, lane pitch per crop, 128-lane tiles per row
+  int n_xbox, box_px;                     // a crop row wider than one TMA box (256 pixels) is staged as n_xbox boxes of box_px pixels (then G = 1)
   const uint16_t* w; uint32_t w_bytes; const float* bias;
   void* out; int out_pitch, out_off;
   const void* res; int res_pitch, res_off;
@@ -186,7 +187,9 @@ __global__ void __launch_bounds__(rowconv_max_threads(COUT), 1) rowconv_kernel(c
               ptx::mbar_arrive_expect_tx(bar, p.sub_tx[sb]);
               const uint32_t dst0 = ptx::smem_u32(a_smem + (size_t)entry * p.stage_bytes);
               for (int c = p.sub_c0[sb]; c < p.sub_c0[sb + 1]; ++c)
-                ptx::tma_load_4d(dst0 + p.chunk_smem[c] + (uint32_t)(kRowLead * p.chunk_ch[c] * 2), &tm.m[c], bar, p.chunk_coff[c], 0, yin, grp * p.G);
+                for (int xb = 0; xb < p.n_xbox; ++xb)
+                  ptx::tma_load_4d(dst0 + p.chunk_smem[c] + (uint32_t)((kRowLead + xb * p.box_px) * p.chunk_ch[c] * 2), &tm.m[c], bar, p.chunk_coff[c],
+                                   xb * p.box_px, yin, grp * p.G);
             }
             ++entry;
           }
@@ -366,8 +369,9 @@ inline const char* rowconv_plan(RowPlan& plan, const RowWeights& w, const ConvPa
   memset(&plan.tm, 0, sizeof plan.tm);
   if (!w.packed) return "weights not packed";
   if (cp.H % 4 || cp.H < 4) return "image height not a multiple of 4";
-  const int P8 = (cp.W + 1 + 7) / 8 * 8;
-  if (P8 > 256) return "image wider than one TMA box";
+  const int n_xbox = (cp.W + 1 + 255) / 256;                    // TMA boxes per crop row (a box dimension is at most 256)
+  const int P8 = (cp.W + 1 + 8 * n_xbox - 1) / (8 * n_xbox) * (8 * n_xbox);
+  if (n_xbox > 2) return "image wider than two TMA boxes";      // W <= 503: one crop per group then (128 x 384: 4 tiles, 75 % of the lanes)
   if (cp.n_chunks != w.cin / 16) return "chunk table does not match Cin/16";
   if (!fp32_out && (cp.out_pitch % 16 || cp.out_off % 16 || reinterpret_cast<uintptr_t>(cp.out) % 32)) return "output not 32-byte aligned";
   if (cp.res && (cp.res_pitch % 8 || cp.res_off % 8 || reinterpret_cast<uintptr_t>(cp.res) % 16)) return "residual not 16-byte aligned";
@@ -436,7 +440,7 @@ inline const char* rowconv_plan(RowPlan& plan, const RowWeights& w, const ConvPa
   const size_t min_entries = (size_t)std::max(2, p.n_sub);
   double best_util = 0.0;
   int bestG = 0;
-  for (int G = 1; G <= 8 && G <= std::max(1, cp.B); ++G) {
+  for (int G = 1; G <= (n_xbox > 1 ? 1 : 8) && G <= std::max(1, cp.B); ++G) {
     const int lanes = G * P8, NT = (lanes + 127) / 128;
     if (NT > nt_max) break;
     const int rows = (std::max(kRowLead + NT * 128 + 1, kRowLead + lanes) + 7) / 8 * 8;
@@ -446,6 +450,7 @@ inline const char* rowconv_plan(RowPlan& plan, const RowWeights& w, const ConvPa
   }
   if (!bestG) return "no crop grouping fits shared memory";
   p.G = bestG; p.P8 = P8;
+  p.n_xbox = n_xbox; p.box_px = P8 / n_xbox;
   p.NT = (bestG * P8 + 127) / 128;
   const int rows = (std::max(kRowLead + p.NT * 128 + 1, kRowLead + bestG * P8) + 7) / 8 * 8;
   for (int sb = 0; sb < p.n_sub; ++sb) {
@@ -496,7 +501,7 @@ inline const char* rowconv_plan(RowPlan& plan, const RowWeights& w, const ConvPa
     const CUtensorMapSwizzle sw = ch == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : ch == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
     const cuuint64_t gdim[4] = {(cuuint64_t)pitch, (cuuint64_t)cp.W, (cuuint64_t)cp.H, (cuuint64_t)cp.B};
     const cuuint64_t gstr[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)cp.W * pitch * 2, (cuuint64_t)cp.H * cp.W * pitch * 2};
-    const cuuint32_t box[4] = {(cuuint32_t)ch, (cuuint32_t)P8, 1, (cuuint32_t)bestG};
+    const cuuint32_t box[4] = {(cuuint32_t)ch, (cuuint32_t)(P8 / n_xbox), 1, (cuuint32_t)bestG};
     const cuuint32_t es[4] = {1, 1, 1, 1};
     const CUresult r = enc(&plan.tm.m[c], fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(chunk_base[c]),
                            gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

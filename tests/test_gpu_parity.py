@@ -127,7 +127,8 @@ CONV_SHAPES = [  # (ks, Cin, Cout, B, H, W, relu) -- every GEMM shape of SURVEY 
     (1, 96, 32, 2, 32, 192, False), (1, 128, 32, 1, 64, 192, False), (1, 32, 64, 1, 24, 40, True), (1, 64, 32, 5, 4, 4, False),
     # row-streaming kernel (rowconv.cuh): crop groups with a partial last group, work ranges cut inside a crop, narrow and 255-wide rows
     (3, 32, 16, 7, 64, 192, True), (3, 80, 16, 5, 64, 192, True), (3, 32, 32, 7, 64, 192, False), (3, 48, 16, 40, 8, 24, True),
-    (3, 32, 16, 2, 12, 255, True), (3, 64, 16, 160, 4, 4, True),
+    (3, 32, 16, 2, 12, 255, True), (3, 64, 16, 160, 4, 4, True), (3, 48, 16, 2, 16, 384, True), (3, 32, 32, 1, 8, 500, False),
+    (3, 80, 16, 1, 8, 503, True),      # rows wider than one TMA box: two boxes per crop row
 ]
 
 
